@@ -1,0 +1,87 @@
+"""Readers/writers for the two flat binary formats exchanged with the reference harness
+(oracle/ref/ref_harness.cpp): positions ("LB2POS01") and evaluation outputs ("LB2OUT01").
+
+Positions carry, per board position, the 32 policy planes and the 32 value planes of
+Network::gather_features_policy / _value (Network.cpp:883-1201) packed one uint32 per board
+point (idx = y*19 + x, bit c = plane c), plus the symmetry (0..7) to evaluate it under.
+"""
+from __future__ import annotations
+
+import dataclasses
+import numpy as np
+
+P = 361
+
+
+@dataclasses.dataclass
+class Positions:
+    policy_planes: np.ndarray  # uint32 [n, 361]
+    value_planes: np.ndarray   # uint32 [n, 361]
+    rotation: np.ndarray       # uint8  [n]
+    to_move: np.ndarray        # int32  [n]
+    movenum: np.ndarray        # int32  [n]
+
+    @property
+    def n(self) -> int:
+        return int(self.policy_planes.shape[0])
+
+    def take(self, idx) -> "Positions":
+        return Positions(*(getattr(self, f.name)[idx] for f in dataclasses.fields(self)))
+
+
+@dataclasses.dataclass
+class RefOutputs:
+    softmax_temp: float
+    policy: np.ndarray      # float32 [n, 361], un-rotated, all 361 points
+    value: np.ndarray       # float32 [n]
+    policy_avg: np.ndarray  # float32 [n_avg, 361]; AVERAGE_ALL via the API, -1 where not EMPTY
+    value_avg: np.ndarray   # float32 [n_avg]
+
+
+def read_positions(path) -> Positions:
+    raw = np.fromfile(path, dtype=np.uint8)
+    if raw[:8].tobytes() != b"LB2POS01":
+        raise ValueError(f"{path}: not a positions file")
+    n = int(raw[8:12].view(np.int32)[0])
+    off = 16
+    def take(count, dtype):
+        nonlocal off
+        nbytes = count * np.dtype(dtype).itemsize
+        a = raw[off:off + nbytes].view(dtype).copy()
+        off += nbytes
+        return a
+    pol = take(n * P, np.uint32).reshape(n, P)
+    val = take(n * P, np.uint32).reshape(n, P)
+    rot = take((n + 3) // 4 * 4, np.uint8)[:n]
+    tm = take(n, np.int32)
+    mv = take(n, np.int32)
+    return Positions(pol, val, rot, tm, mv)
+
+
+def write_positions(path, ps: Positions) -> None:
+    n = ps.n
+    with open(path, "wb") as f:
+        f.write(b"LB2POS01")
+        f.write(np.array([n, 0], dtype=np.int32).tobytes())
+        f.write(np.ascontiguousarray(ps.policy_planes, dtype=np.uint32).tobytes())
+        f.write(np.ascontiguousarray(ps.value_planes, dtype=np.uint32).tobytes())
+        rot = np.zeros((n + 3) // 4 * 4, dtype=np.uint8)
+        rot[:n] = ps.rotation
+        f.write(rot.tobytes())
+        f.write(np.ascontiguousarray(ps.to_move, dtype=np.int32).tobytes())
+        f.write(np.ascontiguousarray(ps.movenum, dtype=np.int32).tobytes())
+
+
+def read_outputs(path) -> RefOutputs:
+    raw = np.fromfile(path, dtype=np.uint8)
+    if raw[:8].tobytes() != b"LB2OUT01":
+        raise ValueError(f"{path}: not an outputs file")
+    n, n_avg = (int(v) for v in raw[8:16].view(np.int32))
+    temp = float(raw[16:20].view(np.float32)[0])
+    body = raw[20:].view(np.float32)
+    o = 0
+    pol = body[o:o + n * P].reshape(n, P).copy(); o += n * P
+    val = body[o:o + n].copy(); o += n
+    pavg = body[o:o + n_avg * P].reshape(n_avg, P).copy(); o += n_avg * P
+    vavg = body[o:o + n_avg].copy()
+    return RefOutputs(temp, pol, val, pavg, vavg)
