@@ -1,0 +1,134 @@
+/* leela_b200.h — C ABI of the B200 (sm_100a) evaluator for Leela's policy and value networks.
+ *
+ * This is the drop-in boundary for ONE hot path of gcp/Leela: the convolutional policy+value
+ * network evaluation behind Network.cpp. It replaces the reference's two backends
+ *   - OpenCL:  OpenCL.h:47-134 (OpenCL_Network::push_convolve / push_innerproduct / forward,
+ *              OpenCL::initialize / join_outstanding_cb), kernels OpenCL.cpp:25-438
+ *   - CPU:     Im2Col.h:8-50 + cblas_sgemm/sgemv templates, Network.cpp:344-447
+ * and is what Network::get_scored_moves / get_value / async_scored_moves (Network.h:43-61)
+ * call instead. Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ *
+ * Conventions
+ *   - Every function returns LB2_OK (0) or a negative lb2_status; nothing throws.
+ *     lb2_last_error() gives the text of the calling thread's most recent failure.
+ *   - Board is 19x19. A position's input is 32 binary feature planes packed one uint32 per
+ *     board point: planes[i*361 + idx], idx = y*19 + x, bit c = plane c, in the order of
+ *     Network::gather_features_policy (Network.cpp:886-917) or gather_features_value
+ *     (Network.cpp:1050-1081). (std::bitset<361> x 32 -> uint32[361].)
+ *   - rotation[i] in 0..7 is the symmetry of Network::rotate_nn_idx (Network.cpp:1348-1379)
+ *     the position is evaluated under; outputs come back un-rotated (rev_rotate_nn_idx,
+ *     Network.cpp:820-823), i.e. indexed by the ORIGINAL board idx.
+ *   - Policy output is the temperature softmax over all 361 points (Network::softmax,
+ *     Network.cpp:450-469). Filtering to EMPTY points, vertex mapping and losing-ladder
+ *     pruning (Network.cpp:820-829, 656-667) need the board and stay with the caller.
+ *   - Value output is (1 + tanh(x)) / 2 for the side to move (Network.cpp:736).
+ *   - Host pointers are caller-owned and may be pageable; pinned staging is internal.
+ *   - There is no CPU fallback: without a B200 and the compiled kernels, lb2_init fails.
+ */
+#ifndef LEELA_B200_H
+#define LEELA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LB2_BOARD_POINTS 361
+#define LB2_INPUT_PLANES 32
+
+typedef enum lb2_status {
+    LB2_OK = 0,
+    LB2_ERR_INVALID = -1,     /* bad argument: n < 0, rotation > 7, null pointer, bad geometry */
+    LB2_ERR_CUDA = -2,        /* a CUDA call failed (message in lb2_last_error) */
+    LB2_ERR_STATE = -3,       /* net not finalized / already finalized / wrong net kind */
+    LB2_ERR_NOMEM = -4,
+    LB2_ERR_UNSUPPORTED = -5  /* layer stack this evaluator has no kernel for */
+} lb2_status;
+
+typedef enum lb2_net_kind { LB2_POLICY = 0, LB2_VALUE = 1 } lb2_net_kind;
+
+typedef struct lb2_ctx lb2_ctx;
+typedef struct lb2_net lb2_net;
+
+/* Replaces OpenCL::initialize (OpenCL.cpp:764-908). device_ids == NULL or n_devices == 0
+ * selects CUDA device 0. With several devices, weights are replicated on each and every
+ * eval call shards its positions over them in contiguous slices (no collective). */
+int lb2_init(const int* device_ids, int n_devices, lb2_ctx** ctx_out);
+void lb2_destroy(lb2_ctx* ctx);
+
+/* Replaces the globals opencl_policy_net / opencl_value_net (OpenCL.h:137-138): one net of
+ * each kind per context. The net is owned by the context. */
+int lb2_net_create(lb2_ctx* ctx, int kind, lb2_net** net_out);
+
+/* Replaces OpenCL_Network::push_convolve (OpenCL.h:66-87): w is OIHW fp32
+ * [c_out][c_in][k][k] (Network.cpp:363), bias [c_out]. Bias + ELU follow every conv
+ * (Network.cpp:382-392). Layers run in push order (Network.cpp:206-233). */
+int lb2_net_push_conv(lb2_net* net, int k, int c_in, int c_out, const float* w_oihw, const float* bias);
+
+/* Replaces OpenCL_Network::push_innerproduct (OpenCL.h:89-94): w row-major [n_out][n_in];
+ * ELU follows iff n_out > 1 (Network.cpp:411-421). */
+int lb2_net_push_ip(lb2_net* net, int n_in, int n_out, const float* w, const float* bias);
+
+/* Repacks the weights for the tensor-core kernels and replicates them to every device.
+ * Supported stacks: a 5x5 conv from 32 planes, then 3x3 convs of constant width
+ * (c_out a multiple of 16, <= 128), then a 3x3 conv to 1 channel; the value net adds
+ * innerproduct 361 -> H (H <= 256) and H -> 1. That covers NN128 and NNValue. */
+int lb2_net_finalize(lb2_net* net);
+
+/* Replace OpenCL_Network::forward (OpenCL.cpp:490-569) for a BATCH of n positions (the
+ * reference evaluates one). Blocking. probs_out: [n][361] fp32; winrate_out: [n] fp32. */
+int lb2_eval_policy(lb2_ctx* ctx, const uint32_t* planes, const uint8_t* rotation, int n,
+                    float softmax_temp, float* probs_out);
+int lb2_eval_value(lb2_ctx* ctx, const uint32_t* planes, const uint8_t* rotation, int n,
+                   float* winrate_out);
+/* Both nets for the same n positions (policy and value planes are different 32-plane sets),
+ * run concurrently on the device. The benchmark unit. */
+int lb2_eval_both(lb2_ctx* ctx, const uint32_t* policy_planes, const uint32_t* value_planes,
+                  const uint8_t* rotation, int n, float softmax_temp,
+                  float* probs_out, float* winrate_out);
+
+/* Same as lb2_eval_both but every pointer is DEVICE memory on context device `dev_index`,
+ * work is enqueued on `cuda_stream` (a cudaStream_t, NULL = the context's own stream) and the
+ * call returns without synchronising. Used to time the kernels with inputs resident in HBM.
+ * Either output pointer may be NULL to skip that net. */
+int lb2_eval_both_device(lb2_ctx* ctx, int dev_index, const uint32_t* d_policy_planes,
+                         const uint32_t* d_value_planes, const uint8_t* d_rotation, int n,
+                         float softmax_temp, float* d_probs_out, float* d_winrate_out,
+                         void* cuda_stream);
+
+/* Asynchronous submission from many search threads; replaces forward(cb) +
+ * thread_can_issue / join_outstanding_cb (OpenCL.cpp:446-454, 560-577). Requests are
+ * coalesced into device batches by a worker thread; cb(user, status) runs on that thread once
+ * the caller's output buffer is filled. Input buffers are copied before the call returns. */
+typedef void (*lb2_callback)(void* user, int status);
+int lb2_submit_policy(lb2_ctx* ctx, const uint32_t* planes, const uint8_t* rotation, int n,
+                      float softmax_temp, float* probs_out, lb2_callback cb, void* user);
+int lb2_submit_value(lb2_ctx* ctx, const uint32_t* planes, const uint8_t* rotation, int n,
+                     float* winrate_out, lb2_callback cb, void* user);
+int lb2_drain(lb2_ctx* ctx);
+
+/* Replaces OpenCL::get_device_name / Network::get_backend (Network.cpp:1535-1553). */
+const char* lb2_backend_name(lb2_ctx* ctx);
+const char* lb2_last_error(void);
+int lb2_device_count(lb2_ctx* ctx);
+
+/* Tuning / introspection.
+ *   "trunk_mode": 0 = one launch per layer, 1 = single persistent dataflow launch (default)
+ *   "max_batch":  positions per device pass (larger calls are chunked), default 2048 */
+int lb2_set_option(lb2_ctx* ctx, const char* name, long value);
+long lb2_get_option(lb2_ctx* ctx, const char* name);
+/* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
+long lb2_launch_count(lb2_ctx* ctx);
+
+/* Test hook: run the first `n_layers` convs of net `kind` on n positions and return the
+ * activations of the last one as fp32 [n][c_out][361] in NETWORK orientation (i.e. still
+ * rotated), after bias + ELU, as stored (fp16-rounded). Lets tests check each layer against
+ * the oracle's convolve<>. */
+int lb2_debug_trunk(lb2_ctx* ctx, int kind, const uint32_t* planes, const uint8_t* rotation,
+                    int n, int n_layers, float* act_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEELA_B200_H */

@@ -1,0 +1,851 @@
+// lb2_api.cu — host side of the C ABI declared in include/leela_b200.h.
+// Owns devices, replicated weights, per-device workspaces, TMA tensor maps and the batch
+// pipeline: pinned staging -> H2D -> expand -> trunk (tcgen05) -> heads -> D2H.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/leela_b200.h"
+#include "lb2_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                  \
+    do {                                                                                              \
+        cudaError_t e_ = (expr);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(LB2_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_tiled = nullptr;
+
+int load_driver_entry() {
+    if (g_encode_tiled) return LB2_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CU_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(LB2_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+    return LB2_OK;
+}
+
+struct HostConv {
+    int k, c_in, c_out;
+    std::vector<float> w, b;
+};
+struct HostIp {
+    int n_in, n_out;
+    std::vector<float> w, b;
+};
+
+struct TrunkLayerDev {
+    int k, c_in, c_out;
+    __half* wpk = nullptr;
+    float* bias = nullptr;
+};
+
+// One net replicated on one device, with its workspace.
+struct NetDev {
+    std::vector<TrunkLayerDev> trunk;
+    int head_c_in = 0;
+    float *head_w = nullptr, *head_b = nullptr;
+    int hidden = 0;
+    float *ip1_wt = nullptr, *ip1_b = nullptr, *ip2_w = nullptr, *ip2_b = nullptr;
+    // workspace
+    int cap = 0;
+    int width = 0;           // widest trunk c_out
+    int rows5 = 0, rows3 = 0;  // chunk-plane rows of the S=21 / S=20 buffers
+    uint32_t* planes = nullptr;
+    __half* x0 = nullptr;
+    __half* act[2] = {nullptr, nullptr};
+    float* out = nullptr;    // probs [cap][361] or winrate [cap]
+    uint32_t* flags = nullptr;
+    int flags_stride = 0;
+    CUtensorMap tm_x0, tm_act[2];
+};
+
+struct DeviceState {
+    int id = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    NetDev net[2];
+    uint8_t* rot = nullptr;
+    lb2::LayerJob* jobs_dev = nullptr;
+    // pinned staging
+    uint32_t* h_planes[2] = {nullptr, nullptr};
+    uint8_t* h_rot = nullptr;
+    float* h_probs = nullptr;
+    float* h_win = nullptr;
+    lb2::LayerJob* h_jobs = nullptr;
+    int cap = 0;
+    uint32_t epoch = 0;
+    long plan_key[7] = {-1, -1, -1, -1, -1, -1, -1};  // n, run0, run1, limit0, limit1, workspace pointers
+};
+
+struct Request {
+    int kind;
+    std::vector<uint32_t> planes;
+    std::vector<uint8_t> rot;
+    int n;
+    float temp;
+    float* out;
+    lb2_callback cb;
+    void* user;
+};
+
+}  // namespace
+
+struct lb2_net {
+    lb2_ctx* ctx;
+    int kind;
+    bool finalized = false;
+    std::vector<HostConv> convs;
+    std::vector<HostIp> ips;
+};
+
+struct lb2_ctx {
+    std::vector<DeviceState> dev;
+    std::unique_ptr<lb2_net> nets[2];
+    std::string backend;
+    long trunk_mode = 1;
+    long max_batch = 512;
+    std::atomic<long> launches{0};
+    std::mutex eval_mu;
+    // async submission
+    std::mutex q_mu;
+    std::condition_variable q_cv, q_idle;
+    std::deque<Request> queue;
+    bool worker_run = false, worker_busy = false;
+    std::thread worker;
+};
+
+namespace {
+
+// --------------------------------------------------------------------------------------------
+// weights
+// --------------------------------------------------------------------------------------------
+void tap_groups(int k, int* n, int* begin, int* end) {
+    if (k == 3) { *n = 1; begin[0] = 0; end[0] = 9; }
+    else { *n = 3; begin[0] = 0; end[0] = 9; begin[1] = 9; end[1] = 17; begin[2] = 17; end[2] = 25; }
+}
+
+// [slab][tap group][tap][2 chunks][c_out][8] fp16 — the smem image of each pipeline stage.
+std::vector<__half> pack_trunk_weights(const HostConv& c) {
+    const int kk = c.k * c.k;
+    std::vector<__half> out((size_t)kk * c.c_in * c.c_out);
+    int ng, gb[3], ge[3];
+    tap_groups(c.k, &ng, gb, ge);
+    size_t o = 0;
+    for (int s = 0; s < c.c_in / 16; s++)
+        for (int g = 0; g < ng; g++)
+            for (int t = gb[g]; t < ge[g]; t++)
+                for (int j = 0; j < 2; j++)
+                    for (int n = 0; n < c.c_out; n++)
+                        for (int e = 0; e < 8; e++) {
+                            const int ci = 16 * s + 8 * j + e;
+                            out[o++] = __float2half_rn(c.w[((size_t)n * c.c_in + ci) * kk + t]);
+                        }
+    return out;
+}
+
+template <class T>
+int upload(T** dst, const void* src, size_t bytes) {
+    CU_TRY(cudaMalloc(reinterpret_cast<void**>(dst), bytes));
+    CU_TRY(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    return LB2_OK;
+}
+
+int upload_net(const lb2_net* net, NetDev* nd) {
+    const size_t nconv = net->convs.size();
+    nd->trunk.clear();
+    nd->width = 0;
+    for (size_t l = 0; l + 1 < nconv; l++) {
+        const HostConv& c = net->convs[l];
+        TrunkLayerDev t;
+        t.k = c.k; t.c_in = c.c_in; t.c_out = c.c_out;
+        std::vector<__half> pk = pack_trunk_weights(c);
+        int rc = upload(&t.wpk, pk.data(), pk.size() * sizeof(__half));
+        if (rc) return rc;
+        rc = upload(&t.bias, c.b.data(), c.b.size() * sizeof(float));
+        if (rc) return rc;
+        nd->trunk.push_back(t);
+        nd->width = std::max(nd->width, c.c_out);
+    }
+    const HostConv& h = net->convs.back();
+    nd->head_c_in = h.c_in;
+    int rc = upload(&nd->head_w, h.w.data(), h.w.size() * sizeof(float));
+    if (rc) return rc;
+    rc = upload(&nd->head_b, h.b.data(), sizeof(float));
+    if (rc) return rc;
+    if (net->kind == LB2_VALUE) {
+        const HostIp& a = net->ips[0];
+        const HostIp& b = net->ips[1];
+        nd->hidden = a.n_out;
+        std::vector<float> wt((size_t)a.n_in * a.n_out);  // transpose to [n_in][n_out] for coalesced reads
+        for (int o = 0; o < a.n_out; o++)
+            for (int i = 0; i < a.n_in; i++) wt[(size_t)i * a.n_out + o] = a.w[(size_t)o * a.n_in + i];
+        if ((rc = upload(&nd->ip1_wt, wt.data(), wt.size() * sizeof(float)))) return rc;
+        if ((rc = upload(&nd->ip1_b, a.b.data(), a.b.size() * sizeof(float)))) return rc;
+        if ((rc = upload(&nd->ip2_w, b.w.data(), b.w.size() * sizeof(float)))) return rc;
+        if ((rc = upload(&nd->ip2_b, b.b.data(), sizeof(float)))) return rc;
+    }
+    return LB2_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// workspaces + tensor maps
+// --------------------------------------------------------------------------------------------
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// Activation buffer [chunks][rows][8] fp16 viewed as 3-D {64 elems = 8 rows x 8 ch, rows/8, chunks};
+// a box {64, (256+2*halo)/8, 2} is one [rows x 16 channels] A slab in core-matrix order.
+int make_act_tmap(CUtensorMap* tm, __half* base, int rows, int chunks, int halo) {
+    cuuint64_t gdim[3] = {64, (cuuint64_t)rows / 8, (cuuint64_t)chunks};
+    cuuint64_t gstride[2] = {128, (cuuint64_t)rows * 16};
+    cuuint32_t box[3] = {64, (cuuint32_t)(lb2::kTileRows + 2 * halo) / 8, 2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, gdim, gstride, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LB2_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return LB2_OK;
+}
+
+void free_workspace(NetDev* nd) {
+    cudaFree(nd->planes); cudaFree(nd->x0); cudaFree(nd->act[0]); cudaFree(nd->act[1]);
+    cudaFree(nd->out); cudaFree(nd->flags);
+    nd->planes = nullptr; nd->x0 = nullptr; nd->act[0] = nd->act[1] = nullptr; nd->out = nullptr; nd->flags = nullptr;
+    nd->cap = 0;
+}
+
+int ensure_workspace(NetDev* nd, int kind, int cap) {
+    if (nd->cap >= cap) return LB2_OK;
+    free_workspace(nd);
+    nd->rows5 = round_up(cap * 441, lb2::kTileRows);
+    nd->rows3 = round_up(cap * 400, lb2::kTileRows);
+    const size_t x0_bytes = (size_t)4 * nd->rows5 * 16;
+    const size_t act_bytes = (size_t)(nd->width / 8) * nd->rows3 * 16;
+    CU_TRY(cudaMalloc(&nd->planes, (size_t)cap * lb2::kPoints * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&nd->x0, x0_bytes));
+    CU_TRY(cudaMalloc(&nd->act[0], act_bytes));
+    CU_TRY(cudaMalloc(&nd->act[1], act_bytes));
+    CU_TRY(cudaMemset(nd->x0, 0, x0_bytes));
+    CU_TRY(cudaMemset(nd->act[0], 0, act_bytes));  // padding rows/columns must start (and stay) zero
+    CU_TRY(cudaMemset(nd->act[1], 0, act_bytes));
+    const size_t out_elems = kind == LB2_POLICY ? (size_t)cap * lb2::kPoints : (size_t)cap;
+    CU_TRY(cudaMalloc(&nd->out, out_elems * sizeof(float)));
+    nd->flags_stride = nd->rows5 / lb2::kTileRows + 1;
+    CU_TRY(cudaMalloc(&nd->flags, (size_t)lb2::kMaxJobs * nd->flags_stride * sizeof(uint32_t)));
+    CU_TRY(cudaMemset(nd->flags, 0, (size_t)lb2::kMaxJobs * nd->flags_stride * sizeof(uint32_t)));
+    int rc;
+    if ((rc = make_act_tmap(&nd->tm_x0, nd->x0, nd->rows5, 4, 48))) return rc;
+    if ((rc = make_act_tmap(&nd->tm_act[0], nd->act[0], nd->rows3, nd->width / 8, 24))) return rc;
+    if ((rc = make_act_tmap(&nd->tm_act[1], nd->act[1], nd->rows3, nd->width / 8, 24))) return rc;
+    nd->cap = cap;
+    return LB2_OK;
+}
+
+int ensure_device_staging(DeviceState* d, int cap) {
+    if (d->cap >= cap) return LB2_OK;
+    if (d->cap) {
+        cudaFree(d->rot); cudaFreeHost(d->h_planes[0]); cudaFreeHost(d->h_planes[1]); cudaFreeHost(d->h_rot);
+        cudaFreeHost(d->h_probs); cudaFreeHost(d->h_win);
+    }
+    CU_TRY(cudaMalloc(&d->rot, cap));
+    for (int k = 0; k < 2; k++) CU_TRY(cudaMallocHost(&d->h_planes[k], (size_t)cap * lb2::kPoints * sizeof(uint32_t)));
+    CU_TRY(cudaMallocHost(&d->h_rot, cap));
+    CU_TRY(cudaMallocHost(&d->h_probs, (size_t)cap * lb2::kPoints * sizeof(float)));
+    CU_TRY(cudaMallocHost(&d->h_win, (size_t)cap * sizeof(float)));
+    d->cap = cap;
+    return LB2_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// the batch pipeline on one device; all pointers are device pointers
+// --------------------------------------------------------------------------------------------
+struct JobPlan {
+    std::vector<lb2::LayerJob> jobs;
+    std::vector<int> round_of;  // launch round (layer depth) of each job, for per-layer mode
+    int total_items = 0;
+    const __half* last_act[2] = {nullptr, nullptr};
+    int tmap_base[2] = {0, 3};
+};
+
+// Interleave the two nets layer by layer: P1 V1 P2 V2 ... so that one launch round holds
+// independent jobs of equal depth.
+JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2]) {
+    JobPlan pl;
+    size_t depth = 0;
+    for (int k = 0; k < 2; k++)
+        if (run[k]) depth = std::max(depth, (size_t)std::min<int>(limit_layers[k], d->net[k].trunk.size()));
+    int prev_job[2] = {-1, -1};
+    for (size_t l = 0; l < depth; l++) {
+        for (int k = 0; k < 2; k++) {
+            NetDev& nd = d->net[k];
+            if (!run[k] || l >= nd.trunk.size() || (int)l >= limit_layers[k]) continue;
+            const TrunkLayerDev& t = nd.trunk[l];
+            lb2::LayerJob J;
+            memset(&J, 0, sizeof J);
+            const bool first = (l == 0);
+            J.S = first ? 21 : 20;
+            J.ksize = t.k;
+            J.halo = first ? 48 : 24;
+            J.n_slabs = t.c_in / 16;
+            J.n_out = t.c_out;
+            J.n_items = (n * J.S * J.S + lb2::kTileRows - 1) / lb2::kTileRows;
+            J.item_base = pl.total_items;
+            J.remap = first ? 1 : 0;
+            // buffers: x0 -> act0 -> act1 -> act0 ...
+            J.tmap = pl.tmap_base[k] + (first ? 0 : 1 + (int)((l - 1) & 1));
+            J.out = nd.act[l & 1];
+            J.out_chunk_rows = nd.rows3;
+            J.dep_job = prev_job[k];
+            if (J.dep_job >= 0) {
+                J.dep_remap = pl.jobs[J.dep_job].remap;
+                J.dep_n_items = pl.jobs[J.dep_job].n_items;
+            }
+            J.n_pos = n;
+            J.wpk = t.wpk;
+            J.bias = t.bias;
+            J.flags = nd.flags + (size_t)l * nd.flags_stride;
+            prev_job[k] = (int)pl.jobs.size();
+            pl.jobs.push_back(J);
+            pl.round_of.push_back((int)l);
+            pl.total_items += J.n_items;
+            pl.last_act[k] = J.out;
+        }
+    }
+    return pl;
+}
+
+int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers[2], cudaStream_t st,
+              JobPlan* plan_out) {
+    JobPlan pl = plan_jobs(d, run, n, limit_layers);
+    if (pl.jobs.empty()) return fail(LB2_ERR_STATE, "no trunk layers to run");
+    if ((int)pl.jobs.size() > lb2::kMaxJobs) return fail(LB2_ERR_UNSUPPORTED, "too many layers");
+    const long key[7] = {n, run[0], run[1], limit_layers[0], limit_layers[1],
+                         (long)reinterpret_cast<uintptr_t>(d->net[0].act[0]), (long)reinterpret_cast<uintptr_t>(d->net[1].act[0])};
+    if (memcmp(key, d->plan_key, sizeof key)) {
+        // the job table on the device is reused by back-to-back launches of the same shape;
+        // rewrite it only when the shape changes, after earlier work has drained
+        CU_TRY(cudaStreamSynchronize(st));
+        CU_TRY(cudaStreamSynchronize(d->stream));
+        memcpy(d->h_jobs, pl.jobs.data(), pl.jobs.size() * sizeof(lb2::LayerJob));
+        CU_TRY(cudaMemcpyAsync(d->jobs_dev, d->h_jobs, pl.jobs.size() * sizeof(lb2::LayerJob), cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        memcpy(d->plan_key, key, sizeof key);
+    }
+    lb2::TrunkParams P;
+    memset(&P, 0, sizeof P);
+    for (int k = 0; k < 2; k++) {
+        if (!d->net[k].cap) continue;
+        P.tmaps[pl.tmap_base[k] + 0] = d->net[k].tm_x0;
+        P.tmaps[pl.tmap_base[k] + 1] = d->net[k].tm_act[0];
+        P.tmaps[pl.tmap_base[k] + 2] = d->net[k].tm_act[1];
+    }
+    for (int k = 0; k < 2; k++)  // unused slots still get prefetched: point them at a valid map
+        if (!d->net[k].cap)
+            for (int i = 0; i < 3; i++) P.tmaps[pl.tmap_base[k] + i] = d->net[1 - k].tm_x0;
+    P.jobs = d->jobs_dev;
+    P.n_jobs = (int)pl.jobs.size();
+    P.epoch = ++d->epoch;
+    if (const char* dbg = getenv("LB2_DEBUG_FLAGS")) P.debug_flags = atoi(dbg);
+    if (ctx->trunk_mode == 1) {
+        P.item_begin = 0;
+        P.item_end = pl.total_items;
+        P.use_flags = 1;
+        const int grid = std::min(d->sm_count, pl.total_items);
+        CU_TRY(lb2::launch_trunk(P, grid, true, st));
+        ctx->launches++;
+    } else {
+        P.use_flags = 0;
+        size_t i = 0;
+        while (i < pl.jobs.size()) {
+            size_t e = i;
+            while (e < pl.jobs.size() && pl.round_of[e] == pl.round_of[i]) e++;
+            P.item_begin = pl.jobs[i].item_base;
+            P.item_end = pl.jobs[e - 1].item_base + pl.jobs[e - 1].n_items;
+            const int grid = std::min(d->sm_count, P.item_end - P.item_begin);
+            CU_TRY(lb2::launch_trunk(P, grid, false, st));
+            ctx->launches++;
+            i = e;
+        }
+    }
+    if (plan_out) *plan_out = pl;
+    return LB2_OK;
+}
+
+int eval_on_device(lb2_ctx* ctx, DeviceState* d, const uint32_t* d_pol, const uint32_t* d_val, const uint8_t* d_rot,
+                   int n, float temp, float* d_probs, float* d_win, cudaStream_t st) {
+    bool run[2] = {d_probs != nullptr, d_win != nullptr};
+    const uint32_t* planes[2] = {d_pol, d_val};
+    int limit[2] = {1 << 20, 1 << 20};
+    for (int k = 0; k < 2; k++) {
+        if (!run[k]) continue;
+        NetDev& nd = d->net[k];
+        if (nd.cap < n) return fail(LB2_ERR_STATE, "workspace too small");
+        CU_TRY(lb2::launch_expand(planes[k], d_rot, n, nd.x0, nd.rows5, st));
+        ctx->launches++;
+    }
+    JobPlan pl;
+    int rc = run_trunk(ctx, d, run, n, limit, st, &pl);
+    if (rc) return rc;
+    if (run[0]) {
+        NetDev& nd = d->net[0];
+        CU_TRY(lb2::launch_policy_head(pl.last_act[0], nd.rows3, nd.head_c_in, nd.head_w, nd.head_b, d_rot, n, temp,
+                                       d_probs, st));
+        ctx->launches++;
+    }
+    if (run[1]) {
+        NetDev& nd = d->net[1];
+        CU_TRY(lb2::launch_value_head(pl.last_act[1], nd.rows3, nd.head_c_in, nd.head_w, nd.head_b, nd.ip1_wt, nd.ip1_b,
+                                      nd.hidden, nd.ip2_w, nd.ip2_b, n, d_win, st));
+        ctx->launches++;
+    }
+    return LB2_OK;
+}
+
+int check_ready(lb2_ctx* ctx, bool need[2]) {
+    if (!ctx) return fail(LB2_ERR_INVALID, "null context");
+    for (int k = 0; k < 2; k++)
+        if (need[k] && !(ctx->nets[k] && ctx->nets[k]->finalized))
+            return fail(LB2_ERR_STATE, "%s net not finalized", k == 0 ? "policy" : "value");
+    return LB2_OK;
+}
+
+int check_rotations(const uint8_t* rot, int n) {
+    for (int i = 0; i < n; i++)
+        if (rot[i] > 7) return fail(LB2_ERR_INVALID, "rotation[%d] = %d out of range 0..7", i, (int)rot[i]);
+    return LB2_OK;
+}
+
+// Host-buffer evaluation: shard positions over devices in contiguous slices, chunk each slice
+// by max_batch, stage through pinned memory.
+int eval_host(lb2_ctx* ctx, const uint32_t* pol, const uint32_t* val, const uint8_t* rot, int n, float temp,
+              float* probs, float* win) {
+    bool need[2] = {probs != nullptr, win != nullptr};
+    int rc = check_ready(ctx, need);
+    if (rc) return rc;
+    if (n < 0) return fail(LB2_ERR_INVALID, "n < 0");
+    if (n == 0) return LB2_OK;
+    if (!rot || (need[0] && !pol) || (need[1] && !val)) return fail(LB2_ERR_INVALID, "null input pointer");
+    if (need[0] && !(temp > 0.0f)) return fail(LB2_ERR_INVALID, "softmax temperature must be > 0");
+    if ((rc = check_rotations(rot, n))) return rc;
+    std::lock_guard<std::mutex> lk(ctx->eval_mu);
+    const int ndev = (int)ctx->dev.size();
+    const int per = (n + ndev - 1) / ndev;
+    const int chunk = (int)std::min<long>(ctx->max_batch, per);
+    for (int base = 0; base < per; base += chunk) {
+        // enqueue one chunk on every device, then collect
+        std::vector<int> cnt(ndev, 0), off(ndev, 0);
+        for (int di = 0; di < ndev; di++) {
+            const int lo = std::min(n, di * per + base), hi = std::min(n, std::min((di + 1) * per, di * per + base + chunk));
+            cnt[di] = std::max(0, hi - lo);
+            off[di] = lo;
+            if (!cnt[di]) continue;
+            DeviceState* d = &ctx->dev[di];
+            CU_TRY(cudaSetDevice(d->id));
+            if ((rc = ensure_device_staging(d, std::max(chunk, cnt[di])))) return rc;
+            for (int k = 0; k < 2; k++)
+                if (need[k] && (rc = ensure_workspace(&d->net[k], k, std::max(chunk, cnt[di])))) return rc;
+            const size_t pbytes = (size_t)cnt[di] * lb2::kPoints * sizeof(uint32_t);
+            memcpy(d->h_rot, rot + lo, cnt[di]);
+            CU_TRY(cudaMemcpyAsync(d->rot, d->h_rot, cnt[di], cudaMemcpyHostToDevice, d->stream));
+            const uint32_t* src[2] = {pol, val};
+            for (int k = 0; k < 2; k++) {
+                if (!need[k]) continue;
+                memcpy(d->h_planes[k], src[k] + (size_t)lo * lb2::kPoints, pbytes);
+                CU_TRY(cudaMemcpyAsync(d->net[k].planes, d->h_planes[k], pbytes, cudaMemcpyHostToDevice, d->stream));
+            }
+            rc = eval_on_device(ctx, d, d->net[0].planes, d->net[1].planes, d->rot, cnt[di], temp,
+                                need[0] ? d->net[0].out : nullptr, need[1] ? d->net[1].out : nullptr, d->stream);
+            if (rc) return rc;
+            if (need[0])
+                CU_TRY(cudaMemcpyAsync(d->h_probs, d->net[0].out, (size_t)cnt[di] * lb2::kPoints * sizeof(float),
+                                       cudaMemcpyDeviceToHost, d->stream));
+            if (need[1])
+                CU_TRY(cudaMemcpyAsync(d->h_win, d->net[1].out, (size_t)cnt[di] * sizeof(float), cudaMemcpyDeviceToHost,
+                                       d->stream));
+        }
+        for (int di = 0; di < ndev; di++) {
+            if (!cnt[di]) continue;
+            DeviceState* d = &ctx->dev[di];
+            CU_TRY(cudaSetDevice(d->id));
+            CU_TRY(cudaStreamSynchronize(d->stream));
+            if (need[0]) memcpy(probs + (size_t)off[di] * lb2::kPoints, d->h_probs, (size_t)cnt[di] * lb2::kPoints * sizeof(float));
+            if (need[1]) memcpy(win + off[di], d->h_win, (size_t)cnt[di] * sizeof(float));
+        }
+    }
+    return LB2_OK;
+}
+
+void worker_loop(lb2_ctx* ctx) {
+    for (;;) {
+        std::vector<Request> batch;
+        {
+            std::unique_lock<std::mutex> lk(ctx->q_mu);
+            ctx->q_cv.wait(lk, [&] { return !ctx->worker_run || !ctx->queue.empty(); });
+            if (!ctx->worker_run && ctx->queue.empty()) return;
+            // coalesce every queued request of the same kind and temperature as the head one
+            const int kind = ctx->queue.front().kind;
+            const float temp = ctx->queue.front().temp;
+            int total = 0;
+            for (auto it = ctx->queue.begin(); it != ctx->queue.end();) {
+                if (it->kind == kind && it->temp == temp && total + it->n <= std::max<long>(ctx->max_batch * (long)ctx->dev.size(), it->n)) {
+                    total += it->n;
+                    batch.push_back(std::move(*it));
+                    it = ctx->queue.erase(it);
+                } else {
+                    ++it;
+                }
+            }
+            ctx->worker_busy = true;
+        }
+        int total = 0;
+        for (auto& r : batch) total += r.n;
+        std::vector<uint32_t> planes((size_t)total * lb2::kPoints);
+        std::vector<uint8_t> rot(total);
+        int o = 0;
+        for (auto& r : batch) {
+            memcpy(planes.data() + (size_t)o * lb2::kPoints, r.planes.data(), r.planes.size() * sizeof(uint32_t));
+            memcpy(rot.data() + o, r.rot.data(), r.n);
+            o += r.n;
+        }
+        const int kind = batch[0].kind;
+        std::vector<float> out(kind == LB2_POLICY ? (size_t)total * lb2::kPoints : (size_t)total);
+        int rc = kind == LB2_POLICY
+                     ? eval_host(ctx, planes.data(), nullptr, rot.data(), total, batch[0].temp, out.data(), nullptr)
+                     : eval_host(ctx, nullptr, planes.data(), rot.data(), total, 1.0f, nullptr, out.data());
+        o = 0;
+        for (auto& r : batch) {
+            if (rc == LB2_OK) {
+                const size_t per = kind == LB2_POLICY ? lb2::kPoints : 1;
+                memcpy(r.out, out.data() + (size_t)o * per, (size_t)r.n * per * sizeof(float));
+            }
+            o += r.n;
+            if (r.cb) r.cb(r.user, rc);
+        }
+        {
+            std::lock_guard<std::mutex> lk(ctx->q_mu);
+            ctx->worker_busy = false;
+            if (ctx->queue.empty()) ctx->q_idle.notify_all();
+        }
+    }
+}
+
+int submit(lb2_ctx* ctx, int kind, const uint32_t* planes, const uint8_t* rot, int n, float temp, float* out,
+           lb2_callback cb, void* user) {
+    bool need[2] = {kind == LB2_POLICY, kind == LB2_VALUE};
+    int rc = check_ready(ctx, need);
+    if (rc) return rc;
+    if (n <= 0 || !planes || !rot || !out) return fail(LB2_ERR_INVALID, "bad submit arguments");
+    if ((rc = check_rotations(rot, n))) return rc;
+    Request r;
+    r.kind = kind; r.n = n; r.temp = temp; r.out = out; r.cb = cb; r.user = user;
+    r.planes.assign(planes, planes + (size_t)n * lb2::kPoints);
+    r.rot.assign(rot, rot + n);
+    {
+        std::lock_guard<std::mutex> lk(ctx->q_mu);
+        if (!ctx->worker_run) {
+            ctx->worker_run = true;
+            ctx->worker = std::thread(worker_loop, ctx);
+        }
+        ctx->queue.push_back(std::move(r));
+    }
+    ctx->q_cv.notify_one();
+    return LB2_OK;
+}
+
+}  // namespace
+
+// ============================================================================================
+// C ABI
+// ============================================================================================
+extern "C" {
+
+const char* lb2_last_error(void) { return g_last_error.c_str(); }
+
+int lb2_init(const int* device_ids, int n_devices, lb2_ctx** ctx_out) {
+    if (!ctx_out) return fail(LB2_ERR_INVALID, "ctx_out is null");
+    *ctx_out = nullptr;
+    int count = 0;
+    CU_TRY(cudaGetDeviceCount(&count));
+    if (count <= 0) return fail(LB2_ERR_CUDA, "no CUDA device");
+    std::vector<int> ids;
+    if (!device_ids || n_devices <= 0) ids.push_back(0);
+    else ids.assign(device_ids, device_ids + n_devices);
+    std::unique_ptr<lb2_ctx> ctx(new lb2_ctx);
+    for (int id : ids) {
+        if (id < 0 || id >= count) return fail(LB2_ERR_INVALID, "device id %d out of range (have %d)", id, count);
+        cudaDeviceProp prop;
+        CU_TRY(cudaGetDeviceProperties(&prop, id));
+        if (prop.major != 10)
+            return fail(LB2_ERR_UNSUPPORTED, "device %d (%s, sm_%d%d) is not a Blackwell B200-class GPU; no fallback path",
+                        id, prop.name, prop.major, prop.minor);
+        CU_TRY(cudaSetDevice(id));
+        DeviceState d;
+        d.id = id;
+        d.sm_count = prop.multiProcessorCount;
+        CU_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+        CU_TRY(cudaMalloc(&d.jobs_dev, lb2::kMaxJobs * sizeof(lb2::LayerJob)));
+        CU_TRY(cudaMallocHost(&d.h_jobs, lb2::kMaxJobs * sizeof(lb2::LayerJob)));
+        CU_TRY(lb2::trunk_kernel_setup());
+        if (ctx->backend.empty()) ctx->backend = std::string("B200 tcgen05: ") + prop.name;
+        ctx->dev.push_back(d);
+    }
+    int rc = load_driver_entry();
+    if (rc) return rc;
+    if (ids.size() > 1) ctx->backend += " x" + std::to_string(ids.size());
+    *ctx_out = ctx.release();
+    return LB2_OK;
+}
+
+void lb2_destroy(lb2_ctx* ctx) {
+    if (!ctx) return;
+    lb2_drain(ctx);
+    {
+        std::lock_guard<std::mutex> lk(ctx->q_mu);
+        ctx->worker_run = false;
+    }
+    ctx->q_cv.notify_all();
+    if (ctx->worker.joinable()) ctx->worker.join();
+    for (auto& d : ctx->dev) {
+        cudaSetDevice(d.id);
+        cudaStreamSynchronize(d.stream);
+        for (int k = 0; k < 2; k++) {
+            NetDev& nd = d.net[k];
+            for (auto& t : nd.trunk) { cudaFree(t.wpk); cudaFree(t.bias); }
+            cudaFree(nd.head_w); cudaFree(nd.head_b); cudaFree(nd.ip1_wt); cudaFree(nd.ip1_b);
+            cudaFree(nd.ip2_w); cudaFree(nd.ip2_b);
+            free_workspace(&nd);
+        }
+        cudaFree(d.rot); cudaFree(d.jobs_dev);
+        cudaFreeHost(d.h_planes[0]); cudaFreeHost(d.h_planes[1]); cudaFreeHost(d.h_rot);
+        cudaFreeHost(d.h_probs); cudaFreeHost(d.h_win); cudaFreeHost(d.h_jobs);
+        cudaStreamDestroy(d.stream);
+    }
+    delete ctx;
+}
+
+int lb2_net_create(lb2_ctx* ctx, int kind, lb2_net** net_out) {
+    if (!ctx || !net_out) return fail(LB2_ERR_INVALID, "null argument");
+    if (kind != LB2_POLICY && kind != LB2_VALUE) return fail(LB2_ERR_INVALID, "unknown net kind %d", kind);
+    if (ctx->nets[kind]) return fail(LB2_ERR_STATE, "net of kind %d already exists", kind);
+    ctx->nets[kind].reset(new lb2_net);
+    ctx->nets[kind]->ctx = ctx;
+    ctx->nets[kind]->kind = kind;
+    *net_out = ctx->nets[kind].get();
+    return LB2_OK;
+}
+
+int lb2_net_push_conv(lb2_net* net, int k, int c_in, int c_out, const float* w, const float* bias) {
+    if (!net || !w || !bias) return fail(LB2_ERR_INVALID, "null argument");
+    if (net->finalized) return fail(LB2_ERR_STATE, "net already finalized");
+    if (!net->ips.empty()) return fail(LB2_ERR_STATE, "convolutions must precede inner products");
+    if ((k != 3 && k != 5) || c_in <= 0 || c_out <= 0) return fail(LB2_ERR_INVALID, "bad conv geometry k=%d %d->%d", k, c_in, c_out);
+    if (!net->convs.empty() && net->convs.back().c_out != c_in)
+        return fail(LB2_ERR_INVALID, "conv input channels %d do not match previous output %d", c_in, net->convs.back().c_out);
+    HostConv c;
+    c.k = k; c.c_in = c_in; c.c_out = c_out;
+    c.w.assign(w, w + (size_t)k * k * c_in * c_out);
+    c.b.assign(bias, bias + c_out);
+    net->convs.push_back(std::move(c));
+    return LB2_OK;
+}
+
+int lb2_net_push_ip(lb2_net* net, int n_in, int n_out, const float* w, const float* bias) {
+    if (!net || !w || !bias) return fail(LB2_ERR_INVALID, "null argument");
+    if (net->finalized) return fail(LB2_ERR_STATE, "net already finalized");
+    if (n_in <= 0 || n_out <= 0) return fail(LB2_ERR_INVALID, "bad inner product geometry");
+    HostIp p;
+    p.n_in = n_in; p.n_out = n_out;
+    p.w.assign(w, w + (size_t)n_in * n_out);
+    p.b.assign(bias, bias + n_out);
+    net->ips.push_back(std::move(p));
+    return LB2_OK;
+}
+
+int lb2_net_finalize(lb2_net* net) {
+    if (!net) return fail(LB2_ERR_INVALID, "null net");
+    if (net->finalized) return fail(LB2_ERR_STATE, "net already finalized");
+    const auto& cv = net->convs;
+    if (cv.size() < 3) return fail(LB2_ERR_UNSUPPORTED, "need at least 3 conv layers");
+    if (cv[0].k != 5 || cv[0].c_in != LB2_INPUT_PLANES) return fail(LB2_ERR_UNSUPPORTED, "first layer must be 5x5 from 32 planes");
+    for (size_t l = 0; l + 1 < cv.size(); l++) {
+        if (l > 0 && cv[l].k != 3) return fail(LB2_ERR_UNSUPPORTED, "layer %zu: only 3x3 after the first layer", l + 1);
+        if (cv[l].c_out % 32 || cv[l].c_out > 128 || cv[l].c_in % 16)
+            return fail(LB2_ERR_UNSUPPORTED, "layer %zu: channels %d->%d not supported", l + 1, cv[l].c_in, cv[l].c_out);
+    }
+    if (cv.back().k != 3 || cv.back().c_out != 1) return fail(LB2_ERR_UNSUPPORTED, "last conv must be 3x3 to 1 channel");
+    if (net->kind == LB2_POLICY) {
+        if (!net->ips.empty()) return fail(LB2_ERR_UNSUPPORTED, "policy net takes no inner products");
+    } else {
+        if (net->ips.size() != 2 || net->ips[0].n_in != LB2_BOARD_POINTS || net->ips[0].n_out > 256 ||
+            net->ips[1].n_in != net->ips[0].n_out || net->ips[1].n_out != 1)
+            return fail(LB2_ERR_UNSUPPORTED, "value net needs inner products 361->H (H<=256) and H->1");
+    }
+    for (auto& d : net->ctx->dev) {
+        CU_TRY(cudaSetDevice(d.id));
+        int rc = upload_net(net, &d.net[net->kind]);
+        if (rc) return rc;
+    }
+    net->finalized = true;
+    return LB2_OK;
+}
+
+int lb2_eval_policy(lb2_ctx* ctx, const uint32_t* planes, const uint8_t* rotation, int n, float temp, float* probs) {
+    if (!probs && n > 0) return fail(LB2_ERR_INVALID, "null output pointer");
+    return eval_host(ctx, planes, nullptr, rotation, n, temp, probs, nullptr);
+}
+
+int lb2_eval_value(lb2_ctx* ctx, const uint32_t* planes, const uint8_t* rotation, int n, float* winrate) {
+    if (!winrate && n > 0) return fail(LB2_ERR_INVALID, "null output pointer");
+    return eval_host(ctx, nullptr, planes, rotation, n, 1.0f, nullptr, winrate);
+}
+
+int lb2_eval_both(lb2_ctx* ctx, const uint32_t* pol, const uint32_t* val, const uint8_t* rotation, int n, float temp,
+                  float* probs, float* winrate) {
+    if ((!probs || !winrate) && n > 0) return fail(LB2_ERR_INVALID, "null output pointer");
+    return eval_host(ctx, pol, val, rotation, n, temp, probs, winrate);
+}
+
+int lb2_eval_both_device(lb2_ctx* ctx, int dev_index, const uint32_t* d_pol, const uint32_t* d_val,
+                         const uint8_t* d_rot, int n, float temp, float* d_probs, float* d_win, void* stream) {
+    bool need[2] = {d_probs != nullptr, d_win != nullptr};
+    int rc = check_ready(ctx, need);
+    if (rc) return rc;
+    if (dev_index < 0 || dev_index >= (int)ctx->dev.size()) return fail(LB2_ERR_INVALID, "bad device index");
+    if (n < 0) return fail(LB2_ERR_INVALID, "n < 0");
+    if (n == 0) return LB2_OK;
+    if (!d_rot || (need[0] && !d_pol) || (need[1] && !d_val)) return fail(LB2_ERR_INVALID, "null input pointer");
+    std::lock_guard<std::mutex> lk(ctx->eval_mu);
+    DeviceState* d = &ctx->dev[dev_index];
+    CU_TRY(cudaSetDevice(d->id));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : d->stream;
+    const int chunk = (int)ctx->max_batch;
+    for (int k = 0; k < 2; k++)
+        if (need[k] && (rc = ensure_workspace(&d->net[k], k, std::min(n, chunk)))) return rc;
+    for (int lo = 0; lo < n; lo += chunk) {
+        const int c = std::min(chunk, n - lo);
+        rc = eval_on_device(ctx, d, d_pol ? d_pol + (size_t)lo * lb2::kPoints : nullptr,
+                            d_val ? d_val + (size_t)lo * lb2::kPoints : nullptr, d_rot + lo, c, temp,
+                            d_probs ? d_probs + (size_t)lo * lb2::kPoints : nullptr, d_win ? d_win + lo : nullptr, st);
+        if (rc) return rc;
+    }
+    return LB2_OK;
+}
+
+int lb2_submit_policy(lb2_ctx* ctx, const uint32_t* planes, const uint8_t* rotation, int n, float temp, float* probs,
+                      lb2_callback cb, void* user) {
+    if (!(temp > 0.0f)) return fail(LB2_ERR_INVALID, "softmax temperature must be > 0");
+    return submit(ctx, LB2_POLICY, planes, rotation, n, temp, probs, cb, user);
+}
+
+int lb2_submit_value(lb2_ctx* ctx, const uint32_t* planes, const uint8_t* rotation, int n, float* winrate,
+                     lb2_callback cb, void* user) {
+    return submit(ctx, LB2_VALUE, planes, rotation, n, 1.0f, winrate, cb, user);
+}
+
+int lb2_drain(lb2_ctx* ctx) {
+    if (!ctx) return fail(LB2_ERR_INVALID, "null context");
+    std::unique_lock<std::mutex> lk(ctx->q_mu);
+    ctx->q_idle.wait(lk, [&] { return ctx->queue.empty() && !ctx->worker_busy; });
+    return LB2_OK;
+}
+
+const char* lb2_backend_name(lb2_ctx* ctx) { return ctx ? ctx->backend.c_str() : ""; }
+int lb2_device_count(lb2_ctx* ctx) { return ctx ? (int)ctx->dev.size() : 0; }
+
+int lb2_set_option(lb2_ctx* ctx, const char* name, long value) {
+    if (!ctx || !name) return fail(LB2_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->eval_mu);
+    if (!strcmp(name, "trunk_mode")) {
+        if (value != 0 && value != 1) return fail(LB2_ERR_INVALID, "trunk_mode must be 0 or 1");
+        ctx->trunk_mode = value;
+    } else if (!strcmp(name, "max_batch")) {
+        if (value < 1 || value > 65536) return fail(LB2_ERR_INVALID, "max_batch out of range");
+        ctx->max_batch = value;
+    } else {
+        return fail(LB2_ERR_INVALID, "unknown option %s", name);
+    }
+    return LB2_OK;
+}
+
+long lb2_get_option(lb2_ctx* ctx, const char* name) {
+    if (!ctx || !name) return -1;
+    if (!strcmp(name, "trunk_mode")) return ctx->trunk_mode;
+    if (!strcmp(name, "max_batch")) return ctx->max_batch;
+    if (!strcmp(name, "sm_count")) return ctx->dev.empty() ? 0 : ctx->dev[0].sm_count;
+    return -1;
+}
+
+long lb2_launch_count(lb2_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+int lb2_debug_trunk(lb2_ctx* ctx, int kind, const uint32_t* planes, const uint8_t* rotation, int n, int n_layers,
+                    float* act_out) {
+    if (kind != LB2_POLICY && kind != LB2_VALUE) return fail(LB2_ERR_INVALID, "bad kind");
+    bool need[2] = {kind == LB2_POLICY, kind == LB2_VALUE};
+    int rc = check_ready(ctx, need);
+    if (rc) return rc;
+    if (n <= 0 || !planes || !rotation || !act_out) return fail(LB2_ERR_INVALID, "bad arguments");
+    if ((rc = check_rotations(rotation, n))) return rc;
+    std::lock_guard<std::mutex> lk(ctx->eval_mu);
+    DeviceState* d = &ctx->dev[0];
+    CU_TRY(cudaSetDevice(d->id));
+    NetDev& nd = d->net[kind];
+    if (n_layers < 1 || n_layers > (int)nd.trunk.size()) return fail(LB2_ERR_INVALID, "n_layers out of range");
+    if ((rc = ensure_device_staging(d, n))) return rc;
+    if ((rc = ensure_workspace(&nd, kind, n))) return rc;
+    CU_TRY(cudaMemcpyAsync(d->rot, rotation, n, cudaMemcpyHostToDevice, d->stream));
+    CU_TRY(cudaMemcpyAsync(nd.planes, planes, (size_t)n * lb2::kPoints * sizeof(uint32_t), cudaMemcpyHostToDevice, d->stream));
+    CU_TRY(lb2::launch_expand(nd.planes, d->rot, n, nd.x0, nd.rows5, d->stream));
+    ctx->launches++;
+    int limit[2] = {0, 0};
+    limit[kind] = n_layers;
+    JobPlan pl;
+    if ((rc = run_trunk(ctx, d, need, n, limit, d->stream, &pl))) return rc;
+    const int c_out = nd.trunk[n_layers - 1].c_out;
+    std::vector<__half> host((size_t)(c_out / 8) * nd.rows3 * 8);
+    CU_TRY(cudaMemcpyAsync(host.data(), pl.last_act[kind], host.size() * sizeof(__half), cudaMemcpyDeviceToHost, d->stream));
+    CU_TRY(cudaStreamSynchronize(d->stream));
+    for (int p = 0; p < n; p++)
+        for (int c = 0; c < c_out; c++)
+            for (int y = 0; y < 19; y++)
+                for (int x = 0; x < 19; x++) {
+                    const size_t row = (size_t)p * 400 + y * 20 + x;
+                    act_out[((size_t)p * c_out + c) * 361 + y * 19 + x] =
+                        __half2float(host[((size_t)(c / 8) * nd.rows3 + row) * 8 + (c % 8)]);
+                }
+    return LB2_OK;
+}
+
+}  // extern "C"

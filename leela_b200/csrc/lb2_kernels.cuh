@@ -1,0 +1,78 @@
+// lb2_kernels.cuh — device-side data model shared by the kernels and the host API.
+//
+// HBM layout of activations ("row space"):
+//   A position's 19x19 feature map is stored as S x S rows (S = 20 for inputs of 3x3 convs,
+//   S = 21 for the input of the first 5x5 conv): row = pos*S*S + y*S + x. Columns x >= 19 and
+//   rows y >= 19 are zero padding SHARED between neighbours (the right pad of one board row is
+//   the left pad of the next; the bottom pad of one position is the top pad of the next), so a
+//   conv tap (dy, dx) of output row r reads input row r + dy*S + dx with no bounds logic.
+//   Channels are split into chunks of 8 (16 bytes of fp16); a buffer is
+//   [C/8 chunks][rows][8] fp16, i.e. each chunk plane is a dense array of 16-byte rows. This is
+//   exactly the tcgen05 K-major no-swizzle core-matrix layout, so a [rows x 16 channels] slab
+//   lands in shared memory with one TMA box and ANY row shift of it is a valid MMA operand.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace lb2 {
+
+constexpr int kPoints = 361;
+constexpr int kBoard = 19;
+constexpr int kTileRows = 256;  // output rows per work item (two M=128 MMA halves)
+constexpr int kStages = 4;      // smem ring depth (A slab + B block per stage)
+constexpr int kMaxHalo = 48;    // 5x5 conv in S=21 space needs 2*21+2 = 44 -> 48 (multiple of 8)
+constexpr int kASlabBytes = (kTileRows + 2 * kMaxHalo) * 32;  // rows x 16 ch x fp16
+constexpr int kBBlockBytes = 9 * 128 * 32;                    // up to 9 taps x N<=128 x 16 ch x fp16
+constexpr int kStageBytes = kASlabBytes + kBBlockBytes;       // 48,128
+constexpr int kTrunkThreads = 192;  // warp0 TMA producer, warp1 MMA issuer, warps2-5 epilogue
+constexpr int kTrunkSmemBytes = kStages * kStageBytes + 256;
+constexpr int kMaxTensorMaps = 6;
+constexpr int kMaxJobs = 32;
+
+// One trunk layer of one net over the whole batch.
+struct LayerJob {
+    int32_t n_items;         // 256-row tiles of this job's row space
+    int32_t item_base;       // index of its first item in the launch-wide item order
+    int32_t S;               // row-space stride (20 or 21)
+    int32_t ksize;           // 3 or 5
+    int32_t halo;            // halo rows loaded each side of a tile (multiple of 8)
+    int32_t n_slabs;         // c_in / 16
+    int32_t n_out;           // c_out = MMA N (multiple of 16, <= 128)
+    int32_t tmap;            // index of the input buffer's tensor map
+    int32_t remap;           // 1: outputs are re-addressed from S=21 space into S=20 space
+    int32_t dep_job;         // job producing this job's input in the same launch, or -1
+    int32_t dep_remap;       // that job's remap flag
+    int32_t dep_n_items;     // that job's item count
+    int32_t n_pos;           // positions in the batch
+    int32_t out_chunk_rows;  // rows per chunk plane of the output buffer
+    int32_t head_taps;       // >0: fused 1-channel head, number of taps (reserved)
+    int32_t pad_;
+    const __half* wpk;       // packed weights: per (slab, tap group): [tap][2 chunks][n_out][8]
+    const float* bias;       // [n_out]
+    __half* out;             // output activation buffer
+    uint32_t* flags;         // [n_items] completion flags (value = launch epoch)
+};
+
+struct TrunkParams {
+    CUtensorMap tmaps[kMaxTensorMaps];
+    const LayerJob* jobs;
+    int32_t n_jobs;
+    int32_t item_begin, item_end;  // launch-wide item index range handled by this launch
+    uint32_t epoch;
+    int32_t use_flags;  // 1: cross-CTA dataflow through flags (single persistent launch)
+    int32_t debug_flags;  // bring-up only; bit0: swap LBO/SBO in the smem descriptors
+};
+
+// launchers (lb2_kernels.cu)
+cudaError_t launch_expand(const uint32_t* planes, const uint8_t* rotation, int n, __half* x0, int chunk_rows,
+                          cudaStream_t st);
+cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, cudaStream_t st);
+cudaError_t launch_policy_head(const __half* act, int chunk_rows, int c_in, const float* w, const float* bias,
+                               const uint8_t* rotation, int n, float temp, float* probs, cudaStream_t st);
+cudaError_t launch_value_head(const __half* act, int chunk_rows, int c_in, const float* w, const float* bias,
+                              const float* ip1_wt, const float* ip1_b, int hidden, const float* ip2_w,
+                              const float* ip2_b, int n, float* winrate, cudaStream_t st);
+cudaError_t trunk_kernel_setup();
+
+}  // namespace lb2
