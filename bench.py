@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py — positions/s of batched policy+value evaluation (BASELINE.json's metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 256] [--impl ours|reference]
+
+A step = one pass of the hot path over one batch of 256 synthetic positions per GPU (policy net
+NN128 + value net NNValue shapes, seeded synthetic weights — the reference's weight files are
+missing from the snapshot — on positions from Leela's own Playout self-play, tests/golden/
+bench_positions.npz). N > 1 is launched by torchrun, one rank per GPU; weights replicated,
+positions sharded, no collective on the data path (weak scaling).
+
+  value     kernels only: inputs resident in HBM, CUDA events around every step on the launching
+            stream, L2 flushed between steps (outside the timed region), max over ranks.
+  e2e       the same metric through the C ABI with HOST buffers (lb2_eval_both): pinned host
+            planes -> H2D -> kernels -> D2H of probabilities and winrates inside the timed region.
+  roofline  trunk_kernel (tcgen05 conv stack): algorithmic FLOPs per launch / its CUDA-event time.
+  cpu_baseline  the reference's own OpenBLAS path (oracle/_ref, built from /root/reference) on all
+            host cores, bounded sample, rank 0 at N=1 only.
+
+--impl reference times that CPU path alone with the same JSON shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from leela_b200 import fileio, netdefs  # noqa: E402
+
+METRIC = "nn_evals_per_sec_policy_plus_value_batch256"
+UNIT = "positions/s"
+TEMP = 0.75
+TRUNK_FLOPS = (netdefs.POLICY_FLOPS - 2 * 361 * 9 * 128) + \
+              (netdefs.VALUE_FLOPS - 2 * 361 * 9 * 64 - 2 * (361 * 256 + 256))  # per position, heads excluded
+
+
+def load_positions():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "bench_positions.npz"))
+    return g["policy_planes"], g["value_planes"], g["rotation"]
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except OSError:
+        return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(prefix="lb2clk_", suffix=".csv")
+        self.f = open(self.path, "w")
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-i", str(gpu_index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is not None:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.p.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1])); mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        top = sorted(sm)[len(sm) // 2:]  # samples under load = upper half
+        return {"sm_mhz": statistics.median(top), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference(sample, warmup, steps, threads=None):
+    """Times the reference's own CPU path (oracle/_ref) — or, if it is unavailable on this box,
+    the plain-C port — on `threads` host cores. Returns (pos_per_s, dict)."""
+    from oracle import reference
+    threads = threads or (os.cpu_count() or 1)
+    pp, vp, rot = load_positions()
+    if reference.available():
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, "bench.pos")
+            n = pp.shape[0]
+            fileio.write_positions(path, fileio.Positions(pp, vp, rot, np.zeros(n, np.int32), np.zeros(n, np.int32)))
+            r = reference.steps(path, threads, sample, warmup, steps, "both")
+        return r["pos_per_s"], {"kind": "reference", "cores": threads, "blas_core": r["blas_core"],
+                                "sample": f"{steps} steps x {sample} positions (policy+value, batch 1 per thread as "
+                                          f"Network::benchmark), OpenBLAS 1 thread/worker"}
+    from leela_b200 import synth
+    from oracle import oracle
+    pn, vn = oracle.OracleNet(synth.policy_weights()), oracle.OracleNet(synth.value_weights())
+    k = min(sample, 4 * threads)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        sl = slice((s * k) % 512, (s * k) % 512 + k)
+        oracle.policy_forward(pn, pp[sl], rot[sl], TEMP)
+        oracle.value_forward(vn, vp[sl], rot[sl])
+    dt = time.perf_counter() - t0
+    return k * steps / dt, {"kind": "port", "cores": min(threads, 32),
+                            "sample": f"{steps} steps x {k} positions through oracle/leela_oracle.c"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    sample = args.batch
+    # keep the whole run within a few minutes: ~30 positions/s/core expected
+    est = (args.steps + args.warmup) * sample / (25.0 * threads)
+    if est > 150:
+        sample = max(threads, int(sample * 150 / est))
+    v, info = cpu_reference(sample, args.warmup, args.steps, threads)
+    info["value"] = v
+    info["unit"] = UNIT
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sample / v, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"policy NN128 + value NNValue, {sample} positions per step on host cores "
+                                   f"(reference evaluates batch 1 per thread)", "batch_per_step": sample},
+            "cpu_baseline": info,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from leela_b200 import capi, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200; there is no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    B = args.batch
+
+    ev = capi.Evaluator(policy=synth.policy_weights(), value=synth.value_weights(), devices=[local])
+    ev.set_option("max_batch", max(B, 512))
+    pp, vp, rot = load_positions()
+    n_sets = pp.shape[0] // B
+    # rank r starts at a different offset so ranks do not evaluate identical positions
+    order = [(rank + i) % n_sets for i in range(n_sets)]
+    d_pp = [torch.from_numpy(pp[s * B:(s + 1) * B].astype(np.int32)).to(dev) for s in order]
+    d_vp = [torch.from_numpy(vp[s * B:(s + 1) * B].astype(np.int32)).to(dev) for s in order]
+    d_rot = [torch.from_numpy(rot[s * B:(s + 1) * B].copy()).to(dev) for s in order]
+    d_probs = torch.empty((B, 361), dtype=torch.float32, device=dev)
+    d_win = torch.empty((B,), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stream = torch.cuda.current_stream(dev)
+
+    def step(i):
+        s = i % n_sets
+        ev.eval_both_device(d_pp[s].data_ptr(), d_vp[s].data_ptr(), d_rot[s].data_ptr(), B, TEMP,
+                            d_probs.data_ptr(), d_win.data_ptr(), stream=stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------------------------------------------------------- kernels, inputs in HBM
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev.set_option("profile_trunk", 1)
+    ev.get_option("trunk_ns")
+    launches0 = ev.launch_count
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)            # evict L2 between steps; outside the timed region
+        starts[i].record(stream)
+        step(i)
+        stops[i].record(stream)
+    barrier()
+    launches = ev.launch_count - launches0
+    step_ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
+    total_ms = sum(step_ms)
+    trunk_ns = ev.get_option("trunk_ns")
+    ev.set_option("profile_trunk", 0)
+
+    # ---------------------------------------------------------------- end to end through the C ABI
+    h_pp = [torch.from_numpy(pp[s * B:(s + 1) * B].astype(np.int32)).pin_memory() for s in order]
+    h_vp = [torch.from_numpy(vp[s * B:(s + 1) * B].astype(np.int32)).pin_memory() for s in order]
+    h_rot = [torch.from_numpy(rot[s * B:(s + 1) * B].copy()).pin_memory() for s in order]
+    h_probs = torch.empty((B, 361), dtype=torch.float32).pin_memory()
+    h_win = torch.empty((B,), dtype=torch.float32).pin_memory()
+
+    def step_e2e(i):
+        s = i % n_sets
+        ev.eval_both_raw(h_pp[s].data_ptr(), h_vp[s].data_ptr(), h_rot[s].data_ptr(), B, TEMP,
+                         h_probs.data_ptr(), h_win.data_ptr())
+
+    for i in range(3):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(i)          # blocking: returns after the D2H of this step's results
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    checksum = float(h_probs.sum()) + float(h_win.sum())
+    barrier()
+    clocks = sampler.stop() if sampler else None
+
+    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        n_gpus = world
+        value = n_gpus * B * args.steps / (total_ms * 1e-3)
+        e2e_value = n_gpus * B * args.steps / (e2e_ms * 1e-3)
+        peaks, peak_src = measured_peaks()
+        trunk_s = trunk_ns * 1e-9 / args.steps
+        achieved = TRUNK_FLOPS * B / trunk_s / 1e12 if trunk_s > 0 else 0.0
+        peak = float(peaks["bf16_tflops"])
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "trunk_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except OSError:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "policy NN128 + value NNValue, batch 256 positions per GPU per step "
+                                   "(BASELINE.json configs[1] shape, policy+value as the metric names)",
+                       "batch_per_gpu": B, "global_batch": B * n_gpus, "parallelism": f"replicas x{n_gpus}, positions sharded",
+                       "weights": "synthetic U(+-sqrt(6/fan_in)), seed 20260001, policy gain 2 (in-repo weights missing)",
+                       "positions": "Leela Playout self-play, 1024 distinct, cycled", "l2": "flushed between steps (256 MB write)",
+                       "trunk_mode": ev.get_option("trunk_mode"), "flops_per_position": netdefs.POLICY_FLOPS + netdefs.VALUE_FLOPS,
+                       "pct_of_bf16_peak_whole_step": 100.0 * (netdefs.POLICY_FLOPS + netdefs.VALUE_FLOPS) * value / n_gpus / (peak * 1e12)},
+            "roofline": {"bound": "tensor", "kernel": "trunk_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": f"{peak_src} burst (MEASURED_PEAKS.json bf16_tflops)",
+                         "flops_per_launch": TRUNK_FLOPS * B, "launch_ms": trunk_s * 1e3},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (2 * 1444 + 1),
+                    "d2h_bytes_per_step": B * (1444 + 4), "timing": "host clock around the blocking C-ABI call", "checksum": checksum},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        if n_gpus == 1 and not args.no_cpu:
+            v, info = cpu_reference(min(B, 256), 1, 8)
+            info["value"] = v
+            info["unit"] = UNIT
+            line["cpu_baseline"] = info
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    ev.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # convenience: relaunch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__), "--gpus", str(args.gpus),
+               "--steps", str(args.steps), "--warmup", str(args.warmup), "--batch", str(args.batch)]
+        return subprocess.call(cmd)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

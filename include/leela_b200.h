@@ -115,7 +115,9 @@ int lb2_device_count(lb2_ctx* ctx);
 
 /* Tuning / introspection.
  *   "trunk_mode": 0 = one launch per layer, 1 = single persistent dataflow launch (default)
- *   "max_batch":  positions per device pass (larger calls are chunked), default 2048 */
+ *   "max_batch":  positions per device pass (larger calls are chunked), default 512
+ *   "profile_trunk": 1 = bracket every trunk launch with CUDA events; lb2_get_option("trunk_ns")
+ *                 then returns the device nanoseconds accumulated since the last query */
 int lb2_set_option(lb2_ctx* ctx, const char* name, long value);
 long lb2_get_option(lb2_ctx* ctx, const char* name);
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */

@@ -108,6 +108,7 @@ struct DeviceState {
     lb2::LayerJob* h_jobs = nullptr;
     int cap = 0;
     uint32_t epoch = 0;
+    std::vector<cudaEvent_t> prof_events;  // (start, stop) pairs around trunk launches
     long plan_key[7] = {-1, -1, -1, -1, -1, -1, -1};  // n, run0, run1, limit0, limit1, workspace pointers
 };
 
@@ -138,6 +139,7 @@ struct lb2_ctx {
     std::string backend;
     long trunk_mode = 1;
     long max_batch = 512;
+    long profile_trunk = 0;
     std::atomic<long> launches{0};
     std::mutex eval_mu;
     // async submission
@@ -378,6 +380,12 @@ int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers
     P.jobs = d->jobs_dev;
     P.n_jobs = (int)pl.jobs.size();
     P.epoch = ++d->epoch;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ctx->profile_trunk) {
+        CU_TRY(cudaEventCreate(&ev0));
+        CU_TRY(cudaEventCreate(&ev1));
+        CU_TRY(cudaEventRecord(ev0, st));
+    }
     if (const char* dbg = getenv("LB2_DEBUG_FLAGS")) P.debug_flags = atoi(dbg);
     if (ctx->trunk_mode == 1) {
         P.item_begin = 0;
@@ -399,6 +407,11 @@ int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers
             ctx->launches++;
             i = e;
         }
+    }
+    if (ev0) {
+        CU_TRY(cudaEventRecord(ev1, st));
+        d->prof_events.push_back(ev0);
+        d->prof_events.push_back(ev1);
     }
     if (plan_out) *plan_out = pl;
     return LB2_OK;
@@ -791,6 +804,8 @@ int lb2_set_option(lb2_ctx* ctx, const char* name, long value) {
     if (!strcmp(name, "trunk_mode")) {
         if (value != 0 && value != 1) return fail(LB2_ERR_INVALID, "trunk_mode must be 0 or 1");
         ctx->trunk_mode = value;
+    } else if (!strcmp(name, "profile_trunk")) {
+        ctx->profile_trunk = value ? 1 : 0;
     } else if (!strcmp(name, "max_batch")) {
         if (value < 1 || value > 65536) return fail(LB2_ERR_INVALID, "max_batch out of range");
         ctx->max_batch = value;
@@ -805,6 +820,25 @@ long lb2_get_option(lb2_ctx* ctx, const char* name) {
     if (!strcmp(name, "trunk_mode")) return ctx->trunk_mode;
     if (!strcmp(name, "max_batch")) return ctx->max_batch;
     if (!strcmp(name, "sm_count")) return ctx->dev.empty() ? 0 : ctx->dev[0].sm_count;
+    if (!strcmp(name, "trunk_ns") || !strcmp(name, "trunk_launches_timed")) {
+        // device time spent in trunk launches since the last query (profile_trunk = 1); resets
+        std::lock_guard<std::mutex> lk(ctx->eval_mu);
+        double ms_total = 0;
+        long pairs = 0;
+        for (auto& d : ctx->dev) {
+            cudaSetDevice(d.id);
+            for (size_t i = 0; i + 1 < d.prof_events.size(); i += 2) {
+                float ms = 0;
+                cudaEventSynchronize(d.prof_events[i + 1]);
+                if (cudaEventElapsedTime(&ms, d.prof_events[i], d.prof_events[i + 1]) == cudaSuccess) ms_total += ms;
+                cudaEventDestroy(d.prof_events[i]);
+                cudaEventDestroy(d.prof_events[i + 1]);
+                pairs++;
+            }
+            d.prof_events.clear();
+        }
+        return !strcmp(name, "trunk_ns") ? (long)(ms_total * 1e6) : pairs;
+    }
     return -1;
 }
 

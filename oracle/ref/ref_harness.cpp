@@ -336,11 +336,56 @@ int cmd_bench(int argc, char** argv) {
     return 0;
 }
 
+/* Fixed-work timing for bench.py --impl reference: `warmup` untimed then `steps` timed steps,
+ * each step = `sample` positions (policy and/or value forwards, batch 1 each, like
+ * Network::benchmark) shared over `threads` pool threads. Prints one JSON line. */
+int cmd_steps(int argc, char** argv) {
+    if (argc < 8) { fprintf(stderr, "usage: steps <in.pos> <threads> <sample> <warmup> <steps> policy|value|both\n"); return 2; }
+    Positions ps = read_positions(argv[2]);
+    int threads = atoi(argv[3]), sample = atoi(argv[4]), warmup = atoi(argv[5]), steps = atoi(argv[6]);
+    std::string which = argv[7];
+    init_reference(threads);
+    double timed = 0.0;
+    for (int s = 0; s < warmup + steps; s++) {
+        std::atomic<int> next{0};
+        auto t0 = std::chrono::steady_clock::now();
+        ThreadGroup tg(thread_pool);
+        for (int t = 0; t < threads; t++) {
+            tg.add_task([&, s]() {
+                FastState empty_state;
+                empty_state.init_game(19, 7.5f);
+                Network::NNPlanes pp, vp;
+                volatile float sink = 0;
+                for (;;) {
+                    int k = next.fetch_add(1);
+                    if (k >= sample) break;
+                    int i = (s * sample + k) % ps.n;
+                    if (which != "value") {
+                        unpack(&ps.pol[(size_t)i * P], pp);
+                        auto r = Network::get_scored_moves_internal(&empty_state, pp, ps.rot[i]);
+                        sink = sink + r[0].first;
+                    }
+                    if (which != "policy") {
+                        unpack(&ps.val[(size_t)i * P], vp);
+                        sink = sink + Network::get_value_internal(&empty_state, vp, ps.rot[i]);
+                    }
+                }
+            });
+        }
+        tg.wait_all();
+        std::chrono::duration<double> el = std::chrono::steady_clock::now() - t0;
+        if (s >= warmup) timed += el.count();
+    }
+    printf("{\"positions\": %ld, \"seconds\": %.6f, \"pos_per_s\": %.3f, \"threads\": %d, \"sample\": %d, \"steps\": %d, \"which\": \"%s\", \"blas_core\": \"%s\"}\n",
+           (long)sample * steps, timed, (double)sample * steps / timed, threads, sample, steps, which.c_str(), openblas_get_corename());
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
     if (argc < 2) {
-        fprintf(stderr, "usage: ref_harness dump|planes|eval|layer|bench ...\n");
+        fprintf(stderr, "usage: ref_harness dump|planes|eval|layer|bench|steps ...\n");
         return 2;
     }
     std::string cmd = argv[1];
@@ -349,6 +394,7 @@ int main(int argc, char** argv) {
     if (cmd == "eval") return cmd_eval(argc, argv);
     if (cmd == "layer") return cmd_layer(argc, argv);
     if (cmd == "bench") return cmd_bench(argc, argv);
+    if (cmd == "steps") return cmd_steps(argc, argv);
     fprintf(stderr, "unknown command %s\n", cmd.c_str());
     return 2;
 }

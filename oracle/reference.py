@@ -103,3 +103,7 @@ def layer(kind, k, c_in, c_out, x, w, b) -> np.ndarray:
 
 def bench(pos_path, threads, seconds, which="both", **kw) -> dict:
     return json.loads(run(["bench", pos_path, threads, seconds, which], timeout=seconds * 4 + 120, **kw))
+
+
+def steps(pos_path, threads, sample, warmup, steps_, which="both", **kw) -> dict:
+    return json.loads(run(["steps", pos_path, threads, sample, warmup, steps_, which], timeout=3600, **kw))

@@ -1,0 +1,246 @@
+"""Parity of the CUDA path (through the C ABI, leela_b200/libleela_b200.so) against
+  - the reference's own outputs (tests/golden/*.npz, fp32 OpenBLAS path)  -> "tier B", model fidelity
+  - the plain-C oracle applying the same fp16 operand roundings             -> "tier A", kernel exactness
+
+Tolerances (stated from measurement on B200, synthetic weights with final-conv gain 2 —
+harsher than the real net):
+  layer 1 (binary inputs, fp16 weights)      : <= 1 fp16 ulp of the output
+  deeper layers vs same-rounding oracle      : <= 1.5e-2 abs (activations reach ~8, fp16 ulp 7.8e-3;
+                                               accumulation order flips last-bit roundings)
+  policy probability, per point              : <= 6e-3 abs (measured max 3.8e-3), mean <= 5e-5
+  value winrate                              : <= 6e-3 abs (measured max 3.1e-3)
+  top-1 move agreement                       : >= 97 %, every miss must be a near tie (< 6e-3)
+The reference is fp32 end to end; the B200 path keeps fp16 operands with fp32 accumulation.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_P = 6e-3
+TOL_V = 6e-3
+TEMP = 0.75
+
+
+@pytest.fixture(scope="module")
+def ev():
+    from leela_b200 import capi, synth
+    e = capi.Evaluator(policy=synth.policy_weights(), value=synth.value_weights())
+    yield e
+    e.close()
+
+
+def _top1_ok(got, want):
+    gi, wi = got.argmax(1), want.argmax(1)
+    agree = gi == wi
+    for i in np.nonzero(~agree)[0]:
+        assert abs(want[i, gi[i]] - want[i, wi[i]]) < TOL_P, f"position {i}: top-1 differs and is not a near tie"
+    return agree.mean()
+
+
+def test_policy_and_value_vs_reference(ev, ref_golden):
+    g = ref_golden
+    probs, win = ev.eval_both(g["policy_planes"], g["value_planes"], g["rotation"], float(g["softmax_temp"]))
+    dp = np.abs(probs - g["policy"])
+    assert dp.max() < TOL_P and dp.mean() < 5e-5
+    assert np.abs(win - g["value"]).max() < TOL_V
+    assert _top1_ok(probs, g["policy"]) >= 0.97
+    np.testing.assert_allclose(probs.sum(1), 1.0, atol=1e-4)
+
+
+def test_separate_entry_points_match_eval_both(ev, ref_golden):
+    g = ref_golden
+    probs, win = ev.eval_both(g["policy_planes"], g["value_planes"], g["rotation"], TEMP)
+    assert np.array_equal(ev.eval_policy(g["policy_planes"], g["rotation"], TEMP), probs)
+    assert np.array_equal(ev.eval_value(g["value_planes"], g["rotation"]), win)
+
+
+def test_edge_cases_vs_reference(ev, edge_golden):
+    g = edge_golden
+    probs, win = ev.eval_both(g["planes"], g["planes"], g["rotation"], float(g["softmax_temp"]))
+    assert np.abs(probs - g["policy"]).max() < TOL_P
+    assert np.abs(win - g["value"]).max() < TOL_V
+
+
+def test_vs_oracle_same_rounding(ev, ref_golden, oracle_nets):
+    from oracle import oracle
+    pn, vn = oracle_nets
+    g = ref_golden
+    sel = slice(0, 32)
+    probs, win = ev.eval_both(g["policy_planes"][sel], g["value_planes"][sel], g["rotation"][sel], TEMP)
+    pe = oracle.policy_forward(pn, g["policy_planes"][sel], g["rotation"][sel], TEMP, emulate=7)
+    ve = oracle.value_forward(vn, g["value_planes"][sel], g["rotation"][sel], emulate=7)
+    assert np.abs(probs - pe).max() < TOL_P and np.abs(probs - pe).mean() < 5e-5
+    assert np.abs(win - ve).max() < TOL_V
+
+
+@pytest.mark.parametrize("kind,n_layers", [(0, 1), (0, 2), (0, 3), (0, 12), (1, 1), (1, 2), (1, 11)])
+def test_trunk_layers_vs_oracle(ev, ref_golden, oracle_nets, kind, n_layers):
+    """Every distinct layer shape (5x5 32->96, 3x3 96->128, 128->128; 5x5 32->64, 3x3 64->64)
+    against the oracle's convolve<> with the same fp16 operand roundings."""
+    from oracle import oracle
+    g = ref_golden
+    net = oracle_nets[kind]
+    planes = (g["policy_planes"] if kind == 0 else g["value_planes"])[:3]
+    rot = g["rotation"][:3]
+    c_out = net.weights.convs[n_layers - 1].c_out
+    got = ev.debug_trunk(kind, planes, rot, n_layers, c_out)
+    for i in range(3):
+        want = oracle.trunk_activations(net, planes[i], int(rot[i]), emulate=7)[n_layers - 1]
+        if n_layers == 1:
+            ulp = np.maximum(np.abs(want), 2.0 ** -14) * 2.0 ** -10
+            assert (np.abs(got[i] - want) <= ulp).all()
+        else:
+            assert np.abs(got[i] - want).max() < 1.5e-2
+            assert np.abs(got[i] - want).mean() < 2e-3
+
+
+def test_launch_modes_bit_identical(ev, ref_golden):
+    """One launch per layer vs the single persistent dataflow launch: same arithmetic, same bits."""
+    g = ref_golden
+    args = (g["policy_planes"], g["value_planes"], g["rotation"], TEMP)
+    ev.set_option("trunk_mode", 0)
+    p0, v0 = ev.eval_both(*args)
+    ev.set_option("trunk_mode", 1)
+    p1, v1 = ev.eval_both(*args)
+    assert np.array_equal(p0, p1) and np.array_equal(v0, v1)
+
+
+def test_batch_and_slot_invariance(ev, ref_golden):
+    """A position's result does not depend on batch size, its slot, or chunking (tiles straddle
+    positions; 400 rows per position is not a multiple of the 256-row tile)."""
+    g = ref_golden
+    pp, vp, rot = g["policy_planes"], g["value_planes"], g["rotation"]
+    full_p, full_v = ev.eval_both(pp, vp, rot, TEMP)
+    for i in (0, 1, 37, 95):
+        p1, v1 = ev.eval_both(pp[i:i + 1], vp[i:i + 1], rot[i:i + 1], TEMP)
+        assert np.array_equal(p1[0], full_p[i]) and v1[0] == full_v[i]
+    perm = np.random.default_rng(3).permutation(96)
+    pp2, vv2 = ev.eval_both(pp[perm], vp[perm], rot[perm], TEMP)
+    assert np.array_equal(pp2, full_p[perm]) and np.array_equal(vv2, full_v[perm])
+    ev.set_option("max_batch", 7)
+    try:
+        p3, v3 = ev.eval_both(pp, vp, rot, TEMP)
+    finally:
+        ev.set_option("max_batch", 512)
+    assert np.array_equal(p3, full_p) and np.array_equal(v3, full_v)
+
+
+def test_deterministic(ev, ref_golden):
+    g = ref_golden
+    a = ev.eval_both(g["policy_planes"], g["value_planes"], g["rotation"], TEMP)
+    b = ev.eval_both(g["policy_planes"], g["value_planes"], g["rotation"], TEMP)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def _rotate_planes(planes, s):
+    """planes'[i] = planes[rotate_nn_idx(i, s)] — what the network sees under symmetry s."""
+    from oracle import oracle
+    idx = np.array([oracle.rotate_nn_idx(i, s) for i in range(361)])
+    return planes[:, idx]
+
+
+def test_rotation_kat_full_size(ev, bench_positions):
+    """Size-independent property at the full benchmark batch (1024 positions, chunked):
+    evaluating under symmetry s == evaluating the pre-rotated planes under s=0 and un-rotating
+    (rotate_nn_idx / rev_rotate_nn_idx semantics, Network.cpp:765-773, 820-823)."""
+    from oracle import oracle
+    g = bench_positions
+    pp, vp = g["policy_planes"], g["value_planes"]
+    n = pp.shape[0]
+    zero = np.zeros(n, np.uint8)
+    for s in (1, 5, 6):
+        rot = np.full(n, s, np.uint8)
+        p_s, v_s = ev.eval_both(pp, vp, rot, TEMP)
+        p_0, v_0 = ev.eval_both(_rotate_planes(pp, s), _rotate_planes(vp, s), zero, TEMP)
+        rev = np.array([oracle.rev_rotate_nn_idx(i, s) for i in range(361)])
+        assert np.array_equal(p_s, p_0[:, rev])
+        assert np.array_equal(v_s, v_0)
+        np.testing.assert_allclose(p_s.sum(1), 1.0, atol=1e-4)
+
+
+def test_average_all_as_microbatch(ev, ref_golden):
+    """AVERAGE_ALL (Network.cpp:643-667) = mean over the 8 symmetries as one 8-entry batch, then
+    EMPTY filter + ladder prune on the host; compared with the reference's API-level output."""
+    g = ref_golden
+    for i in range(g["policy_avg"].shape[0]):
+        rot = np.arange(8, dtype=np.uint8)
+        p, v = ev.eval_both(np.repeat(g["policy_planes"][i:i + 1], 8, 0), np.repeat(g["value_planes"][i:i + 1], 8, 0),
+                            rot, float(g["softmax_temp"]))
+        acc = p.sum(0) / np.float32(8)
+        empty = (g["policy_planes"][i] & 1).astype(bool)
+        ladder = ((g["policy_planes"][i] >> 25) & 1).astype(bool)
+        acc[ladder] = 0
+        want = g["policy_avg"][i]
+        assert np.abs(acc[empty] - want[empty]).max() < TOL_P
+        assert abs(v.mean() - g["value_avg"][i]) < TOL_V
+
+
+def test_softmax_temperature_is_runtime(ev, ref_golden, oracle_nets):
+    from oracle import oracle
+    g = ref_golden
+    sel = slice(0, 4)
+    for t in (1.0, 0.5):
+        got = ev.eval_policy(g["policy_planes"][sel], g["rotation"][sel], t)
+        want = oracle.policy_forward(oracle_nets[0], g["policy_planes"][sel], g["rotation"][sel], t)
+        assert np.abs(got - want).max() < 2 * TOL_P
+        np.testing.assert_allclose(got.sum(1), 1.0, atol=1e-4)
+
+
+def test_abi_misuse_returns_error_codes(ref_golden):
+    """n = 0, bad rotation, unfinalized net, unsupported stack: error codes, never a crash."""
+    from leela_b200 import capi, synth
+    from leela_b200.netdefs import Conv
+    g = ref_golden
+    e = capi.Evaluator()
+    with pytest.raises(capi.Lb2Error) as ei:
+        e.eval_policy(g["policy_planes"][:1], g["rotation"][:1])
+    assert ei.value.code == -3  # LB2_ERR_STATE: not finalized
+    e.push_net(capi.POLICY, synth.policy_weights())
+    assert e.eval_policy(g["policy_planes"][:0], g["rotation"][:0]).shape == (0, 361)
+    with pytest.raises(capi.Lb2Error) as ei:
+        e.eval_policy(g["policy_planes"][:2], np.array([0, 8], np.uint8))
+    assert ei.value.code == -1  # LB2_ERR_INVALID
+    with pytest.raises(capi.Lb2Error) as ei:
+        e.eval_policy(g["policy_planes"][:1], g["rotation"][:1], temp=0.0)
+    assert ei.value.code == -1
+    with pytest.raises(capi.Lb2Error) as ei:
+        e.eval_value(g["value_planes"][:1], g["rotation"][:1])
+    assert ei.value.code == -3
+    bad = synth.value_weights()
+    bad.convs = (Conv(3, 32, 64),) + tuple(bad.convs[1:])
+    bad.conv_w[0] = bad.conv_w[0][:, :, :3, :3]
+    with pytest.raises(capi.Lb2Error) as ei:
+        e.push_net(capi.VALUE, bad)
+    assert ei.value.code == -5  # LB2_ERR_UNSUPPORTED
+    e.close()
+
+
+def test_async_submit_coalesces(ev, ref_golden):
+    """lb2_submit_* from several threads + lb2_drain (replaces forward(cb) + join_outstanding_cb)."""
+    import ctypes as C
+    import threading
+    from leela_b200 import capi
+    g = ref_golden
+    want_p, want_v = ev.eval_both(g["policy_planes"], g["value_planes"], g["rotation"], TEMP)
+    n = 48
+    outs_p = [np.zeros((1, 361), np.float32) for _ in range(n)]
+    outs_v = [np.zeros(1, np.float32) for _ in range(n)]
+    status = []
+    cb = capi.CALLBACK(lambda user, st: status.append(st))
+    L = capi.load()
+
+    def worker(lo, hi):
+        for i in range(lo, hi):
+            pp = np.ascontiguousarray(g["policy_planes"][i:i + 1]); vp = np.ascontiguousarray(g["value_planes"][i:i + 1])
+            r = np.ascontiguousarray(g["rotation"][i:i + 1])
+            capi.check(L.lb2_submit_policy(ev.ctx, pp.ctypes.data, r.ctypes.data, 1, TEMP, outs_p[i].ctypes.data, cb, None))
+            capi.check(L.lb2_submit_value(ev.ctx, vp.ctypes.data, r.ctypes.data, 1, outs_v[i].ctypes.data, cb, None))
+
+    ts = [threading.Thread(target=worker, args=(k * 12, (k + 1) * 12)) for k in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    ev.drain()
+    assert len(status) == 2 * n and all(s == 0 for s in status)
+    for i in range(n):
+        assert np.array_equal(outs_p[i][0], want_p[i]) and outs_v[i][0] == want_v[i]
