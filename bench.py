@@ -184,7 +184,9 @@ def run_ours(args):
     d_probs = torch.empty((B, 361), dtype=torch.float32, device=dev)
     d_win = torch.empty((B,), dtype=torch.float32, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    stream = torch.cuda.current_stream(dev)
+    # a dedicated (non-default) stream: kernels, L2 flush and the timing events all go on it
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
 
     def step(i):
         s = i % n_sets

@@ -77,7 +77,8 @@ struct TrunkLayerDev {
 struct NetDev {
     std::vector<TrunkLayerDev> trunk;
     int head_c_in = 0;
-    float *head_w = nullptr, *head_b = nullptr;
+    float *head_wt = nullptr, *head_b = nullptr;  // final conv weights transposed to [9 taps][c_in]
+    float* zbuf = nullptr;                        // fused-head partial sums [2][9][rows3]
     int hidden = 0;
     float *ip1_wt = nullptr, *ip1_b = nullptr, *ip2_w = nullptr, *ip2_b = nullptr;
     // workspace
@@ -204,7 +205,10 @@ int upload_net(const lb2_net* net, NetDev* nd) {
     }
     const HostConv& h = net->convs.back();
     nd->head_c_in = h.c_in;
-    int rc = upload(&nd->head_w, h.w.data(), h.w.size() * sizeof(float));
+    std::vector<float> hwt((size_t)9 * h.c_in);
+    for (int c = 0; c < h.c_in; c++)
+        for (int t = 0; t < 9; t++) hwt[(size_t)t * h.c_in + c] = h.w[(size_t)c * 9 + t];
+    int rc = upload(&nd->head_wt, hwt.data(), hwt.size() * sizeof(float));
     if (rc) return rc;
     rc = upload(&nd->head_b, h.b.data(), sizeof(float));
     if (rc) return rc;
@@ -244,7 +248,8 @@ int make_act_tmap(CUtensorMap* tm, __half* base, int rows, int chunks, int halo)
 
 void free_workspace(NetDev* nd) {
     cudaFree(nd->planes); cudaFree(nd->x0); cudaFree(nd->act[0]); cudaFree(nd->act[1]);
-    cudaFree(nd->out); cudaFree(nd->flags);
+    cudaFree(nd->out); cudaFree(nd->flags); cudaFree(nd->zbuf);
+    nd->zbuf = nullptr;
     nd->planes = nullptr; nd->x0 = nullptr; nd->act[0] = nd->act[1] = nullptr; nd->out = nullptr; nd->flags = nullptr;
     nd->cap = 0;
 }
@@ -265,6 +270,7 @@ int ensure_workspace(NetDev* nd, int kind, int cap) {
     CU_TRY(cudaMemset(nd->act[1], 0, act_bytes));
     const size_t out_elems = kind == LB2_POLICY ? (size_t)cap * lb2::kPoints : (size_t)cap;
     CU_TRY(cudaMalloc(&nd->out, out_elems * sizeof(float)));
+    CU_TRY(cudaMalloc(&nd->zbuf, (size_t)18 * nd->rows3 * sizeof(float)));
     nd->flags_stride = nd->rows5 / lb2::kTileRows + 1;
     CU_TRY(cudaMalloc(&nd->flags, (size_t)lb2::kMaxJobs * nd->flags_stride * sizeof(uint32_t)));
     CU_TRY(cudaMemset(nd->flags, 0, (size_t)lb2::kMaxJobs * nd->flags_stride * sizeof(uint32_t)));
@@ -339,6 +345,12 @@ JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2]) {
             J.wpk = t.wpk;
             J.bias = t.bias;
             J.flags = nd.flags + (size_t)l * nd.flags_stride;
+            if (l + 1 == nd.trunk.size() && limit_layers[k] > (int)nd.trunk.size()) {
+                // whole net: fold the final 3x3 conv to one channel into this layer's epilogue
+                J.head_taps = 9;
+                J.head_w = nd.head_wt;
+                J.zbuf = nd.zbuf;
+            }
             prev_job[k] = (int)pl.jobs.size();
             pl.jobs.push_back(J);
             pl.round_of.push_back((int)l);
@@ -434,14 +446,13 @@ int eval_on_device(lb2_ctx* ctx, DeviceState* d, const uint32_t* d_pol, const ui
     if (rc) return rc;
     if (run[0]) {
         NetDev& nd = d->net[0];
-        CU_TRY(lb2::launch_policy_head(pl.last_act[0], nd.rows3, nd.head_c_in, nd.head_w, nd.head_b, d_rot, n, temp,
-                                       d_probs, st));
+        CU_TRY(lb2::launch_policy_head(nd.zbuf, nd.rows3, nd.head_b, d_rot, n, temp, d_probs, st));
         ctx->launches++;
     }
     if (run[1]) {
         NetDev& nd = d->net[1];
-        CU_TRY(lb2::launch_value_head(pl.last_act[1], nd.rows3, nd.head_c_in, nd.head_w, nd.head_b, nd.ip1_wt, nd.ip1_b,
-                                      nd.hidden, nd.ip2_w, nd.ip2_b, n, d_win, st));
+        CU_TRY(lb2::launch_value_head(nd.zbuf, nd.rows3, nd.head_b, nd.ip1_wt, nd.ip1_b, nd.hidden, nd.ip2_w, nd.ip2_b, n,
+                                      d_win, st));
         ctx->launches++;
     }
     return LB2_OK;
@@ -657,7 +668,7 @@ void lb2_destroy(lb2_ctx* ctx) {
         for (int k = 0; k < 2; k++) {
             NetDev& nd = d.net[k];
             for (auto& t : nd.trunk) { cudaFree(t.wpk); cudaFree(t.bias); }
-            cudaFree(nd.head_w); cudaFree(nd.head_b); cudaFree(nd.ip1_wt); cudaFree(nd.ip1_b);
+            cudaFree(nd.head_wt); cudaFree(nd.head_b); cudaFree(nd.ip1_wt); cudaFree(nd.ip1_b);
             cudaFree(nd.ip2_w); cudaFree(nd.ip2_b);
             free_workspace(&nd);
         }

@@ -67,17 +67,12 @@ __global__ void __launch_bounds__(256) expand_planes_kernel(const uint32_t* __re
 //   one bulk copy). For every tap the MMA reads the SAME A slab at a row offset
 //   dy*S+dx — the im2col matrix is never materialised and each activation byte is fetched
 //   from L2 once per item instead of k*k times.
+//   Warps: 0 = TMA producer, 1 = MMA issuer (+ TMEM owner), 2..9 = epilogue (warp w reads TMEM
+//   lane quadrant w%4 and column half (w-2)/4).
 // ------------------------------------------------------------------------------------------
-struct TapGroups {
-    int n;
-    int begin[3], end[3];
-};
-__device__ __forceinline__ TapGroups tap_groups(int ksize) {
-    TapGroups g;
-    if (ksize == 3) { g.n = 1; g.begin[0] = 0; g.end[0] = 9; g.begin[1] = g.end[1] = g.begin[2] = g.end[2] = 0; }
-    else { g.n = 3; g.begin[0] = 0; g.end[0] = 9; g.begin[1] = 9; g.end[1] = 17; g.begin[2] = 17; g.end[2] = 25; }
-    return g;
-}
+__device__ __forceinline__ int n_tap_groups(int ksize) { return ksize == 3 ? 1 : 3; }
+__device__ __forceinline__ int tap_group_begin(int g) { return g == 0 ? 0 : (g == 1 ? 9 : 17); }
+__device__ __forceinline__ int tap_group_end(int ksize, int g) { return ksize == 3 ? 9 : (g == 0 ? 9 : (g == 1 ? 17 : 25)); }
 
 __device__ __forceinline__ void wait_dependencies(const LayerJob& J, const LayerJob* jobs, int tile, uint32_t epoch) {
     const int r_lo = tile * kTileRows - J.halo;
@@ -102,6 +97,14 @@ __device__ __forceinline__ void wait_dependencies(const LayerJob& J, const Layer
     fence_proxy_async();  // order the TMA (async proxy) reads after the acquire
 }
 
+// ELU(alpha = 1): v > 0 ? v : exp(v) - 1, written branch-free: max(v,0) + min(exp(v) - 1, 0).
+__device__ __forceinline__ float elu_fast(float v) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 1.4426950408889634f));  // inf for large v is clamped by the min
+    e -= 1.0f;
+    return fmaxf(v, 0.0f) + fminf(e, 0.0f);
+}
+
 __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_constant__ TrunkParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -109,6 +112,8 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
     uint64_t* tfull_bar = empty_bar + kStages;   // [2] accumulator ready   (MMA -> epilogue)
     uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulator drained (epilogue -> MMA)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* bias_s = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);  // [2][128]
+    float* headw_all = bias_s + 2 * 128;                                           // [2][9][128]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -116,7 +121,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 127u) __trap();  // TMA destinations need 128-byte alignment
         for (int i = 0; i < kStages; i++) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 4); }
+        for (int i = 0; i < 2; i++) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, kEpilogueWarps); }
         fence_mbar_init();
         fence_proxy_async_smem();
         for (int i = 0; i < kMaxTensorMaps; i++) tma_prefetch_desc(&P.tmaps[i]);
@@ -141,11 +146,11 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                 const int rows_halo = kTileRows + 2 * J.halo;
                 const uint32_t a_bytes = rows_halo * 32;
                 const int row0_8 = (tile * kTileRows - J.halo) / 8;  // exact: both multiples of 8
-                const TapGroups G = tap_groups(J.ksize);
+                const int ng = n_tap_groups(J.ksize);
                 const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(J.wpk);
                 for (int s = 0; s < J.n_slabs; s++) {
-                    for (int g = 0; g < G.n; g++) {
-                        const uint32_t b_bytes = (G.end[g] - G.begin[g]) * J.n_out * 32;
+                    for (int g = 0; g < ng; g++) {
+                        const uint32_t b_bytes = (tap_group_end(J.ksize, g) - tap_group_begin(g)) * J.n_out * 32;
                         mbar_wait(empty_bar + stage, phase ^ 1);
                         uint8_t* sa = smem + stage * kStageBytes;
                         mbar_arrive_expect_tx(full_bar + stage, a_bytes + b_bytes);
@@ -159,63 +164,97 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0; int j = 0; uint32_t it = 0;
-            for (int q = P.item_begin + blockIdx.x; q < P.item_end; q += gridDim.x, it++) {
-                while (q >= jobs[j].item_base + jobs[j].n_items) j++;
-                const LayerJob J = jobs[j];
-                const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-                mbar_wait(tempty_bar + acc, acc_phase ^ 1);
-                tc_fence_after_sync();
-                const uint32_t idesc = umma_idesc_f16(128, J.n_out);
-                const int rows_halo = kTileRows + 2 * J.halo;
-                uint32_t lbo_a = rows_halo * 16, lbo_b = J.n_out * 16, sbo = 128;
-                if (P.debug_flags & 1) { sbo = lbo_a; lbo_a = 128; }
-                const int pad = J.ksize >> 1;
-                const TapGroups G = tap_groups(J.ksize);
-                const uint32_t d0 = tmem_base + (acc * 2 + 0) * 128;
-                const uint32_t d1 = tmem_base + (acc * 2 + 1) * 128;
-                bool first = true;
-                for (int s = 0; s < J.n_slabs; s++) {
-                    for (int g = 0; g < G.n; g++) {
-                        mbar_wait(full_bar + stage, phase);
-                        tc_fence_after_sync();
+        // The whole warp walks the pipeline; one elected lane issues the tcgen05 instructions.
+        int stage = 0; uint32_t phase = 0; int j = 0; uint32_t it = 0;
+        for (int q = P.item_begin + blockIdx.x; q < P.item_end; q += gridDim.x, it++) {
+            while (q >= jobs[j].item_base + jobs[j].n_items) j++;
+            const LayerJob& J = jobs[j];
+            const int ksize = J.ksize, n_out = J.n_out, n_slabs = J.n_slabs, halo = J.halo;
+            const int S = (P.debug_flags & 2) ? 0 : J.S, DX = (P.debug_flags & 2) ? 0 : 1;
+            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+            mbar_wait(tempty_bar + acc, acc_phase ^ 1);
+            tc_fence_after_sync();
+            const uint32_t idesc = umma_idesc_f16(128, n_out);
+            const int rows_halo = kTileRows + 2 * halo;
+            // descriptor = hi32 (SBO = 128 B, version 1) : lo32 (LBO << 16 | start address >> 4)
+            const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+            const uint32_t a_lo_base = ((uint32_t)(rows_halo * 16) >> 4) << 16;
+            const uint32_t b_lo_base = ((uint32_t)(n_out * 16) >> 4) << 16;
+            const uint32_t b_step = (uint32_t)(n_out * 32) >> 4;  // one tap of B, in 16-byte units
+            const uint32_t d0 = tmem_base + (acc * 2 + 0) * 128;
+            const uint32_t d1 = tmem_base + (acc * 2 + 1) * 128;
+            const int ng = n_tap_groups(ksize);
+            const int pad = ksize >> 1;
+            uint32_t accumulate = 0;
+            for (int s = 0; s < n_slabs; s++) {
+                for (int g = 0; g < ng; g++) {
+                    mbar_wait(full_bar + stage, phase);
+                    tc_fence_after_sync();
+                    __syncwarp();
+                    if (elect_one()) {
                         const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
-                        const uint32_t b_addr = a_addr + kASlabBytes;
-                        for (int t = G.begin[g]; t < G.end[g]; t++) {
-                            const int kr = t / J.ksize, kc = t - kr * J.ksize;
-                            const int off = (kr - pad) * J.S + (kc - pad);
-                            const uint64_t bdesc =
-                                (P.debug_flags & 1)
-                                    ? umma_desc_kmajor_noswizzle(b_addr + (t - G.begin[g]) * J.n_out * 32, 128, lbo_b)
-                                    : umma_desc_kmajor_noswizzle(b_addr + (t - G.begin[g]) * J.n_out * 32, lbo_b, 128);
-                            const uint32_t a0 = a_addr + (J.halo + off) * 16;
-                            umma_f16(d0, umma_desc_kmajor_noswizzle(a0, lbo_a, sbo), bdesc, idesc, first ? 0u : 1u);
-                            umma_f16(d1, umma_desc_kmajor_noswizzle(a0 + 128 * 16, lbo_a, sbo), bdesc, idesc,
-                                     first ? 0u : 1u);
-                            first = false;
+                        // (address of row `halo` of the A slab) >> 4; a tap shifts it by dy*S+dx rows
+                        const uint32_t a16 = (a_addr >> 4) + halo;
+                        uint32_t b16 = (a_addr + kASlabBytes) >> 4;
+                        if (ksize == 3) {
+#pragma unroll
+                            for (int t = 0; t < 9; t++) {
+                                const int off = (t / 3 - 1) * S + (t % 3 - 1) * DX;
+                                const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo_base | (b16 & 0x3FFFu));
+                                const uint32_t a0 = a16 + off;
+                                umma_f16(d0, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo_base | (a0 & 0x3FFFu)), bdesc, idesc, accumulate);
+                                umma_f16(d1, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo_base | ((a0 + 128) & 0x3FFFu)), bdesc, idesc, accumulate);
+                                accumulate = 1;
+                                b16 += b_step;
+                            }
+                        } else {
+                            const int t0 = tap_group_begin(g), t1 = tap_group_end(ksize, g);
+                            int kr = t0 / 5, kc = t0 - kr * 5;
+                            for (int t = t0; t < t1; t++) {
+                                const int off = (kr - pad) * S + (kc - pad) * DX;
+                                const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo_base | (b16 & 0x3FFFu));
+                                const uint32_t a0 = a16 + off;
+                                umma_f16(d0, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo_base | (a0 & 0x3FFFu)), bdesc, idesc, accumulate);
+                                umma_f16(d1, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo_base | ((a0 + 128) & 0x3FFFu)), bdesc, idesc, accumulate);
+                                accumulate = 1;
+                                b16 += b_step;
+                                if (++kc == 5) { kc = 0; kr++; }
+                            }
                         }
                         umma_commit(empty_bar + stage);  // frees the smem stage when these MMAs finish
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(tfull_bar + acc);  // accumulator complete -> epilogue
             }
+            if (elect_one()) umma_commit(tfull_bar + acc);  // accumulator complete -> epilogue
+            __syncwarp();
         }
     } else {
         // ================================ epilogue ====================================
-        const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+        const int ew = warp - 2;          // 0..7
+        const int quad = warp & 3;        // TMEM lane quadrant this warp may read
+        const int half = ew >> 2;         // which half of the output channels
+        const int etid = threadIdx.x - 64;  // 0..255
         int j = 0; uint32_t it = 0;
         for (int q = P.item_begin + blockIdx.x; q < P.item_end; q += gridDim.x, it++) {
             while (q >= jobs[j].item_base + jobs[j].n_items) j++;
             const LayerJob& J = jobs[j];
             const int tile = q - J.item_base;
             const int S = J.S, SS = S * S, n_out = J.n_out, chunk_rows = J.out_chunk_rows;
-            const float* __restrict__ bias = J.bias;
+            const int head = J.head_taps;
             __half* __restrict__ out = J.out;
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+            // stage this job's bias (and fused-head weights) in smem while the MMAs run
+            float* bs = bias_s + acc * 128;
+            if (etid < n_out) bs[etid] = J.bias[etid];
+            float* headw_s = headw_all + acc * (9 * 128);
+            if (head) for (int i = etid; i < 9 * n_out; i += 256) headw_s[i] = J.head_w[i];
+            named_bar_sync(1, 256);
             mbar_wait(tfull_bar + acc, acc_phase);
             tc_fence_after_sync();
+            const int cols = n_out >> 1;          // columns handled by this warp
+            const int col0 = half * cols;
 #pragma unroll 1
             for (int h = 0; h < 2; h++) {
                 const int row = tile * kTileRows + h * 128 + quad * 32 + lane;
@@ -225,29 +264,60 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                 int out_row = row;
                 bool store = true;
                 if (J.remap) { out_row = pos * 400 + y * 20 + x; store = valid && pos < J.n_pos; }
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (acc * 2 + h) * 128;
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (acc * 2 + h) * 128 + col0;
+                float z[9];
+#pragma unroll
+                for (int t = 0; t < 9; t++) z[t] = 0.0f;
 #pragma unroll 1
-                for (int cc = 0; cc < n_out / 32; cc++) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(taddr + cc * 32, r);
+                for (int cc = 0; cc < cols; cc += 16) {
+                    uint32_t r[16];
+                    tmem_ld_32x16(taddr + cc, r);
                     tmem_ld_wait();
-                    uint32_t pk[16];
+                    float v[16];
+                    if (!(P.debug_flags & 4)) {
 #pragma unroll
-                    for (int e = 0; e < 16; e++) {
-                        float v0 = __uint_as_float(r[2 * e]) + __ldg(bias + cc * 32 + 2 * e);
-                        float v1 = __uint_as_float(r[2 * e + 1]) + __ldg(bias + cc * 32 + 2 * e + 1);
-                        v0 = valid ? elu1(v0) : 0.0f;
-                        v1 = valid ? elu1(v1) : 0.0f;
-                        __half2 hh = __floats2half2_rn(v0, v1);
-                        pk[e] = *reinterpret_cast<uint32_t*>(&hh);
-                    }
-                    if (store) {
-#pragma unroll
-                        for (int c8 = 0; c8 < 4; c8++) {
-                            uint4 v = make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
-                            *reinterpret_cast<uint4*>(out + ((size_t)(cc * 4 + c8) * chunk_rows + out_row) * 8) = v;
+                        for (int e = 0; e < 16; e += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(bs + col0 + cc + e);
+                            v[e + 0] = elu_fast(__uint_as_float(r[e + 0]) + b4.x);
+                            v[e + 1] = elu_fast(__uint_as_float(r[e + 1]) + b4.y);
+                            v[e + 2] = elu_fast(__uint_as_float(r[e + 2]) + b4.z);
+                            v[e + 3] = elu_fast(__uint_as_float(r[e + 3]) + b4.w);
                         }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; e++) v[e] = __uint_as_float(r[e]);
                     }
+                    if (head) {
+                        // fused 1-channel 3x3 head: z[t] += sum_c w[t][c] * v[c]  (fp32, unrounded v)
+#pragma unroll
+                        for (int t = 0; t < 9; t++) {
+                            const float* wt = headw_s + t * n_out + col0 + cc;
+#pragma unroll
+                            for (int e = 0; e < 16; e += 4) {
+                                const float4 w4 = *reinterpret_cast<const float4*>(wt + e);
+                                z[t] = fmaf(v[e + 0], w4.x, z[t]);
+                                z[t] = fmaf(v[e + 1], w4.y, z[t]);
+                                z[t] = fmaf(v[e + 2], w4.z, z[t]);
+                                z[t] = fmaf(v[e + 3], w4.w, z[t]);
+                            }
+                        }
+                    } else if (store) {
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int e = 0; e < 8; e++) {
+                            __half2 hh = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                            pk[e] = valid ? *reinterpret_cast<uint32_t*>(&hh) : 0u;
+                        }
+                        const int c8 = (col0 + cc) >> 3;
+                        *reinterpret_cast<uint4*>(out + ((size_t)c8 * chunk_rows + out_row) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4*>(out + ((size_t)(c8 + 1) * chunk_rows + out_row) * 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    }
+                }
+                if (head) {
+                    // partial sums of this channel half: zbuf[half][t][row]; padding rows contribute 0
+                    float* zb = J.zbuf + (size_t)half * 9 * chunk_rows + out_row;
+#pragma unroll
+                    for (int t = 0; t < 9; t++) zb[(size_t)t * chunk_rows] = valid ? z[t] : 0.0f;
                 }
             }
             // accumulator drained: hand it back to the MMA warp
@@ -256,8 +326,8 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             if (lane == 0) mbar_arrive(tempty_bar + acc);
             if (P.use_flags) {
                 __threadfence();
-                named_bar_sync(1, 128);
-                if (threadIdx.x == 64) {
+                named_bar_sync(2, 256);
+                if (etid == 0) {
                     fence_proxy_async();  // generic-proxy stores -> visible to other CTAs' TMA loads
                     st_release_gpu(J.flags + tile, P.epoch);
                 }
@@ -271,28 +341,17 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------
-// policy head: one CTA per position. conv C->1 (3x3, fp32 weights) + bias + ELU, softmax with
-// temperature over the 361 points, un-rotate.
+// heads. The 3x3 conv to one channel was folded into the last trunk layer's epilogue as per-tap
+// partial sums z[half][t][row]; what is left is a 9-point gather per board point.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float head_conv_pixel(const __half* __restrict__ act, int chunk_rows, int c_in,
-                                                 const float* __restrict__ w_s /*[9][c_in]*/, int base_row, int y,
-                                                 int x) {
+__device__ __forceinline__ float head_gather(const float* __restrict__ zbuf, int chunk_rows, int base_row, int y, int x) {
     float acc = 0.0f;
-#pragma unroll 1
-    for (int t = 0; t < 9; t++) {
-        const int dy = t / 3 - 1, dx = t % 3 - 1;
-        const int row = base_row + (y + dy) * 20 + (x + dx);
-        if (row < 0) continue;  // above the first position: implicit zero padding
-        const float* wt = w_s + t * c_in;
-        for (int c8 = 0; c8 < c_in / 8; c8++) {
-            const uint4 v = *reinterpret_cast<const uint4*>(act + ((size_t)c8 * chunk_rows + row) * 8);
-            const __half2* hp = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const float2 f = __half22float2(hp[e]);
-                acc = fmaf(f.x, wt[c8 * 8 + 2 * e], acc);
-                acc = fmaf(f.y, wt[c8 * 8 + 2 * e + 1], acc);
-            }
+    for (int t = 0; t < 9; t++) {
+        const int row = base_row + (y + t / 3 - 1) * 20 + (x + t % 3 - 1);
+        if (row >= 0) {  // rows above the first position are implicit zero padding
+            acc += zbuf[(size_t)t * chunk_rows + row];
+            acc += zbuf[(size_t)(9 + t) * chunk_rows + row];
         }
     }
     return acc;
@@ -307,27 +366,20 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-__global__ void __launch_bounds__(384) policy_head_kernel(const __half* __restrict__ act, int chunk_rows, int c_in,
-                                                          const float* __restrict__ w /*[c_in][3][3]*/,
+// policy head: one CTA per position. logit = ELU(b + conv), softmax with temperature over the
+// 361 points (Network.cpp:450-469), un-rotate (Network.cpp:820-823).
+__global__ void __launch_bounds__(384) policy_head_kernel(const float* __restrict__ zbuf, int chunk_rows,
                                                           const float* __restrict__ bias,
                                                           const uint8_t* __restrict__ rotation, float temp,
                                                           float* __restrict__ probs) {
-    extern __shared__ float hs[];
-    float* w_s = hs;                  // [9][c_in]
-    float* sm = hs + 9 * c_in;        // [361]
+    __shared__ float sm[kPoints];
     __shared__ float red[12];
     const int pos = blockIdx.x, tid = threadIdx.x;
-    for (int i = tid; i < 9 * c_in; i += blockDim.x) {
-        const int t = i / c_in, c = i - t * c_in;
-        w_s[i] = w[c * 9 + t];
-    }
-    __syncthreads();
     float logit = -INFINITY;
     if (tid < kPoints) {
         const int y = tid / kBoard, x = tid - y * kBoard;
-        logit = elu1(bias[0] + head_conv_pixel(act, chunk_rows, c_in, w_s, pos * 400, y, x));
+        logit = elu1(bias[0] + head_gather(zbuf, chunk_rows, pos * 400, y, x));
     }
-    // softmax(x / T): p = exp(x/T - max/T) / sum  (Network.cpp:450-469)
     float m = warp_max(logit);
     if ((tid & 31) == 0) red[tid >> 5] = m;
     __syncthreads();
@@ -345,47 +397,42 @@ __global__ void __launch_bounds__(384) policy_head_kernel(const __half* __restri
     if (tid < kPoints) probs[(size_t)pos * kPoints + tid] = sm[rev_rotate_idx(tid, rotation[pos] & 7)];
 }
 
-// ------------------------------------------------------------------------------------------
 // value head: kValueGroup positions per CTA so the 361xH inner-product matrix is read once per
-// group. conv C->1 + ELU -> v[361]; h = ELU(W1 v + b1); out = (1 + tanh(w2.h + b2)) / 2.
-// ------------------------------------------------------------------------------------------
-constexpr int kValueGroup = 4;
+// group. v = ELU(b + conv) [361]; h = ELU(W1 v + b1); out = (1 + tanh(w2.h + b2)) / 2.
+constexpr int kValueGroup = 8;
 
-__global__ void __launch_bounds__(256) value_head_kernel(const __half* __restrict__ act, int chunk_rows, int c_in,
-                                                         const float* __restrict__ w, const float* __restrict__ bias,
+__global__ void __launch_bounds__(256) value_head_kernel(const float* __restrict__ zbuf, int chunk_rows,
+                                                         const float* __restrict__ bias,
                                                          const float* __restrict__ ip1_wt /*[361][hidden]*/,
                                                          const float* __restrict__ ip1_b, int hidden,
                                                          const float* __restrict__ ip2_w, const float* __restrict__ ip2_b,
                                                          int n, float* __restrict__ winrate) {
     extern __shared__ float hs[];
-    float* w_s = hs;                              // [9][c_in]
-    float* v_s = w_s + 9 * c_in;                  // [G][361]
+    float* v_s = hs;                              // [361][G]  (position fastest: float4 broadcast reads)
     float* h_s = v_s + kValueGroup * kPoints;     // [G][hidden]
     const int tid = threadIdx.x;
     const int pos0 = blockIdx.x * kValueGroup;
-    for (int i = tid; i < 9 * c_in; i += blockDim.x) {
-        const int t = i / c_in, c = i - t * c_in;
-        w_s[i] = w[c * 9 + t];
-    }
-    __syncthreads();
     for (int i = tid; i < kValueGroup * kPoints; i += blockDim.x) {
         const int g = i / kPoints, p = i - g * kPoints;
         float v = 0.0f;
         if (pos0 + g < n) {
             const int y = p / kBoard, x = p - y * kBoard;
-            v = elu1(bias[0] + head_conv_pixel(act, chunk_rows, c_in, w_s, (pos0 + g) * 400, y, x));
+            v = elu1(bias[0] + head_gather(zbuf, chunk_rows, (pos0 + g) * 400, y, x));
         }
-        v_s[i] = v;
+        v_s[p * kValueGroup + g] = v;
     }
     __syncthreads();
     for (int o = tid; o < hidden; o += blockDim.x) {
         float a[kValueGroup];
 #pragma unroll
         for (int g = 0; g < kValueGroup; g++) a[g] = 0.0f;
+#pragma unroll 4
         for (int i = 0; i < kPoints; i++) {
             const float wv = ip1_wt[(size_t)i * hidden + o];
-#pragma unroll
-            for (int g = 0; g < kValueGroup; g++) a[g] = fmaf(wv, v_s[g * kPoints + i], a[g]);
+            const float4 v0 = *reinterpret_cast<const float4*>(v_s + i * kValueGroup);
+            const float4 v1 = *reinterpret_cast<const float4*>(v_s + i * kValueGroup + 4);
+            a[0] = fmaf(wv, v0.x, a[0]); a[1] = fmaf(wv, v0.y, a[1]); a[2] = fmaf(wv, v0.z, a[2]); a[3] = fmaf(wv, v0.w, a[3]);
+            a[4] = fmaf(wv, v1.x, a[4]); a[5] = fmaf(wv, v1.y, a[5]); a[6] = fmaf(wv, v1.z, a[6]); a[7] = fmaf(wv, v1.w, a[7]);
         }
 #pragma unroll
         for (int g = 0; g < kValueGroup; g++) h_s[g * hidden + o] = elu1(a[g] + ip1_b[o]);
@@ -428,19 +475,18 @@ cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, cudaS
     return cudaLaunchKernelEx(&cfg, trunk_kernel, p);
 }
 
-cudaError_t launch_policy_head(const __half* act, int chunk_rows, int c_in, const float* w, const float* bias,
-                               const uint8_t* rotation, int n, float temp, float* probs, cudaStream_t st) {
-    const size_t smem = (9 * c_in + kPoints) * sizeof(float);
-    policy_head_kernel<<<n, 384, smem, st>>>(act, chunk_rows, c_in, w, bias, rotation, temp, probs);
+cudaError_t launch_policy_head(const float* zbuf, int chunk_rows, const float* bias, const uint8_t* rotation, int n,
+                               float temp, float* probs, cudaStream_t st) {
+    policy_head_kernel<<<n, 384, 0, st>>>(zbuf, chunk_rows, bias, rotation, temp, probs);
     return cudaGetLastError();
 }
 
-cudaError_t launch_value_head(const __half* act, int chunk_rows, int c_in, const float* w, const float* bias,
-                              const float* ip1_wt, const float* ip1_b, int hidden, const float* ip2_w,
-                              const float* ip2_b, int n, float* winrate, cudaStream_t st) {
-    const size_t smem = (9 * c_in + kValueGroup * kPoints + kValueGroup * hidden) * sizeof(float);
-    value_head_kernel<<<(n + kValueGroup - 1) / kValueGroup, 256, smem, st>>>(act, chunk_rows, c_in, w, bias, ip1_wt,
-                                                                             ip1_b, hidden, ip2_w, ip2_b, n, winrate);
+cudaError_t launch_value_head(const float* zbuf, int chunk_rows, const float* bias, const float* ip1_wt,
+                              const float* ip1_b, int hidden, const float* ip2_w, const float* ip2_b, int n,
+                              float* winrate, cudaStream_t st) {
+    const size_t smem = (kValueGroup * kPoints + kValueGroup * hidden) * sizeof(float);
+    value_head_kernel<<<(n + kValueGroup - 1) / kValueGroup, 256, smem, st>>>(zbuf, chunk_rows, bias, ip1_wt, ip1_b, hidden,
+                                                                             ip2_w, ip2_b, n, winrate);
     return cudaGetLastError();
 }
 

@@ -25,8 +25,10 @@ constexpr int kMaxHalo = 48;    // 5x5 conv in S=21 space needs 2*21+2 = 44 -> 4
 constexpr int kASlabBytes = (kTileRows + 2 * kMaxHalo) * 32;  // rows x 16 ch x fp16
 constexpr int kBBlockBytes = 9 * 128 * 32;                    // up to 9 taps x N<=128 x 16 ch x fp16
 constexpr int kStageBytes = kASlabBytes + kBBlockBytes;       // 48,128
-constexpr int kTrunkThreads = 192;  // warp0 TMA producer, warp1 MMA issuer, warps2-5 epilogue
-constexpr int kTrunkSmemBytes = kStages * kStageBytes + 256;
+constexpr int kEpilogueWarps = 8;
+constexpr int kTrunkThreads = 64 + 32 * kEpilogueWarps;  // warp0 TMA producer, warp1 MMA issuer, warps2-9 epilogue
+// stages | mbarriers + TMEM slot (256 B) | bias [2][128] f32 | fused-head weights [2][9][128] f32
+constexpr int kTrunkSmemBytes = kStages * kStageBytes + 256 + 2 * 128 * 4 + 2 * 9 * 128 * 4;
 constexpr int kMaxTensorMaps = 6;
 constexpr int kMaxJobs = 32;
 
@@ -46,12 +48,14 @@ struct LayerJob {
     int32_t dep_n_items;     // that job's item count
     int32_t n_pos;           // positions in the batch
     int32_t out_chunk_rows;  // rows per chunk plane of the output buffer
-    int32_t head_taps;       // >0: fused 1-channel head, number of taps (reserved)
+    int32_t head_taps;       // 9: the net's final 3x3 conv to 1 channel is fused into this job's epilogue
     int32_t pad_;
     const __half* wpk;       // packed weights: per (slab, tap group): [tap][2 chunks][n_out][8]
     const float* bias;       // [n_out]
     __half* out;             // output activation buffer
     uint32_t* flags;         // [n_items] completion flags (value = launch epoch)
+    const float* head_w;     // fused head weights [9 taps][n_out] fp32
+    float* zbuf;             // fused head output [2 channel halves][9 taps][out_chunk_rows] fp32
 };
 
 struct TrunkParams {
@@ -61,18 +65,18 @@ struct TrunkParams {
     int32_t item_begin, item_end;  // launch-wide item index range handled by this launch
     uint32_t epoch;
     int32_t use_flags;  // 1: cross-CTA dataflow through flags (single persistent launch)
-    int32_t debug_flags;  // bring-up only; bit0: swap LBO/SBO in the smem descriptors
+    int32_t debug_flags;  // timing experiments only (results wrong): bit1 = all tap offsets 0, bit2 = no epilogue math
 };
 
 // launchers (lb2_kernels.cu)
 cudaError_t launch_expand(const uint32_t* planes, const uint8_t* rotation, int n, __half* x0, int chunk_rows,
                           cudaStream_t st);
 cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, cudaStream_t st);
-cudaError_t launch_policy_head(const __half* act, int chunk_rows, int c_in, const float* w, const float* bias,
-                               const uint8_t* rotation, int n, float temp, float* probs, cudaStream_t st);
-cudaError_t launch_value_head(const __half* act, int chunk_rows, int c_in, const float* w, const float* bias,
-                              const float* ip1_wt, const float* ip1_b, int hidden, const float* ip2_w,
-                              const float* ip2_b, int n, float* winrate, cudaStream_t st);
+cudaError_t launch_policy_head(const float* zbuf, int chunk_rows, const float* bias, const uint8_t* rotation, int n,
+                               float temp, float* probs, cudaStream_t st);
+cudaError_t launch_value_head(const float* zbuf, int chunk_rows, const float* bias, const float* ip1_wt,
+                              const float* ip1_b, int hidden, const float* ip2_w, const float* ip2_b, int n,
+                              float* winrate, cudaStream_t st);
 cudaError_t trunk_kernel_setup();
 
 }  // namespace lb2

@@ -68,8 +68,10 @@ def test_vs_oracle_same_rounding(ev, ref_golden, oracle_nets):
     g = ref_golden
     sel = slice(0, 32)
     probs, win = ev.eval_both(g["policy_planes"][sel], g["value_planes"][sel], g["rotation"][sel], TEMP)
-    pe = oracle.policy_forward(pn, g["policy_planes"][sel], g["rotation"][sel], TEMP, emulate=7)
-    ve = oracle.value_forward(vn, g["value_planes"][sel], g["rotation"][sel], emulate=7)
+    # trunk weights and stored activations fp16; the last trunk layer feeds the fused fp32 head unrounded
+    emu = oracle.ROUND_W | oracle.ROUND_ACT
+    pe = oracle.policy_forward(pn, g["policy_planes"][sel], g["rotation"][sel], TEMP, emulate=emu)
+    ve = oracle.value_forward(vn, g["value_planes"][sel], g["rotation"][sel], emulate=emu)
     assert np.abs(probs - pe).max() < TOL_P and np.abs(probs - pe).mean() < 5e-5
     assert np.abs(win - ve).max() < TOL_V
 

@@ -66,8 +66,8 @@ def full_step(n, mode):
     print(f"  eval_both n={n} mode={mode} in {time.time() - t:.3f}s launches={ev.launch_count}", flush=True)
     stats("policy vs reference fp32", probs, g["policy"][:n])
     stats("value  vs reference fp32", win, g["value"][:n])
-    pe = oracle.policy_forward(oracle.OracleNet(pw), pp, rot, float(g["softmax_temp"]), emulate=7)
-    ve = oracle.value_forward(oracle.OracleNet(vw), vp, rot, emulate=7)
+    pe = oracle.policy_forward(oracle.OracleNet(pw), pp, rot, float(g["softmax_temp"]), emulate=3)
+    ve = oracle.value_forward(oracle.OracleNet(vw), vp, rot, emulate=3)
     d1 = stats("policy vs oracle fp16-emulation", probs, pe)
     d2 = stats("value  vs oracle fp16-emulation", win, ve)
     print("  top1 agreement vs reference:", (probs.argmax(1) == g["policy"][:n].argmax(1)).mean())
