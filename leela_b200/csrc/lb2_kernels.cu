@@ -97,12 +97,11 @@ __device__ __forceinline__ void wait_dependencies(const LayerJob& J, const Layer
     fence_proxy_async();  // order the TMA (async proxy) reads after the acquire
 }
 
-// ELU(alpha = 1): v > 0 ? v : exp(v) - 1, written branch-free: max(v,0) + min(exp(v) - 1, 0).
+// ELU(alpha = 1): v > 0 ? v : exp(v) - 1, written branch-free as max(v, min(exp(v) - 1, 0)).
 __device__ __forceinline__ float elu_fast(float v) {
     float e;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 1.4426950408889634f));  // inf for large v is clamped by the min
-    e -= 1.0f;
-    return fmaxf(v, 0.0f) + fminf(e, 0.0f);
+    return fmaxf(v, fminf(e - 1.0f, 0.0f));  // v>0: e-1>0 -> max(v,0)=v; v<=0: e-1 in (-1,0] and e-1 >= v
 }
 
 __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_constant__ TrunkParams P) {
@@ -241,14 +240,15 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             while (q >= jobs[j].item_base + jobs[j].n_items) j++;
             const LayerJob& J = jobs[j];
             const int tile = q - J.item_base;
-            const int S = J.S, SS = S * S, n_out = J.n_out, chunk_rows = J.out_chunk_rows;
-            const int head = J.head_taps;
+            const int n_out = J.n_out, chunk_rows = J.out_chunk_rows, n_pos = J.n_pos;
+            const bool head = J.head_taps != 0, remap = J.remap != 0, wide = (J.S == 21);
             __half* __restrict__ out = J.out;
+            float* __restrict__ zbuf = J.zbuf;
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             // stage this job's bias (and fused-head weights) in smem while the MMAs run
             float* bs = bias_s + acc * 128;
-            if (etid < n_out) bs[etid] = J.bias[etid];
             float* headw_s = headw_all + acc * (9 * 128);
+            if (etid < n_out) bs[etid] = J.bias[etid];
             if (head) for (int i = etid; i < 9 * n_out; i += 256) headw_s[i] = J.head_w[i];
             named_bar_sync(1, 256);
             mbar_wait(tfull_bar + acc, acc_phase);
@@ -258,34 +258,34 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
 #pragma unroll 1
             for (int h = 0; h < 2; h++) {
                 const int row = tile * kTileRows + h * 128 + quad * 32 + lane;
-                const int pos = row / SS, rem = row - pos * SS;
-                const int y = rem / S, x = rem - y * S;
+                int pos, y, x;
+                if (wide) { pos = row / 441; const int rem = row - pos * 441; y = rem / 21; x = rem - y * 21; }
+                else      { pos = row / 400; const int rem = row - pos * 400; y = rem / 20; x = rem - y * 20; }
                 const bool valid = (x < kBoard) && (y < kBoard);
                 int out_row = row;
-                bool store = true;
-                if (J.remap) { out_row = pos * 400 + y * 20 + x; store = valid && pos < J.n_pos; }
+                bool store = !head;
+                if (remap) { out_row = pos * 400 + y * 20 + x; store = valid && pos < n_pos; }
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (acc * 2 + h) * 128 + col0;
                 float z[9];
 #pragma unroll
                 for (int t = 0; t < 9; t++) z[t] = 0.0f;
-#pragma unroll 1
-                for (int cc = 0; cc < cols; cc += 16) {
-                    uint32_t r[16];
-                    tmem_ld_32x16(taddr + cc, r);
-                    tmem_ld_wait();
+
+                // bias + ELU on 16 accumulator columns, then either the fused head's partial dot
+                // products or the fp16 store of two 8-channel chunks
+                auto finish16 = [&](const uint32_t (&r)[16], int cc) {
                     float v[16];
+                    const float* bp = bs + col0 + cc;
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(bp + e);
+                        v[e + 0] = __uint_as_float(r[e + 0]) + b4.x;
+                        v[e + 1] = __uint_as_float(r[e + 1]) + b4.y;
+                        v[e + 2] = __uint_as_float(r[e + 2]) + b4.z;
+                        v[e + 3] = __uint_as_float(r[e + 3]) + b4.w;
+                    }
                     if (!(P.debug_flags & 4)) {
 #pragma unroll
-                        for (int e = 0; e < 16; e += 4) {
-                            const float4 b4 = *reinterpret_cast<const float4*>(bs + col0 + cc + e);
-                            v[e + 0] = elu_fast(__uint_as_float(r[e + 0]) + b4.x);
-                            v[e + 1] = elu_fast(__uint_as_float(r[e + 1]) + b4.y);
-                            v[e + 2] = elu_fast(__uint_as_float(r[e + 2]) + b4.z);
-                            v[e + 3] = elu_fast(__uint_as_float(r[e + 3]) + b4.w);
-                        }
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 16; e++) v[e] = __uint_as_float(r[e]);
+                        for (int e = 0; e < 16; e++) v[e] = elu_fast(v[e]);
                     }
                     if (head) {
                         // fused 1-channel 3x3 head: z[t] += sum_c w[t][c] * v[c]  (fp32, unrounded v)
@@ -309,13 +309,31 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                             pk[e] = valid ? *reinterpret_cast<uint32_t*>(&hh) : 0u;
                         }
                         const int c8 = (col0 + cc) >> 3;
-                        *reinterpret_cast<uint4*>(out + ((size_t)c8 * chunk_rows + out_row) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        *reinterpret_cast<uint4*>(out + ((size_t)(c8 + 1) * chunk_rows + out_row) * 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        __half* o = out + ((size_t)c8 * chunk_rows + out_row) * 8;
+                        *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4*>(o + (size_t)chunk_rows * 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                     }
+                };
+
+                int cc = 0;
+#pragma unroll 1
+                for (; cc + 32 <= cols; cc += 32) {   // two TMEM loads in flight
+                    uint32_t r0[16], r1[16];
+                    tmem_ld_32x16(taddr + cc, r0);
+                    tmem_ld_32x16(taddr + cc + 16, r1);
+                    tmem_ld_wait();
+                    finish16(r0, cc);
+                    finish16(r1, cc + 16);
+                }
+                if (cc < cols) {
+                    uint32_t r0[16];
+                    tmem_ld_32x16(taddr + cc, r0);
+                    tmem_ld_wait();
+                    finish16(r0, cc);
                 }
                 if (head) {
                     // partial sums of this channel half: zbuf[half][t][row]; padding rows contribute 0
-                    float* zb = J.zbuf + (size_t)half * 9 * chunk_rows + out_row;
+                    float* zb = zbuf + (size_t)half * 9 * chunk_rows + out_row;
 #pragma unroll
                     for (int t = 0; t < 9; t++) zb[(size_t)t * chunk_rows] = valid ? z[t] : 0.0f;
                 }
@@ -325,7 +343,8 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar + acc);
             if (P.use_flags) {
-                __threadfence();
+                // publish the tile: every epilogue thread's stores happen-before the barrier; one
+                // thread then releases them at gpu scope (cumulative) for the consumers' acquire
                 named_bar_sync(2, 256);
                 if (etid == 0) {
                     fence_proxy_async();  // generic-proxy stores -> visible to other CTAs' TMA loads
