@@ -348,6 +348,7 @@ JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2]) {
             if (l + 1 == nd.trunk.size() && limit_layers[k] > (int)nd.trunk.size()) {
                 // whole net: fold the final 3x3 conv to one channel into this layer's epilogue
                 J.head_taps = 9;
+                J.head_slot = k;
                 J.head_w = nd.head_wt;
                 J.zbuf = nd.zbuf;
             }
@@ -365,7 +366,7 @@ int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers
               JobPlan* plan_out) {
     JobPlan pl = plan_jobs(d, run, n, limit_layers);
     if (pl.jobs.empty()) return fail(LB2_ERR_STATE, "no trunk layers to run");
-    if ((int)pl.jobs.size() > lb2::kMaxJobs) return fail(LB2_ERR_UNSUPPORTED, "too many layers");
+    if ((int)pl.jobs.size() > lb2::kMaxLaunchJobs) return fail(LB2_ERR_UNSUPPORTED, "too many layers");
     const long key[7] = {n, run[0], run[1], limit_layers[0], limit_layers[1],
                          (long)reinterpret_cast<uintptr_t>(d->net[0].act[0]), (long)reinterpret_cast<uintptr_t>(d->net[1].act[0])};
     if (memcmp(key, d->plan_key, sizeof key)) {

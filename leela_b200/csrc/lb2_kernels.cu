@@ -74,10 +74,10 @@ __device__ __forceinline__ int n_tap_groups(int ksize) { return ksize == 3 ? 1 :
 __device__ __forceinline__ int tap_group_begin(int g) { return g == 0 ? 0 : (g == 1 ? 9 : 17); }
 __device__ __forceinline__ int tap_group_end(int ksize, int g) { return ksize == 3 ? 9 : (g == 0 ? 9 : (g == 1 ? 17 : 25)); }
 
-__device__ __forceinline__ void wait_dependencies(const LayerJob& J, const LayerJob* jobs, int tile, uint32_t epoch) {
+// Producer items [lo, hi] of J.dep_job whose outputs overlap the input rows (tile + halo) of `tile`.
+__device__ __forceinline__ void dependency_range(const LayerJob& J, int tile, int& lo, int& hi) {
     const int r_lo = tile * kTileRows - J.halo;
     const int r_hi = tile * kTileRows + kTileRows - 1 + J.halo;
-    int lo, hi;
     if (!J.dep_remap) {
         lo = r_lo < 0 ? 0 : r_lo / kTileRows;
         hi = r_hi / kTileRows;
@@ -90,11 +90,6 @@ __device__ __forceinline__ void wait_dependencies(const LayerJob& J, const Layer
         hi = ((p_hi + 1) * 441 - 1) / kTileRows;
     }
     if (hi > J.dep_n_items - 1) hi = J.dep_n_items - 1;
-    const uint32_t* flags = jobs[J.dep_job].flags;
-    for (int i = lo; i <= hi; i++) {
-        while (ld_acquire_gpu(flags + i) != epoch) __nanosleep(64);
-    }
-    fence_proxy_async();  // order the TMA (async proxy) reads after the acquire
 }
 
 // ELU(alpha = 1): v > 0 ? v : exp(v) - 1, written branch-free as max(v, min(exp(v) - 1, 0)).
@@ -110,9 +105,11 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tfull_bar = empty_bar + kStages;   // [2] accumulator ready   (MMA -> epilogue)
     uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulator drained (epilogue -> MMA)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    float* bias_s = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);  // [2][128]
-    float* headw_all = bias_s + 2 * 128;                                           // [2][9][128]
+    uint64_t* pub_bar = tempty_bar + 2;          // [kPubDepth] tile stored (epilogue -> publisher)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pub_bar + kPubDepth);
+    volatile uint32_t* pub_done = tmem_slot + 1; // tiles published so far by this CTA
+    float* bias_all = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);  // [kMaxLaunchJobs][128]
+    float* headw_all = bias_all + kMaxLaunchJobs * 128;                              // [2][9][128]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -121,45 +118,75 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         if (smem_u32(smem) & 127u) __trap();  // TMA destinations need 128-byte alignment
         for (int i = 0; i < kStages; i++) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
         for (int i = 0; i < 2; i++) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, kEpilogueWarps); }
+        for (int i = 0; i < kPubDepth; i++) mbar_init(pub_bar + i, kEpilogueWarps);
+        *pub_done = 0;
         fence_mbar_init();
         fence_proxy_async_smem();
         for (int i = 0; i < kMaxTensorMaps; i++) tma_prefetch_desc(&P.tmaps[i]);
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
+    const LayerJob* __restrict__ jobs = P.jobs;
+    // every job's bias and both fused-head weight sets stay resident in smem for the whole launch
+    for (int i = threadIdx.x; i < P.n_jobs * 128; i += blockDim.x) {
+        const int jj = i >> 7, c = i & 127;
+        bias_all[i] = c < jobs[jj].n_out ? jobs[jj].bias[c] : 0.0f;
+    }
+    for (int jj = 0; jj < P.n_jobs; jj++) {
+        if (!jobs[jj].head_taps) continue;
+        float* dst = headw_all + jobs[jj].head_slot * (9 * 128);
+        for (int i = threadIdx.x; i < 9 * jobs[jj].n_out; i += blockDim.x) dst[i] = jobs[jj].head_w[i];
+    }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    const LayerJob* __restrict__ jobs = P.jobs;
-
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0; int j = 0;
-            for (int q = P.item_begin + blockIdx.x; q < P.item_end; q += gridDim.x) {
-                while (q >= jobs[j].item_base + jobs[j].n_items) j++;
-                const LayerJob J = jobs[j];
-                const int tile = q - J.item_base;
-                if (P.use_flags && J.dep_job >= 0) wait_dependencies(J, jobs, tile, P.epoch);
-                const int rows_halo = kTileRows + 2 * J.halo;
-                const uint32_t a_bytes = rows_halo * 32;
-                const int row0_8 = (tile * kTileRows - J.halo) / 8;  // exact: both multiples of 8
-                const int ng = n_tap_groups(J.ksize);
-                const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(J.wpk);
-                for (int s = 0; s < J.n_slabs; s++) {
+        // The whole warp walks the item list; lanes poll the dependency flags in parallel, one
+        // elected lane issues the copies.
+        int stage = 0; uint32_t phase = 0; int j = 0;
+        for (int q = P.item_begin + blockIdx.x; q < P.item_end; q += gridDim.x) {
+            while (q >= jobs[j].item_base + jobs[j].n_items) j++;
+            const LayerJob& J = jobs[j];
+            const int tile = q - J.item_base;
+            const int halo = J.halo, ksize = J.ksize, n_out = J.n_out, n_slabs = J.n_slabs, tmap = J.tmap;
+            if (P.use_flags && J.dep_job >= 0) {
+                int lo, hi;
+                dependency_range(J, tile, lo, hi);
+                const uint32_t* flags = jobs[J.dep_job].flags;
+                if (lo + lane <= hi)
+                    while (ld_acquire_gpu(flags + lo + lane) != P.epoch) __nanosleep(32);
+                __syncwarp();
+            }
+            const int rows_halo = kTileRows + 2 * halo;
+            const uint32_t a_bytes = rows_halo * 32;
+            const int row0_8 = (tile * kTileRows - halo) / 8;  // exact: both multiples of 8
+            const int ng = n_tap_groups(ksize);
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(J.wpk);
+            if (elect_one()) {
+                int st = stage; uint32_t ph = phase;  // private walk; all lanes advance the shared view below
+                fence_proxy_async();  // order the TMA (async proxy) reads after the acquires above
+                for (int s = 0; s < n_slabs; s++) {
                     for (int g = 0; g < ng; g++) {
-                        const uint32_t b_bytes = (tap_group_end(J.ksize, g) - tap_group_begin(g)) * J.n_out * 32;
-                        mbar_wait(empty_bar + stage, phase ^ 1);
-                        uint8_t* sa = smem + stage * kStageBytes;
-                        mbar_arrive_expect_tx(full_bar + stage, a_bytes + b_bytes);
-                        tma_load_3d(sa, &P.tmaps[J.tmap], full_bar + stage, 0, row0_8, 2 * s);
-                        bulk_load_1d(sa + kASlabBytes, wsrc, b_bytes, full_bar + stage);
+                        const uint32_t b_bytes = (tap_group_end(ksize, g) - tap_group_begin(g)) * n_out * 32;
+                        mbar_wait(empty_bar + st, ph ^ 1);
+                        uint8_t* sa = smem + st * kStageBytes;
+                        const bool skip_b = (P.debug_flags & 8) != 0, skip_a = (P.debug_flags & 16) != 0;
+                        mbar_arrive_expect_tx(full_bar + st, (skip_a ? 0u : a_bytes) + (skip_b ? 0u : b_bytes));
+                        if (!skip_a) tma_load_3d(sa, &P.tmaps[tmap], full_bar + st, 0, row0_8, 2 * s);
+                        if (!skip_b) bulk_load_1d(sa + kASlabBytes, wsrc, b_bytes, full_bar + st);
                         wsrc += b_bytes;
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        if (++st == kStages) { st = 0; ph ^= 1; }
                     }
                 }
             }
+            // every lane tracks the ring position the elected lane advanced to
+            const int adv = n_slabs * ng;
+            stage += adv;
+            phase ^= (stage / kStages) & 1;
+            stage %= kStages;
+            __syncwarp();
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
@@ -202,7 +229,8 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                                 const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo_base | (b16 & 0x3FFFu));
                                 const uint32_t a0 = a16 + off;
                                 umma_f16(d0, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo_base | (a0 & 0x3FFFu)), bdesc, idesc, accumulate);
-                                umma_f16(d1, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo_base | ((a0 + 128) & 0x3FFFu)), bdesc, idesc, accumulate);
+                                if (!(P.debug_flags & 32))
+                                    umma_f16(d1, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo_base | ((a0 + 128) & 0x3FFFu)), bdesc, idesc, accumulate);
                                 accumulate = 1;
                                 b16 += b_step;
                             }
@@ -229,12 +257,11 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             if (elect_one()) umma_commit(tfull_bar + acc);  // accumulator complete -> epilogue
             __syncwarp();
         }
-    } else {
+    } else if (warp < 2 + kEpilogueWarps) {
         // ================================ epilogue ====================================
         const int ew = warp - 2;          // 0..7
         const int quad = warp & 3;        // TMEM lane quadrant this warp may read
         const int half = ew >> 2;         // which half of the output channels
-        const int etid = threadIdx.x - 64;  // 0..255
         int j = 0; uint32_t it = 0;
         for (int q = P.item_begin + blockIdx.x; q < P.item_end; q += gridDim.x, it++) {
             while (q >= jobs[j].item_base + jobs[j].n_items) j++;
@@ -245,12 +272,8 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             __half* __restrict__ out = J.out;
             float* __restrict__ zbuf = J.zbuf;
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-            // stage this job's bias (and fused-head weights) in smem while the MMAs run
-            float* bs = bias_s + acc * 128;
-            float* headw_s = headw_all + acc * (9 * 128);
-            if (etid < n_out) bs[etid] = J.bias[etid];
-            if (head) for (int i = etid; i < 9 * n_out; i += 256) headw_s[i] = J.head_w[i];
-            named_bar_sync(1, 256);
+            const float* bs = bias_all + j * 128;
+            const float* headw_s = headw_all + J.head_slot * (9 * 128);
             mbar_wait(tfull_bar + acc, acc_phase);
             tc_fence_after_sync();
             const int cols = n_out >> 1;          // columns handled by this warp
@@ -343,13 +366,26 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar + acc);
             if (P.use_flags) {
-                // publish the tile: every epilogue thread's stores happen-before the barrier; one
-                // thread then releases them at gpu scope (cumulative) for the consumers' acquire
-                named_bar_sync(2, 256);
-                if (etid == 0) {
-                    fence_proxy_async();  // generic-proxy stores -> visible to other CTAs' TMA loads
-                    st_release_gpu(J.flags + tile, P.epoch);
+                // hand the tile to the publisher warp: this warp's stores happen-before its arrive
+                if (lane == 0) {
+                    while (it >= *pub_done + kPubDepth) __nanosleep(32);  // ring slot free? (normally yes)
+                    mbar_arrive(pub_bar + (it % kPubDepth));
                 }
+            }
+        }
+    } else if (warp == 10) {
+        // ================================ tile publisher ==============================
+        // Keeps the gpu-scope release (which waits for the tile's stores to land in L2) off the
+        // epilogue's critical path. One lane: wait until all 8 epilogue warps stored tile `it`,
+        // then release its flag for the consumers' acquire (cumulative over the mbarrier sync).
+        if (P.use_flags && lane == 0) {
+            int j = 0; uint32_t it = 0;
+            for (int q = P.item_begin + blockIdx.x; q < P.item_end; q += gridDim.x, it++) {
+                while (q >= jobs[j].item_base + jobs[j].n_items) j++;
+                mbar_wait(pub_bar + (it % kPubDepth), (it / kPubDepth) & 1);
+                fence_proxy_async();  // generic-proxy stores -> visible to other CTAs' TMA loads
+                st_release_gpu(jobs[j].flags + (q - jobs[j].item_base), P.epoch);
+                *pub_done = it + 1;
             }
         }
     }

@@ -26,9 +26,12 @@ constexpr int kASlabBytes = (kTileRows + 2 * kMaxHalo) * 32;  // rows x 16 ch x 
 constexpr int kBBlockBytes = 9 * 128 * 32;                    // up to 9 taps x N<=128 x 16 ch x fp16
 constexpr int kStageBytes = kASlabBytes + kBBlockBytes;       // 48,128
 constexpr int kEpilogueWarps = 8;
-constexpr int kTrunkThreads = 64 + 32 * kEpilogueWarps;  // warp0 TMA producer, warp1 MMA issuer, warps2-9 epilogue
-// stages | mbarriers + TMEM slot (256 B) | bias [2][128] f32 | fused-head weights [2][9][128] f32
-constexpr int kTrunkSmemBytes = kStages * kStageBytes + 256 + 2 * 128 * 4 + 2 * 9 * 128 * 4;
+// warp0 TMA producer, warp1 MMA issuer, warps2-9 epilogue, warp10 tile publisher
+constexpr int kTrunkThreads = 64 + 32 * kEpilogueWarps + 32;
+constexpr int kMaxLaunchJobs = 24;  // jobs whose biases are kept resident in smem
+constexpr int kPubDepth = 4;        // tiles that may be waiting for publication
+// stages | mbarriers + TMEM slot (256 B) | bias [jobs][128] f32 | fused-head weights [2 nets][9][128] f32
+constexpr int kTrunkSmemBytes = kStages * kStageBytes + 256 + kMaxLaunchJobs * 128 * 4 + 2 * 9 * 128 * 4;
 constexpr int kMaxTensorMaps = 6;
 constexpr int kMaxJobs = 32;
 
@@ -49,7 +52,7 @@ struct LayerJob {
     int32_t n_pos;           // positions in the batch
     int32_t out_chunk_rows;  // rows per chunk plane of the output buffer
     int32_t head_taps;       // 9: the net's final 3x3 conv to 1 channel is fused into this job's epilogue
-    int32_t pad_;
+    int32_t head_slot;       // which resident head-weight slot (0 = policy, 1 = value)
     const __half* wpk;       // packed weights: per (slab, tap group): [tap][2 chunks][n_out][8]
     const float* bias;       // [n_out]
     __half* out;             // output activation buffer
@@ -65,7 +68,8 @@ struct TrunkParams {
     int32_t item_begin, item_end;  // launch-wide item index range handled by this launch
     uint32_t epoch;
     int32_t use_flags;  // 1: cross-CTA dataflow through flags (single persistent launch)
-    int32_t debug_flags;  // timing experiments only (results wrong): bit1 = all tap offsets 0, bit2 = no epilogue math
+    int32_t debug_flags;  // timing experiments only (results wrong): bit1 = all tap offsets 0, bit2 = no epilogue math,
+                          // bit3 = no B loads, bit4 = no A loads, bit5 = only the first M half of 3x3 layers
 };
 
 // launchers (lb2_kernels.cu)
