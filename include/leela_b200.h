@@ -130,6 +130,11 @@ long lb2_launch_count(lb2_ctx* ctx);
 int lb2_debug_trunk(lb2_ctx* ctx, int kind, const uint32_t* planes, const uint8_t* rotation,
                     int n, int n_layers, float* act_out);
 
+/* Debug hook: after lb2_set_option(ctx, "trace", 1), every trunk launch records a per-work-item
+ * timeline (global-timer nanoseconds, [cta][96 items][16 events]); this copies it out and clears
+ * it. Returns the number of CTAs copied, or a negative status. */
+int lb2_debug_read_trace(lb2_ctx* ctx, unsigned long long* out, long max_entries);
+
 #ifdef __cplusplus
 }
 #endif

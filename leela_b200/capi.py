@@ -21,7 +21,7 @@ EXPORTS = [
     "lb2_init", "lb2_destroy", "lb2_net_create", "lb2_net_push_conv", "lb2_net_push_ip", "lb2_net_finalize",
     "lb2_eval_policy", "lb2_eval_value", "lb2_eval_both", "lb2_eval_both_device", "lb2_submit_policy",
     "lb2_submit_value", "lb2_drain", "lb2_backend_name", "lb2_last_error", "lb2_device_count", "lb2_set_option",
-    "lb2_get_option", "lb2_launch_count", "lb2_debug_trunk",
+    "lb2_get_option", "lb2_launch_count", "lb2_debug_trunk", "lb2_debug_read_trace",
 ]
 
 CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_int)
@@ -64,6 +64,7 @@ def load():
     L.lb2_get_option.argtypes = [vp, C.c_char_p]; L.lb2_get_option.restype = C.c_long
     L.lb2_launch_count.argtypes = [vp]; L.lb2_launch_count.restype = C.c_long
     L.lb2_debug_trunk.argtypes = [vp, ip, vp, vp, ip, ip, vp]
+    L.lb2_debug_read_trace.argtypes = [vp, vp, C.c_long]
     _lib = L
     return L
 
@@ -166,6 +167,15 @@ class Evaluator:
         out = np.empty((n, c_out, P), dtype=np.float32)
         check(self._L.lb2_debug_trunk(self.ctx, kind, _p(planes), _p(rotation), n, n_layers, _p(out)))
         return out
+
+    def read_trace(self):
+        """[n_cta, 96, 16] uint64 timeline of the last traced trunk launch (set_option('trace', 1))."""
+        n = 256 * 96 * 16
+        buf = np.zeros(n, dtype=np.uint64)
+        rc = self._L.lb2_debug_read_trace(self.ctx, _p(buf), n)
+        if rc < 0:
+            check(rc)
+        return buf[:rc * 96 * 16].reshape(rc, 96, 16)
 
     # -------------------------------------------------------------- misc
     def set_option(self, name, value):

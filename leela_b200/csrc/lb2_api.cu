@@ -109,6 +109,7 @@ struct DeviceState {
     lb2::LayerJob* h_jobs = nullptr;
     int cap = 0;
     uint32_t epoch = 0;
+    unsigned long long* trace = nullptr;   // debug timeline buffer (option "trace")
     std::vector<cudaEvent_t> prof_events;  // (start, stop) pairs around trunk launches
     long plan_key[7] = {-1, -1, -1, -1, -1, -1, -1};  // n, run0, run1, limit0, limit1, workspace pointers
 };
@@ -400,6 +401,7 @@ int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers
         CU_TRY(cudaEventRecord(ev0, st));
     }
     if (const char* dbg = getenv("LB2_DEBUG_FLAGS")) P.debug_flags = atoi(dbg);
+    P.trace = d->trace;
     if (ctx->trunk_mode == 1) {
         P.item_begin = 0;
         P.item_end = pl.total_items;
@@ -816,6 +818,19 @@ int lb2_set_option(lb2_ctx* ctx, const char* name, long value) {
     if (!strcmp(name, "trunk_mode")) {
         if (value != 0 && value != 1) return fail(LB2_ERR_INVALID, "trunk_mode must be 0 or 1");
         ctx->trunk_mode = value;
+    } else if (!strcmp(name, "trace")) {
+        // debug: per-item timeline of the trunk kernel on device 0 (read back with lb2_debug_read_trace)
+        DeviceState& d = ctx->dev[0];
+        cudaSetDevice(d.id);
+        cudaDeviceSynchronize();
+        if (value && !d.trace) {
+            const size_t bytes = (size_t)d.sm_count * lb2::kTraceItems * lb2::kTraceEvents * sizeof(unsigned long long);
+            if (cudaMalloc(&d.trace, bytes) != cudaSuccess) return fail(LB2_ERR_NOMEM, "trace buffer");
+            cudaMemset(d.trace, 0, bytes);
+        } else if (!value && d.trace) {
+            cudaFree(d.trace);
+            d.trace = nullptr;
+        }
     } else if (!strcmp(name, "profile_trunk")) {
         ctx->profile_trunk = value ? 1 : 0;
     } else if (!strcmp(name, "max_batch")) {
@@ -855,6 +870,18 @@ long lb2_get_option(lb2_ctx* ctx, const char* name) {
 }
 
 long lb2_launch_count(lb2_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+int lb2_debug_read_trace(lb2_ctx* ctx, unsigned long long* out, long max_entries) {
+    if (!ctx || !out) return fail(LB2_ERR_INVALID, "null argument");
+    DeviceState& d = ctx->dev[0];
+    if (!d.trace) return fail(LB2_ERR_STATE, "tracing not enabled");
+    const long n = std::min<long>(max_entries, (long)d.sm_count * lb2::kTraceItems * lb2::kTraceEvents);
+    CU_TRY(cudaSetDevice(d.id));
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(out, d.trace, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemset(d.trace, 0, (size_t)n * sizeof(unsigned long long)));
+    return (int)(n / (lb2::kTraceItems * lb2::kTraceEvents));
+}
 
 int lb2_debug_trunk(lb2_ctx* ctx, int kind, const uint32_t* planes, const uint8_t* rotation, int n, int n_layers,
                     float* act_out) {

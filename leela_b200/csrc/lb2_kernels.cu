@@ -92,6 +92,18 @@ __device__ __forceinline__ void dependency_range(const LayerJob& J, int tile, in
     if (hi > J.dep_n_items - 1) hi = J.dep_n_items - 1;
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// timeline tracing (debug): event e of this CTA's `it`-th item
+#define LB2_TRACE(it, e)                                                                             \
+    do {                                                                                             \
+        if (P.trace && (it) < (uint32_t)kTraceItems)                                                 \
+            P.trace[((size_t)blockIdx.x * kTraceItems + (it)) * kTraceEvents + (e)] = global_ns();   \
+    } while (0)
+
 // ELU(alpha = 1): v > 0 ? v : exp(v) - 1, written branch-free as max(v, min(exp(v) - 1, 0)).
 __device__ __forceinline__ float elu_fast(float v) {
     float e;
@@ -145,12 +157,13 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         // ================================ TMA producer ================================
         // The whole warp walks the item list; lanes poll the dependency flags in parallel, one
         // elected lane issues the copies.
-        int stage = 0; uint32_t phase = 0; int j = 0;
-        for (int q = P.item_begin + blockIdx.x; q < P.item_end; q += gridDim.x) {
+        int stage = 0; uint32_t phase = 0; int j = 0; uint32_t pit = 0;
+        for (int q = P.item_begin + blockIdx.x; q < P.item_end; q += gridDim.x, pit++) {
             while (q >= jobs[j].item_base + jobs[j].n_items) j++;
             const LayerJob& J = jobs[j];
             const int tile = q - J.item_base;
             const int halo = J.halo, ksize = J.ksize, n_out = J.n_out, n_slabs = J.n_slabs, tmap = J.tmap;
+            if (lane == 0) { LB2_TRACE(pit, 0); if (P.trace && pit < (uint32_t)kTraceItems) P.trace[((size_t)blockIdx.x * kTraceItems + pit) * kTraceEvents + 15] = (unsigned long long)q; }
             if (P.use_flags && J.dep_job >= 0) {
                 int lo, hi;
                 dependency_range(J, tile, lo, hi);
@@ -166,6 +179,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(J.wpk);
             if (elect_one()) {
                 int st = stage; uint32_t ph = phase;  // private walk; all lanes advance the shared view below
+                LB2_TRACE(pit, 1);
                 fence_proxy_async();  // order the TMA (async proxy) reads after the acquires above
                 for (int s = 0; s < n_slabs; s++) {
                     for (int g = 0; g < ng; g++) {
@@ -178,8 +192,10 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                         if (!skip_b) bulk_load_1d(sa + kASlabBytes, wsrc, b_bytes, full_bar + st);
                         wsrc += b_bytes;
                         if (++st == kStages) { st = 0; ph ^= 1; }
+                        if (s == 0 && g == 0) LB2_TRACE(pit, 2);
                     }
                 }
+                LB2_TRACE(pit, 3);
             }
             // every lane tracks the ring position the elected lane advanced to
             const int adv = n_slabs * ng;
@@ -198,8 +214,10 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             const int ksize = J.ksize, n_out = J.n_out, n_slabs = J.n_slabs, halo = J.halo;
             const int S = (P.debug_flags & 2) ? 0 : J.S, DX = (P.debug_flags & 2) ? 0 : 1;
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+            if (lane == 0) LB2_TRACE(it, 4);
             mbar_wait(tempty_bar + acc, acc_phase ^ 1);
             tc_fence_after_sync();
+            if (lane == 0) LB2_TRACE(it, 5);
             const uint32_t idesc = umma_idesc_f16(128, n_out);
             const int rows_halo = kTileRows + 2 * halo;
             // descriptor = hi32 (SBO = 128 B, version 1) : lo32 (LBO << 16 | start address >> 4)
@@ -216,6 +234,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                 for (int g = 0; g < ng; g++) {
                     mbar_wait(full_bar + stage, phase);
                     tc_fence_after_sync();
+                    if (lane == 0 && s == 0 && g == 0) LB2_TRACE(it, 6);
                     __syncwarp();
                     if (elect_one()) {
                         const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
@@ -255,6 +274,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                 }
             }
             if (elect_one()) umma_commit(tfull_bar + acc);  // accumulator complete -> epilogue
+            if (lane == 0) LB2_TRACE(it, 7);
             __syncwarp();
         }
     } else if (warp < 2 + kEpilogueWarps) {
@@ -274,8 +294,10 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             const float* bs = bias_all + j * 128;
             const float* headw_s = headw_all + J.head_slot * (9 * 128);
+            if (warp == 2 && lane == 0) LB2_TRACE(it, 8);
             mbar_wait(tfull_bar + acc, acc_phase);
             tc_fence_after_sync();
+            if (warp == 2 && lane == 0) LB2_TRACE(it, 9);
             const int cols = n_out >> 1;          // columns handled by this warp
             const int col0 = half * cols;
 #pragma unroll 1
@@ -365,6 +387,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar + acc);
+            if (warp == 2 && lane == 0) LB2_TRACE(it, 10);
             if (P.use_flags) {
                 // hand the tile to the publisher warp: this warp's stores happen-before its arrive
                 if (lane == 0) {
@@ -383,8 +406,10 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             for (int q = P.item_begin + blockIdx.x; q < P.item_end; q += gridDim.x, it++) {
                 while (q >= jobs[j].item_base + jobs[j].n_items) j++;
                 mbar_wait(pub_bar + (it % kPubDepth), (it / kPubDepth) & 1);
+                LB2_TRACE(it, 11);
                 fence_proxy_async();  // generic-proxy stores -> visible to other CTAs' TMA loads
                 st_release_gpu(jobs[j].flags + (q - jobs[j].item_base), P.epoch);
+                LB2_TRACE(it, 12);
                 *pub_done = it + 1;
             }
         }

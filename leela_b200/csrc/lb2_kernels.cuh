@@ -34,6 +34,8 @@ constexpr int kPubDepth = 4;        // tiles that may be waiting for publication
 constexpr int kTrunkSmemBytes = kStages * kStageBytes + 256 + kMaxLaunchJobs * 128 * 4 + 2 * 9 * 128 * 4;
 constexpr int kMaxTensorMaps = 6;
 constexpr int kMaxJobs = 32;
+constexpr int kTraceItems = 96;
+constexpr int kTraceEvents = 16;
 
 // One trunk layer of one net over the whole batch.
 struct LayerJob {
@@ -68,6 +70,7 @@ struct TrunkParams {
     int32_t item_begin, item_end;  // launch-wide item index range handled by this launch
     uint32_t epoch;
     int32_t use_flags;  // 1: cross-CTA dataflow through flags (single persistent launch)
+    unsigned long long* trace;  // optional timeline buffer [cta][kTraceItems][kTraceEvents] of %globaltimer ns
     int32_t debug_flags;  // timing experiments only (results wrong): bit1 = all tap offsets 0, bit2 = no epilogue math,
                           // bit3 = no B loads, bit4 = no A loads, bit5 = only the first M half of 3x3 layers
 };
