@@ -479,17 +479,22 @@ __global__ void __launch_bounds__(384) policy_head_kernel(const float* __restric
 
 // value head: kValueGroup positions per CTA so the 361xH inner-product matrix is read once per
 // group. v = ELU(b + conv) [361]; h = ELU(W1 v + b1); out = (1 + tanh(w2.h + b2)) / 2.
-constexpr int kValueGroup = 8;
+// 512 threads: thread (o, part) accumulates half of the 361 inputs of output o for all positions
+// of the group (more loads in flight), the halves are combined through shared memory.
+constexpr int kValueGroup = 4;
+constexpr int kValueThreads = 512;
 
-__global__ void __launch_bounds__(256) value_head_kernel(const float* __restrict__ zbuf, int chunk_rows,
-                                                         const float* __restrict__ bias,
-                                                         const float* __restrict__ ip1_wt /*[361][hidden]*/,
-                                                         const float* __restrict__ ip1_b, int hidden,
-                                                         const float* __restrict__ ip2_w, const float* __restrict__ ip2_b,
-                                                         int n, float* __restrict__ winrate) {
+__global__ void __launch_bounds__(kValueThreads) value_head_kernel(const float* __restrict__ zbuf, int chunk_rows,
+                                                                   const float* __restrict__ bias,
+                                                                   const float* __restrict__ ip1_wt /*[361][hidden]*/,
+                                                                   const float* __restrict__ ip1_b, int hidden,
+                                                                   const float* __restrict__ ip2_w,
+                                                                   const float* __restrict__ ip2_b, int n,
+                                                                   float* __restrict__ winrate) {
     extern __shared__ float hs[];
     float* v_s = hs;                              // [361][G]  (position fastest: float4 broadcast reads)
     float* h_s = v_s + kValueGroup * kPoints;     // [G][hidden]
+    float* part_s = h_s + kValueGroup * hidden;   // [G][hidden] partial sums of the second half
     const int tid = threadIdx.x;
     const int pos0 = blockIdx.x * kValueGroup;
     for (int i = tid; i < kValueGroup * kPoints; i += blockDim.x) {
@@ -502,28 +507,44 @@ __global__ void __launch_bounds__(256) value_head_kernel(const float* __restrict
         v_s[p * kValueGroup + g] = v;
     }
     __syncthreads();
-    for (int o = tid; o < hidden; o += blockDim.x) {
-        float a[kValueGroup];
+    const int o = tid % hidden, part = tid / hidden;   // hidden <= 256 -> part in {0, 1}
+    float a[kValueGroup];
 #pragma unroll
-        for (int g = 0; g < kValueGroup; g++) a[g] = 0.0f;
-#pragma unroll 4
-        for (int i = 0; i < kPoints; i++) {
+    for (int g = 0; g < kValueGroup; g++) a[g] = 0.0f;
+    if (part < 2) {
+        const int i0 = part == 0 ? 0 : 181, i1 = part == 0 ? 181 : kPoints;
+#pragma unroll 8
+        for (int i = i0; i < i1; i++) {
             const float wv = ip1_wt[(size_t)i * hidden + o];
             const float4 v0 = *reinterpret_cast<const float4*>(v_s + i * kValueGroup);
-            const float4 v1 = *reinterpret_cast<const float4*>(v_s + i * kValueGroup + 4);
             a[0] = fmaf(wv, v0.x, a[0]); a[1] = fmaf(wv, v0.y, a[1]); a[2] = fmaf(wv, v0.z, a[2]); a[3] = fmaf(wv, v0.w, a[3]);
-            a[4] = fmaf(wv, v1.x, a[4]); a[5] = fmaf(wv, v1.y, a[5]); a[6] = fmaf(wv, v1.z, a[6]); a[7] = fmaf(wv, v1.w, a[7]);
+        }
+        if (part == 1) {
+#pragma unroll
+            for (int g = 0; g < kValueGroup; g++) part_s[g * hidden + o] = a[g];
+        }
+    }
+    __syncthreads();
+    if (part == 0) {
+        const bool have2 = blockDim.x >= 2 * hidden;
+        if (!have2) {  // fewer than 2*hidden threads: finish the second half here
+            for (int i = 181; i < kPoints; i++) {
+                const float wv = ip1_wt[(size_t)i * hidden + o];
+#pragma unroll
+                for (int g = 0; g < kValueGroup; g++) a[g] = fmaf(wv, v_s[i * kValueGroup + g], a[g]);
+            }
         }
 #pragma unroll
-        for (int g = 0; g < kValueGroup; g++) h_s[g * hidden + o] = elu1(a[g] + ip1_b[o]);
+        for (int g = 0; g < kValueGroup; g++)
+            h_s[g * hidden + o] = elu1(a[g] + (have2 ? part_s[g * hidden + o] : 0.0f) + ip1_b[o]);
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
     if (warp < kValueGroup && pos0 + warp < n) {
-        float a = 0.0f;
-        for (int o = lane; o < hidden; o += 32) a = fmaf(ip2_w[o], h_s[warp * hidden + o], a);
-        a = warp_sum(a);
-        if (lane == 0) winrate[pos0 + warp] = (1.0f + tanhf(a + ip2_b[0])) * 0.5f;
+        float s = 0.0f;
+        for (int k = lane; k < hidden; k += 32) s = fmaf(ip2_w[k], h_s[warp * hidden + k], s);
+        s = warp_sum(s);
+        if (lane == 0) winrate[pos0 + warp] = (1.0f + tanhf(s + ip2_b[0])) * 0.5f;
     }
 }
 
@@ -564,8 +585,8 @@ cudaError_t launch_policy_head(const float* zbuf, int chunk_rows, const float* b
 cudaError_t launch_value_head(const float* zbuf, int chunk_rows, const float* bias, const float* ip1_wt,
                               const float* ip1_b, int hidden, const float* ip2_w, const float* ip2_b, int n,
                               float* winrate, cudaStream_t st) {
-    const size_t smem = (kValueGroup * kPoints + kValueGroup * hidden) * sizeof(float);
-    value_head_kernel<<<(n + kValueGroup - 1) / kValueGroup, 256, smem, st>>>(zbuf, chunk_rows, bias, ip1_wt, ip1_b, hidden,
+    const size_t smem = (kValueGroup * kPoints + 2 * kValueGroup * hidden) * sizeof(float);
+    value_head_kernel<<<(n + kValueGroup - 1) / kValueGroup, kValueThreads, smem, st>>>(zbuf, chunk_rows, bias, ip1_wt, ip1_b, hidden,
                                                                              ip2_w, ip2_b, n, winrate);
     return cudaGetLastError();
 }
