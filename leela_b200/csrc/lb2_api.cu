@@ -70,6 +70,7 @@ struct HostIp {
 struct TrunkLayerDev {
     int k, c_in, c_out;
     __half* wpk = nullptr;
+    __half* wpk2 = nullptr;  // CTA-pair packing
     float* bias = nullptr;
 };
 
@@ -111,7 +112,7 @@ struct DeviceState {
     uint32_t epoch = 0;
     unsigned long long* trace = nullptr;   // debug timeline buffer (option "trace")
     std::vector<cudaEvent_t> prof_events;  // (start, stop) pairs around trunk launches
-    long plan_key[7] = {-1, -1, -1, -1, -1, -1, -1};  // n, run0, run1, limit0, limit1, workspace pointers
+    long plan_key[8] = {-1, -1, -1, -1, -1, -1, -1, -1};  // n, run0, run1, limit0, limit1, workspace pointers
 };
 
 struct Request {
@@ -142,6 +143,7 @@ struct lb2_ctx {
     long trunk_mode = 1;
     long max_batch = 512;
     long profile_trunk = 0;
+    long cta_pair = 1;
     std::atomic<long> launches{0};
     std::mutex eval_mu;
     // async submission
@@ -181,6 +183,27 @@ std::vector<__half> pack_trunk_weights(const HostConv& c) {
     return out;
 }
 
+// CTA-pair packing: [slab][tap group][rank][tap][2 chunks][c_out/2][8]; rank r holds output channels
+// [r*c_out/2, (r+1)*c_out/2) — the half of the MMA's B operand that CTA r of the pair stages.
+std::vector<__half> pack_trunk_weights_pair(const HostConv& c) {
+    const int kk = c.k * c.k, nh = c.c_out / 2;
+    std::vector<__half> out((size_t)kk * c.c_in * c.c_out);
+    int ng, gb[3], ge[3];
+    tap_groups(c.k, &ng, gb, ge);
+    size_t o = 0;
+    for (int s = 0; s < c.c_in / 16; s++)
+        for (int g = 0; g < ng; g++)
+            for (int r = 0; r < 2; r++)
+                for (int t = gb[g]; t < ge[g]; t++)
+                    for (int j = 0; j < 2; j++)
+                        for (int n = 0; n < nh; n++)
+                            for (int e = 0; e < 8; e++) {
+                                const int ci = 16 * s + 8 * j + e, co = r * nh + n;
+                                out[o++] = __float2half_rn(c.w[((size_t)co * c.c_in + ci) * kk + t]);
+                            }
+    return out;
+}
+
 template <class T>
 int upload(T** dst, const void* src, size_t bytes) {
     CU_TRY(cudaMalloc(reinterpret_cast<void**>(dst), bytes));
@@ -198,6 +221,9 @@ int upload_net(const lb2_net* net, NetDev* nd) {
         t.k = c.k; t.c_in = c.c_in; t.c_out = c.c_out;
         std::vector<__half> pk = pack_trunk_weights(c);
         int rc = upload(&t.wpk, pk.data(), pk.size() * sizeof(__half));
+        if (rc) return rc;
+        std::vector<__half> pk2 = pack_trunk_weights_pair(c);
+        rc = upload(&t.wpk2, pk2.data(), pk2.size() * sizeof(__half));
         if (rc) return rc;
         rc = upload(&t.bias, c.b.data(), c.b.size() * sizeof(float));
         if (rc) return rc;
@@ -258,8 +284,8 @@ void free_workspace(NetDev* nd) {
 int ensure_workspace(NetDev* nd, int kind, int cap) {
     if (nd->cap >= cap) return LB2_OK;
     free_workspace(nd);
-    nd->rows5 = round_up(cap * 441, lb2::kTileRows);
-    nd->rows3 = round_up(cap * 400, lb2::kTileRows);
+    nd->rows5 = round_up(cap * 441, 2 * lb2::kTileRows);  // whole CTA-pair items
+    nd->rows3 = round_up(cap * 400, 2 * lb2::kTileRows);
     const size_t x0_bytes = (size_t)4 * nd->rows5 * 16;
     const size_t act_bytes = (size_t)(nd->width / 8) * nd->rows3 * 16;
     CU_TRY(cudaMalloc(&nd->planes, (size_t)cap * lb2::kPoints * sizeof(uint32_t)));
@@ -272,7 +298,7 @@ int ensure_workspace(NetDev* nd, int kind, int cap) {
     const size_t out_elems = kind == LB2_POLICY ? (size_t)cap * lb2::kPoints : (size_t)cap;
     CU_TRY(cudaMalloc(&nd->out, out_elems * sizeof(float)));
     CU_TRY(cudaMalloc(&nd->zbuf, (size_t)18 * nd->rows3 * sizeof(float)));
-    nd->flags_stride = nd->rows5 / lb2::kTileRows + 1;
+    nd->flags_stride = nd->rows5 / lb2::kTileRows + 2;
     CU_TRY(cudaMalloc(&nd->flags, (size_t)lb2::kMaxJobs * nd->flags_stride * sizeof(uint32_t)));
     CU_TRY(cudaMemset(nd->flags, 0, (size_t)lb2::kMaxJobs * nd->flags_stride * sizeof(uint32_t)));
     int rc;
@@ -304,6 +330,7 @@ int ensure_device_staging(DeviceState* d, int cap) {
 struct JobPlan {
     std::vector<lb2::LayerJob> jobs;
     std::vector<int> round_of;  // launch round (layer depth) of each job, for per-layer mode
+    std::vector<int> tiles;     // 256-row tiles of each job
     int total_items = 0;
     const __half* last_act[2] = {nullptr, nullptr};
     int tmap_base[2] = {0, 3};
@@ -311,7 +338,7 @@ struct JobPlan {
 
 // Interleave the two nets layer by layer: P1 V1 P2 V2 ... so that one launch round holds
 // independent jobs of equal depth.
-JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2]) {
+JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2], bool pair) {
     JobPlan pl;
     size_t depth = 0;
     for (int k = 0; k < 2; k++)
@@ -330,7 +357,8 @@ JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2]) {
             J.halo = first ? 48 : 24;
             J.n_slabs = t.c_in / 16;
             J.n_out = t.c_out;
-            J.n_items = (n * J.S * J.S + lb2::kTileRows - 1) / lb2::kTileRows;
+            const int n_tiles = (n * J.S * J.S + lb2::kTileRows - 1) / lb2::kTileRows;
+            J.n_items = pair ? (n_tiles + 1) / 2 : n_tiles;
             J.item_base = pl.total_items;
             J.remap = first ? 1 : 0;
             // buffers: x0 -> act0 -> act1 -> act0 ...
@@ -340,10 +368,11 @@ JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2]) {
             J.dep_job = prev_job[k];
             if (J.dep_job >= 0) {
                 J.dep_remap = pl.jobs[J.dep_job].remap;
-                J.dep_n_items = pl.jobs[J.dep_job].n_items;
+                J.dep_n_items = pl.tiles[J.dep_job];
             }
             J.n_pos = n;
             J.wpk = t.wpk;
+            J.wpk2 = t.wpk2;
             J.bias = t.bias;
             J.flags = nd.flags + (size_t)l * nd.flags_stride;
             if (l + 1 == nd.trunk.size() && limit_layers[k] > (int)nd.trunk.size()) {
@@ -356,6 +385,7 @@ JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2]) {
             prev_job[k] = (int)pl.jobs.size();
             pl.jobs.push_back(J);
             pl.round_of.push_back((int)l);
+            pl.tiles.push_back(n_tiles);
             pl.total_items += J.n_items;
             pl.last_act[k] = J.out;
         }
@@ -365,11 +395,12 @@ JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2]) {
 
 int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers[2], cudaStream_t st,
               JobPlan* plan_out) {
-    JobPlan pl = plan_jobs(d, run, n, limit_layers);
+    const bool pair = ctx->cta_pair != 0 && d->sm_count >= 2;
+    JobPlan pl = plan_jobs(d, run, n, limit_layers, pair);
     if (pl.jobs.empty()) return fail(LB2_ERR_STATE, "no trunk layers to run");
     if ((int)pl.jobs.size() > lb2::kMaxLaunchJobs) return fail(LB2_ERR_UNSUPPORTED, "too many layers");
-    const long key[7] = {n, run[0], run[1], limit_layers[0], limit_layers[1],
-                         (long)reinterpret_cast<uintptr_t>(d->net[0].act[0]), (long)reinterpret_cast<uintptr_t>(d->net[1].act[0])};
+    const long key[8] = {n, run[0], run[1], limit_layers[0], limit_layers[1],
+                         (long)reinterpret_cast<uintptr_t>(d->net[0].act[0]), (long)reinterpret_cast<uintptr_t>(d->net[1].act[0]), pair};
     if (memcmp(key, d->plan_key, sizeof key)) {
         // the job table on the device is reused by back-to-back launches of the same shape;
         // rewrite it only when the shape changes, after earlier work has drained
@@ -406,8 +437,8 @@ int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers
         P.item_begin = 0;
         P.item_end = pl.total_items;
         P.use_flags = 1;
-        const int grid = std::min(d->sm_count, pl.total_items);
-        CU_TRY(lb2::launch_trunk(P, grid, true, st));
+        const int grid = pair ? std::min(d->sm_count & ~1, 2 * pl.total_items) : std::min(d->sm_count, pl.total_items);
+        CU_TRY(lb2::launch_trunk(P, grid, true, pair, st));
         ctx->launches++;
     } else {
         P.use_flags = 0;
@@ -417,8 +448,9 @@ int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers
             while (e < pl.jobs.size() && pl.round_of[e] == pl.round_of[i]) e++;
             P.item_begin = pl.jobs[i].item_base;
             P.item_end = pl.jobs[e - 1].item_base + pl.jobs[e - 1].n_items;
-            const int grid = std::min(d->sm_count, P.item_end - P.item_begin);
-            CU_TRY(lb2::launch_trunk(P, grid, false, st));
+            const int items = P.item_end - P.item_begin;
+            const int grid = pair ? std::min(d->sm_count & ~1, 2 * items) : std::min(d->sm_count, items);
+            CU_TRY(lb2::launch_trunk(P, grid, false, pair, st));
             ctx->launches++;
             i = e;
         }
@@ -670,7 +702,7 @@ void lb2_destroy(lb2_ctx* ctx) {
         cudaStreamSynchronize(d.stream);
         for (int k = 0; k < 2; k++) {
             NetDev& nd = d.net[k];
-            for (auto& t : nd.trunk) { cudaFree(t.wpk); cudaFree(t.bias); }
+            for (auto& t : nd.trunk) { cudaFree(t.wpk); cudaFree(t.wpk2); cudaFree(t.bias); }
             cudaFree(nd.head_wt); cudaFree(nd.head_b); cudaFree(nd.ip1_wt); cudaFree(nd.ip1_b);
             cudaFree(nd.ip2_w); cudaFree(nd.ip2_b);
             free_workspace(&nd);
@@ -831,6 +863,8 @@ int lb2_set_option(lb2_ctx* ctx, const char* name, long value) {
             cudaFree(d.trace);
             d.trace = nullptr;
         }
+    } else if (!strcmp(name, "cta_pair")) {
+        ctx->cta_pair = value ? 1 : 0;
     } else if (!strcmp(name, "profile_trunk")) {
         ctx->profile_trunk = value ? 1 : 0;
     } else if (!strcmp(name, "max_batch")) {
@@ -846,6 +880,7 @@ long lb2_get_option(lb2_ctx* ctx, const char* name) {
     if (!ctx || !name) return -1;
     if (!strcmp(name, "trunk_mode")) return ctx->trunk_mode;
     if (!strcmp(name, "max_batch")) return ctx->max_batch;
+    if (!strcmp(name, "cta_pair")) return ctx->cta_pair;
     if (!strcmp(name, "sm_count")) return ctx->dev.empty() ? 0 : ctx->dev[0].sm_count;
     if (!strcmp(name, "trunk_ns") || !strcmp(name, "trunk_launches_timed")) {
         // device time spent in trunk launches since the last query (profile_trunk = 1); resets

@@ -111,6 +111,21 @@ __device__ __forceinline__ float elu_fast(float v) {
     return fmaxf(v, fminf(e - 1.0f, 0.0f));  // v>0: e-1>0 -> max(v,0)=v; v<=0: e-1 in (-1,0] and e-1 >= v
 }
 
+// Work geometry of one CTA for one launch: which items it walks and which 256-row tile of an
+// item is its own. Single mode: item == tile, CTA b takes items b, b+G, ... Pair mode
+// (cta_group::2): item == two adjacent tiles, cluster c takes items c, c+G/2, ...; the CTA with
+// cluster rank r owns tile 2*item + r.
+template <bool kPair>
+struct Walk {
+    int first, step, rank;
+    __device__ __forceinline__ Walk(const TrunkParams& P) {
+        if (kPair) { rank = (int)cluster_ctarank(); first = P.item_begin + (blockIdx.x >> 1); step = gridDim.x >> 1; }
+        else { rank = 0; first = P.item_begin + blockIdx.x; step = gridDim.x; }
+    }
+    __device__ __forceinline__ int tile(int item_in_job) const { return kPair ? 2 * item_in_job + rank : item_in_job; }
+};
+
+template <bool kPair>
 __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_constant__ TrunkParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -118,25 +133,28 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
     uint64_t* tfull_bar = empty_bar + kStages;   // [2] accumulator ready   (MMA -> epilogue)
     uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulator drained (epilogue -> MMA)
     uint64_t* pub_bar = tempty_bar + 2;          // [kPubDepth] tile stored (epilogue -> publisher)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pub_bar + kPubDepth);
+    uint64_t* pfull_bar = pub_bar + kPubDepth;   // [kStages] pair mode: the peer CTA's stage landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pfull_bar + kStages);
     volatile uint32_t* pub_done = tmem_slot + 1; // tiles published so far by this CTA
     float* bias_all = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);  // [kMaxLaunchJobs][128]
     float* headw_all = bias_all + kMaxLaunchJobs * 128;                              // [2][9][128]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const Walk<kPair> W(P);
+    const bool leader = (W.rank == 0);
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 127u) __trap();  // TMA destinations need 128-byte alignment
-        for (int i = 0; i < kStages; i++) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, kEpilogueWarps); }
+        for (int i = 0; i < kStages; i++) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); mbar_init(pfull_bar + i, 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, kPair ? 2 * kEpilogueWarps : kEpilogueWarps); }
         for (int i = 0; i < kPubDepth; i++) mbar_init(pub_bar + i, kEpilogueWarps);
         *pub_done = 0;
         fence_mbar_init();
         fence_proxy_async_smem();
         for (int i = 0; i < kMaxTensorMaps; i++) tma_prefetch_desc(&P.tmaps[i]);
     }
-    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    if (warp == 1) { if (kPair) tmem_alloc_pair<512>(tmem_slot); else tmem_alloc<512>(tmem_slot); }
     const LayerJob* __restrict__ jobs = P.jobs;
     // every job's bias and both fused-head weight sets stay resident in smem for the whole launch
     for (int i = threadIdx.x; i < P.n_jobs * 128; i += blockDim.x) {
@@ -150,18 +168,20 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
     }
     tc_fence_before_sync();
     __syncthreads();
+    if (kPair) cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         // ================================ TMA producer ================================
         // The whole warp walks the item list; lanes poll the dependency flags in parallel, one
-        // elected lane issues the copies.
+        // elected lane issues the copies. In pair mode each CTA loads the A slab of its own tile
+        // and its half of the output channels of the B block.
         int stage = 0; uint32_t phase = 0; int j = 0; uint32_t pit = 0;
-        for (int q = P.item_begin + blockIdx.x; q < P.item_end; q += gridDim.x, pit++) {
+        for (int q = W.first; q < P.item_end; q += W.step, pit++) {
             while (q >= jobs[j].item_base + jobs[j].n_items) j++;
             const LayerJob& J = jobs[j];
-            const int tile = q - J.item_base;
+            const int tile = W.tile(q - J.item_base);
             const int halo = J.halo, ksize = J.ksize, n_out = J.n_out, n_slabs = J.n_slabs, tmap = J.tmap;
             if (lane == 0) { LB2_TRACE(pit, 0); if (P.trace && pit < (uint32_t)kTraceItems) P.trace[((size_t)blockIdx.x * kTraceItems + pit) * kTraceEvents + 15] = (unsigned long long)q; }
             if (P.use_flags && J.dep_job >= 0) {
@@ -176,21 +196,22 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             const uint32_t a_bytes = rows_halo * 32;
             const int row0_8 = (tile * kTileRows - halo) / 8;  // exact: both multiples of 8
             const int ng = n_tap_groups(ksize);
-            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(J.wpk);
+            const int n_mine = kPair ? (n_out >> 1) : n_out;   // output channels whose weights this CTA stages
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(kPair ? J.wpk2 : J.wpk);
             if (elect_one()) {
                 int st = stage; uint32_t ph = phase;  // private walk; all lanes advance the shared view below
                 LB2_TRACE(pit, 1);
                 fence_proxy_async();  // order the TMA (async proxy) reads after the acquires above
                 for (int s = 0; s < n_slabs; s++) {
                     for (int g = 0; g < ng; g++) {
-                        const uint32_t b_bytes = (tap_group_end(ksize, g) - tap_group_begin(g)) * n_out * 32;
+                        const uint32_t b_bytes = (tap_group_end(ksize, g) - tap_group_begin(g)) * n_mine * 32;
                         mbar_wait(empty_bar + st, ph ^ 1);
                         uint8_t* sa = smem + st * kStageBytes;
                         const bool skip_b = (P.debug_flags & 8) != 0, skip_a = (P.debug_flags & 16) != 0;
                         mbar_arrive_expect_tx(full_bar + st, (skip_a ? 0u : a_bytes) + (skip_b ? 0u : b_bytes));
                         if (!skip_a) tma_load_3d(sa, &P.tmaps[tmap], full_bar + st, 0, row0_8, 2 * s);
-                        if (!skip_b) bulk_load_1d(sa + kASlabBytes, wsrc, b_bytes, full_bar + st);
-                        wsrc += b_bytes;
+                        if (!skip_b) bulk_load_1d(sa + kASlabBytes, wsrc + (kPair ? W.rank * b_bytes : 0u), b_bytes, full_bar + st);
+                        wsrc += kPair ? 2 * b_bytes : b_bytes;
                         if (++st == kStages) { st = 0; ph ^= 1; }
                         if (s == 0 && g == 0) LB2_TRACE(pit, 2);
                     }
@@ -204,11 +225,27 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             stage %= kStages;
             __syncwarp();
         }
+    } else if (warp == 1 && !leader) {
+        // ================================ pair mode, peer CTA ==========================
+        // No MMAs are issued here (the leader's tcgen05.mma.cta_group::2 drives both SMs); this
+        // warp only tells the leader when each of OUR stages has landed.
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0; int j = 0;
+            for (int q = W.first; q < P.item_end; q += W.step) {
+                while (q >= jobs[j].item_base + jobs[j].n_items) j++;
+                const int n_st = jobs[j].n_slabs * n_tap_groups(jobs[j].ksize);
+                for (int s = 0; s < n_st; s++) {
+                    mbar_wait(full_bar + stage, phase);
+                    mbar_arrive_remote(pfull_bar + stage, 0);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
         // The whole warp walks the pipeline; one elected lane issues the tcgen05 instructions.
         int stage = 0; uint32_t phase = 0; int j = 0; uint32_t it = 0;
-        for (int q = P.item_begin + blockIdx.x; q < P.item_end; q += gridDim.x, it++) {
+        for (int q = W.first; q < P.item_end; q += W.step, it++) {
             while (q >= jobs[j].item_base + jobs[j].n_items) j++;
             const LayerJob& J = jobs[j];
             const int ksize = J.ksize, n_out = J.n_out, n_slabs = J.n_slabs, halo = J.halo;
@@ -218,13 +255,14 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             mbar_wait(tempty_bar + acc, acc_phase ^ 1);
             tc_fence_after_sync();
             if (lane == 0) LB2_TRACE(it, 5);
-            const uint32_t idesc = umma_idesc_f16(128, n_out);
+            const uint32_t idesc = umma_idesc_f16(kPair ? 256 : 128, n_out);
             const int rows_halo = kTileRows + 2 * halo;
+            const int n_mine = kPair ? (n_out >> 1) : n_out;   // B rows held per CTA
             // descriptor = hi32 (SBO = 128 B, version 1) : lo32 (LBO << 16 | start address >> 4)
             const uint32_t desc_hi = (128u >> 4) | (1u << 14);
             const uint32_t a_lo_base = ((uint32_t)(rows_halo * 16) >> 4) << 16;
-            const uint32_t b_lo_base = ((uint32_t)(n_out * 16) >> 4) << 16;
-            const uint32_t b_step = (uint32_t)(n_out * 32) >> 4;  // one tap of B, in 16-byte units
+            const uint32_t b_lo_base = ((uint32_t)(n_mine * 16) >> 4) << 16;
+            const uint32_t b_step = (uint32_t)(n_mine * 32) >> 4;  // one tap of B, in 16-byte units
             const uint32_t d0 = tmem_base + (acc * 2 + 0) * 128;
             const uint32_t d1 = tmem_base + (acc * 2 + 1) * 128;
             const int ng = n_tap_groups(ksize);
@@ -233,6 +271,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             for (int s = 0; s < n_slabs; s++) {
                 for (int g = 0; g < ng; g++) {
                     mbar_wait(full_bar + stage, phase);
+                    if (kPair) mbar_wait(pfull_bar + stage, phase);
                     tc_fence_after_sync();
                     if (lane == 0 && s == 0 && g == 0) LB2_TRACE(it, 6);
                     __syncwarp();
@@ -247,9 +286,9 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                                 const int off = (t / 3 - 1) * S + (t % 3 - 1) * DX;
                                 const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo_base | (b16 & 0x3FFFu));
                                 const uint32_t a0 = a16 + off;
-                                umma_f16(d0, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo_base | (a0 & 0x3FFFu)), bdesc, idesc, accumulate);
+                                umma_f16<kPair>(d0, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo_base | (a0 & 0x3FFFu)), bdesc, idesc, accumulate);
                                 if (!(P.debug_flags & 32))
-                                    umma_f16(d1, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo_base | ((a0 + 128) & 0x3FFFu)), bdesc, idesc, accumulate);
+                                    umma_f16<kPair>(d1, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo_base | ((a0 + 128) & 0x3FFFu)), bdesc, idesc, accumulate);
                                 accumulate = 1;
                                 b16 += b_step;
                             }
@@ -260,20 +299,20 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                                 const int off = (kr - pad) * S + (kc - pad) * DX;
                                 const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo_base | (b16 & 0x3FFFu));
                                 const uint32_t a0 = a16 + off;
-                                umma_f16(d0, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo_base | (a0 & 0x3FFFu)), bdesc, idesc, accumulate);
-                                umma_f16(d1, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo_base | ((a0 + 128) & 0x3FFFu)), bdesc, idesc, accumulate);
+                                umma_f16<kPair>(d0, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo_base | (a0 & 0x3FFFu)), bdesc, idesc, accumulate);
+                                umma_f16<kPair>(d1, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo_base | ((a0 + 128) & 0x3FFFu)), bdesc, idesc, accumulate);
                                 accumulate = 1;
                                 b16 += b_step;
                                 if (++kc == 5) { kc = 0; kr++; }
                             }
                         }
-                        umma_commit(empty_bar + stage);  // frees the smem stage when these MMAs finish
+                        umma_commit<kPair>(empty_bar + stage);  // frees the smem stage (in both CTAs) when these MMAs finish
                     }
                     __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
-            if (elect_one()) umma_commit(tfull_bar + acc);  // accumulator complete -> epilogue
+            if (elect_one()) umma_commit<kPair>(tfull_bar + acc);  // accumulator complete -> epilogue (both CTAs)
             if (lane == 0) LB2_TRACE(it, 7);
             __syncwarp();
         }
@@ -283,10 +322,10 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         const int quad = warp & 3;        // TMEM lane quadrant this warp may read
         const int half = ew >> 2;         // which half of the output channels
         int j = 0; uint32_t it = 0;
-        for (int q = P.item_begin + blockIdx.x; q < P.item_end; q += gridDim.x, it++) {
+        for (int q = W.first; q < P.item_end; q += W.step, it++) {
             while (q >= jobs[j].item_base + jobs[j].n_items) j++;
             const LayerJob& J = jobs[j];
-            const int tile = q - J.item_base;
+            const int tile = W.tile(q - J.item_base);
             const int n_out = J.n_out, chunk_rows = J.out_chunk_rows, n_pos = J.n_pos;
             const bool head = J.head_taps != 0, remap = J.remap != 0, wide = (J.S == 21);
             __half* __restrict__ out = J.out;
@@ -383,10 +422,13 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                     for (int t = 0; t < 9; t++) zb[(size_t)t * chunk_rows] = valid ? z[t] : 0.0f;
                 }
             }
-            // accumulator drained: hand it back to the MMA warp
+            // accumulator drained: hand it back to the MMA warp (of the leader CTA in pair mode)
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar + acc);
+            if (lane == 0) {
+                if (kPair && !leader) mbar_arrive_remote(tempty_bar + acc, 0);
+                else mbar_arrive(tempty_bar + acc);
+            }
             if (warp == 2 && lane == 0) LB2_TRACE(it, 10);
             if (P.use_flags) {
                 // hand the tile to the publisher warp: this warp's stores happen-before its arrive
@@ -403,12 +445,12 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         // then release its flag for the consumers' acquire (cumulative over the mbarrier sync).
         if (P.use_flags && lane == 0) {
             int j = 0; uint32_t it = 0;
-            for (int q = P.item_begin + blockIdx.x; q < P.item_end; q += gridDim.x, it++) {
+            for (int q = W.first; q < P.item_end; q += W.step, it++) {
                 while (q >= jobs[j].item_base + jobs[j].n_items) j++;
                 mbar_wait(pub_bar + (it % kPubDepth), (it / kPubDepth) & 1);
                 LB2_TRACE(it, 11);
                 fence_proxy_async();  // generic-proxy stores -> visible to other CTAs' TMA loads
-                st_release_gpu(jobs[j].flags + (q - jobs[j].item_base), P.epoch);
+                st_release_gpu(jobs[j].flags + W.tile(q - jobs[j].item_base), P.epoch);
                 LB2_TRACE(it, 12);
                 *pub_done = it + 1;
             }
@@ -417,7 +459,8 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
 
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<512>(tmem_base);
+    if (kPair) cluster_sync_all();  // nobody exits (or frees TMEM) while its peer may still signal it
+    if (warp == 1) { if (kPair) tmem_dealloc_pair<512>(tmem_base); else tmem_dealloc<512>(tmem_base); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -559,21 +602,33 @@ cudaError_t launch_expand(const uint32_t* planes, const uint8_t* rotation, int n
 }
 
 cudaError_t trunk_kernel_setup() {
-    return cudaFuncSetAttribute(trunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(trunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(trunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytes);
 }
 
-cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, cudaStream_t st) {
+cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool pair, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kTrunkThreads);
     cfg.dynamicSmemBytes = kTrunkSmemBytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = cooperative ? 1 : 0;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pair) {
+        // CTA pairs: clusters of 2 are always co-scheduled; with one CTA per SM and grid <= #SMs
+        // every cluster is resident, which is all the dataflow needs
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        na++;
+    } else {
+        attr[na].id = cudaLaunchAttributeCooperative;
+        attr[na].val.cooperative = cooperative ? 1 : 0;
+        na++;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, trunk_kernel, p);
+    cfg.numAttrs = na;
+    return pair ? cudaLaunchKernelEx(&cfg, trunk_kernel<true>, p) : cudaLaunchKernelEx(&cfg, trunk_kernel<false>, p);
 }
 
 cudaError_t launch_policy_head(const float* zbuf, int chunk_rows, const float* bias, const uint8_t* rotation, int n,

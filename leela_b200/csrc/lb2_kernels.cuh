@@ -39,7 +39,7 @@ constexpr int kTraceEvents = 16;
 
 // One trunk layer of one net over the whole batch.
 struct LayerJob {
-    int32_t n_items;         // 256-row tiles of this job's row space
+    int32_t n_items;         // work items: 256-row tiles, or pairs of tiles in CTA-pair mode
     int32_t item_base;       // index of its first item in the launch-wide item order
     int32_t S;               // row-space stride (20 or 21)
     int32_t ksize;           // 3 or 5
@@ -50,12 +50,13 @@ struct LayerJob {
     int32_t remap;           // 1: outputs are re-addressed from S=21 space into S=20 space
     int32_t dep_job;         // job producing this job's input in the same launch, or -1
     int32_t dep_remap;       // that job's remap flag
-    int32_t dep_n_items;     // that job's item count
+    int32_t dep_n_items;     // that job's tile count
     int32_t n_pos;           // positions in the batch
     int32_t out_chunk_rows;  // rows per chunk plane of the output buffer
     int32_t head_taps;       // 9: the net's final 3x3 conv to 1 channel is fused into this job's epilogue
     int32_t head_slot;       // which resident head-weight slot (0 = policy, 1 = value)
     const __half* wpk;       // packed weights: per (slab, tap group): [tap][2 chunks][n_out][8]
+    const __half* wpk2;      // CTA-pair packing: per (slab, tap group): [rank][tap][2 chunks][n_out/2][8]
     const float* bias;       // [n_out]
     __half* out;             // output activation buffer
     uint32_t* flags;         // [n_items] completion flags (value = launch epoch)
@@ -78,7 +79,7 @@ struct TrunkParams {
 // launchers (lb2_kernels.cu)
 cudaError_t launch_expand(const uint32_t* planes, const uint8_t* rotation, int n, __half* x0, int chunk_rows,
                           cudaStream_t st);
-cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, cudaStream_t st);
+cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool pair, cudaStream_t st);
 cudaError_t launch_policy_head(const float* zbuf, int chunk_rows, const float* bias, const uint8_t* rotation, int n,
                                float temp, float* probs, cudaStream_t st);
 cudaError_t launch_value_head(const float* zbuf, int chunk_rows, const float* bias, const float* ip1_wt,

@@ -108,6 +108,23 @@ def test_launch_modes_bit_identical(ev, ref_golden):
     assert np.array_equal(p0, p1) and np.array_equal(v0, v1)
 
 
+def test_cta_pair_and_single_cta_bit_identical(ev, ref_golden):
+    """tcgen05 cta_group::2 (CTA pairs, M = 256 per instruction) vs cta_group::1: same K order, same bits."""
+    g = ref_golden
+    args = (g["policy_planes"], g["value_planes"], g["rotation"], TEMP)
+    try:
+        ev.set_option("cta_pair", 0)
+        p0, v0 = ev.eval_both(*args)
+        ev.set_option("trunk_mode", 0)
+        p2, v2 = ev.eval_both(*args)
+    finally:
+        ev.set_option("cta_pair", 1)
+        ev.set_option("trunk_mode", 1)
+    p1, v1 = ev.eval_both(*args)
+    assert np.array_equal(p0, p1) and np.array_equal(v0, v1)
+    assert np.array_equal(p0, p2) and np.array_equal(v0, v2)
+
+
 def test_batch_and_slot_invariance(ev, ref_golden):
     """A position's result does not depend on batch size, its slot, or chunking (tiles straddle
     positions; 400 rows per position is not a multiple of the 256-row tile)."""

@@ -33,8 +33,9 @@ def layer_step(kind, n_layers, n, mode):
     planes = (g["policy_planes"] if kind == 0 else g["value_planes"])[:n]
     rot = g["rotation"][:n]
     ev = capi.Evaluator(policy=w if kind == 0 else None, value=w if kind == 1 else None)
-    ev.set_option("trunk_mode", mode)
-    print("backend:", ev.backend, flush=True)
+    ev.set_option("trunk_mode", mode & 1)
+    ev.set_option("cta_pair", (mode >> 1) & 1)
+    print("backend:", ev.backend, "mode", mode, flush=True)
     c_out = w.convs[n_layers - 1].c_out
     t = time.time()
     got = ev.debug_trunk(kind, planes, rot, n_layers, c_out)
@@ -59,7 +60,8 @@ def full_step(n, mode):
     g = golden()
     pw, vw = synth.policy_weights(), synth.value_weights()
     ev = capi.Evaluator(policy=pw, value=vw)
-    ev.set_option("trunk_mode", mode)
+    ev.set_option("trunk_mode", mode & 1)
+    ev.set_option("cta_pair", (mode >> 1) & 1)
     pp, vp, rot = g["policy_planes"][:n], g["value_planes"][:n], g["rotation"][:n]
     t = time.time()
     probs, win = ev.eval_both(pp, vp, rot, float(g["softmax_temp"]))
@@ -75,18 +77,14 @@ def full_step(n, mode):
 
 
 STEPS = {
-    "p1": lambda: layer_step(0, 1, 2, 0),
-    "p1_swap": lambda: (os.environ.__setitem__("LB2_DEBUG_FLAGS", "1"), layer_step(0, 1, 2, 0)),
-    "p2": lambda: layer_step(0, 2, 2, 0),
-    "p3": lambda: layer_step(0, 3, 2, 0),
-    "p12": lambda: layer_step(0, 12, 2, 0),
-    "v1": lambda: layer_step(1, 1, 2, 0),
-    "v2": lambda: layer_step(1, 2, 2, 0),
-    "v11": lambda: layer_step(1, 11, 2, 0),
-    "full_layered": lambda: full_step(16, 0),
-    "p12_mega": lambda: layer_step(0, 12, 3, 1),
-    "full_mega": lambda: full_step(16, 1),
-    "full_mega96": lambda: full_step(96, 1),
+    # mode bit0: 1 = persistent dataflow launch, bit1: 1 = CTA pairs (cta_group::2)
+    "p1_pair_layered": lambda: layer_step(0, 1, 2, 2),
+    "p2_pair_layered": lambda: layer_step(0, 2, 2, 2),
+    "v2_pair_layered": lambda: layer_step(1, 2, 2, 2),
+    "p12_pair_mega": lambda: layer_step(0, 12, 3, 3),
+    "full_pair_mega": lambda: full_step(16, 3),
+    "full_pair_mega96": lambda: full_step(96, 3),
+    "full_single_mega96": lambda: full_step(96, 1),
 }
 
 if __name__ == "__main__":
@@ -97,7 +95,7 @@ if __name__ == "__main__":
     for name in names:
         print(f"=== {name}", flush=True)
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "step", name], timeout=150,
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "step", name], timeout=90,
                                capture_output=True, text=True)
             print(r.stdout[-4000:], flush=True)
             if r.returncode != 0:

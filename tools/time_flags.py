@@ -18,8 +18,9 @@ rot = torch.from_numpy(g["rotation"][:B].copy()).to(dev)
 probs = torch.empty((B, 361), device=dev); win = torch.empty((B,), device=dev)
 ev = capi.Evaluator(policy=synth.policy_weights(), value=synth.value_weights())
 ev.set_option("max_batch", max(B, 512))
-for mode in (1, 0):
-    ev.set_option("trunk_mode", mode)
+for mode in (1, 0, 2):
+    ev.set_option("trunk_mode", 1 if mode else 0)
+    ev.set_option("cta_pair", 0 if mode == 2 else 1)
     for which in ("both", "policy", "value"):
         a = (pp.data_ptr(), vp.data_ptr(), rot.data_ptr(), B, 0.75, probs.data_ptr() if which != "value" else None,
              win.data_ptr() if which != "policy" else None)
@@ -32,6 +33,6 @@ for mode in (1, 0):
         for _ in range(20):
             ev.eval_both_device(*a, stream=st.cuda_stream)
         e1.record(st); torch.cuda.synchronize()
-        print(f"flags={os.environ.get('LB2_DEBUG_FLAGS','0')} mode={mode} {which:6s} B={B}: step {e0.elapsed_time(e1)/20*1e3:8.1f} us, "
+        print(f"flags={os.environ.get('LB2_DEBUG_FLAGS','0')} mode={mode}{'(single-cta)' if mode == 2 else ''} {which:6s} B={B}: step {e0.elapsed_time(e1)/20*1e3:8.1f} us, "
               f"trunk {ev.get_option('trunk_ns')/20/1e3:8.1f} us", flush=True)
         ev.set_option("profile_trunk", 0)
