@@ -80,6 +80,8 @@ struct NetDev {
     int head_c_in = 0;
     float *head_wt = nullptr, *head_b = nullptr;  // final conv weights transposed to [9 taps][c_in]
     float* zbuf = nullptr;                        // fused-head partial sums [2][9][rows3]
+    std::vector<std::vector<float>> h_bias;       // host copies for the constant-memory tables
+    std::vector<float> h_head_wt;
     int hidden = 0;
     float *ip1_wt = nullptr, *ip1_b = nullptr, *ip2_w = nullptr, *ip2_b = nullptr;
     // workspace
@@ -156,6 +158,27 @@ struct lb2_ctx {
 
 namespace {
 
+// The bias / head-weight tables are __constant__ symbols, i.e. one instance per device and
+// process. Remember which context's nets they currently hold and reload on a switch.
+std::mutex g_const_mu;
+const void* g_const_owner[64][2] = {};
+
+int ensure_constants(lb2_ctx* ctx, DeviceState* d, bool run[2], cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_const_mu);
+    for (int k = 0; k < 2; k++) {
+        if (!run[k] || d->id >= 64) continue;
+        const void* owner = ctx->nets[k].get();
+        if (g_const_owner[d->id][k] == owner) continue;
+        NetDev& nd = d->net[k];
+        CU_TRY(cudaStreamSynchronize(st));
+        for (size_t l = 0; l < nd.h_bias.size(); l++)
+            CU_TRY(lb2::upload_constants(k, (int)l, nd.h_bias[l].data(), (int)nd.h_bias[l].size(), st));
+        CU_TRY(lb2::upload_head_weights(k, nd.h_head_wt.data(), nd.head_c_in, st));
+        g_const_owner[d->id][k] = owner;
+    }
+    return LB2_OK;
+}
+
 // --------------------------------------------------------------------------------------------
 // weights
 // --------------------------------------------------------------------------------------------
@@ -214,6 +237,7 @@ int upload(T** dst, const void* src, size_t bytes) {
 int upload_net(const lb2_net* net, NetDev* nd) {
     const size_t nconv = net->convs.size();
     nd->trunk.clear();
+    nd->h_bias.clear();
     nd->width = 0;
     for (size_t l = 0; l + 1 < nconv; l++) {
         const HostConv& c = net->convs[l];
@@ -227,6 +251,7 @@ int upload_net(const lb2_net* net, NetDev* nd) {
         if (rc) return rc;
         rc = upload(&t.bias, c.b.data(), c.b.size() * sizeof(float));
         if (rc) return rc;
+        nd->h_bias.push_back(c.b);
         nd->trunk.push_back(t);
         nd->width = std::max(nd->width, c.c_out);
     }
@@ -237,6 +262,7 @@ int upload_net(const lb2_net* net, NetDev* nd) {
         for (int t = 0; t < 9; t++) hwt[(size_t)t * h.c_in + c] = h.w[(size_t)c * 9 + t];
     int rc = upload(&nd->head_wt, hwt.data(), hwt.size() * sizeof(float));
     if (rc) return rc;
+    nd->h_head_wt = hwt;
     rc = upload(&nd->head_b, h.b.data(), sizeof(float));
     if (rc) return rc;
     if (net->kind == LB2_VALUE) {
@@ -371,6 +397,8 @@ JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2], bool 
                 J.dep_n_items = pl.tiles[J.dep_job];
             }
             J.n_pos = n;
+            J.net = k;
+            J.layer = (int)l;
             J.wpk = t.wpk;
             J.wpk2 = t.wpk2;
             J.bias = t.bias;
@@ -378,7 +406,6 @@ JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2], bool 
             if (l + 1 == nd.trunk.size() && limit_layers[k] > (int)nd.trunk.size()) {
                 // whole net: fold the final 3x3 conv to one channel into this layer's epilogue
                 J.head_taps = 9;
-                J.head_slot = k;
                 J.head_w = nd.head_wt;
                 J.zbuf = nd.zbuf;
             }
@@ -395,6 +422,10 @@ JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2], bool 
 
 int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers[2], cudaStream_t st,
               JobPlan* plan_out) {
+    {
+        int rc = ensure_constants(ctx, d, run, st);
+        if (rc) return rc;
+    }
     const bool pair = ctx->cta_pair != 0 && d->sm_count >= 2;
     JobPlan pl = plan_jobs(d, run, n, limit_layers, pair);
     if (pl.jobs.empty()) return fail(LB2_ERR_STATE, "no trunk layers to run");
@@ -697,6 +728,12 @@ void lb2_destroy(lb2_ctx* ctx) {
     }
     ctx->q_cv.notify_all();
     if (ctx->worker.joinable()) ctx->worker.join();
+    {
+        std::lock_guard<std::mutex> lk(g_const_mu);
+        for (auto& d : ctx->dev)
+            for (int k = 0; k < 2; k++)
+                if (d.id < 64 && g_const_owner[d.id][k] == ctx->nets[k].get()) g_const_owner[d.id][k] = nullptr;
+    }
     for (auto& d : ctx->dev) {
         cudaSetDevice(d.id);
         cudaStreamSynchronize(d.stream);
@@ -760,6 +797,7 @@ int lb2_net_finalize(lb2_net* net) {
     if (cv.size() < 3) return fail(LB2_ERR_UNSUPPORTED, "need at least 3 conv layers");
     if (cv[0].k != 5 || cv[0].c_in != LB2_INPUT_PLANES) return fail(LB2_ERR_UNSUPPORTED, "first layer must be 5x5 from 32 planes");
     for (size_t l = 0; l + 1 < cv.size(); l++) {
+        if (l >= (size_t)lb2::kMaxLayers) return fail(LB2_ERR_UNSUPPORTED, "too many layers");
         if (l > 0 && cv[l].k != 3) return fail(LB2_ERR_UNSUPPORTED, "layer %zu: only 3x3 after the first layer", l + 1);
         if (cv[l].c_out % 32 || cv[l].c_out > 128 || cv[l].c_in % 16)
             return fail(LB2_ERR_UNSUPPORTED, "layer %zu: channels %d->%d not supported", l + 1, cv[l].c_in, cv[l].c_out);

@@ -16,6 +16,12 @@
 
 namespace lb2 {
 
+// Per-layer biases and the two fused-head weight sets live in constant memory: every lane of an
+// epilogue warp reads the same address (one row per lane, all channels), which the constant cache
+// broadcasts without touching the shared-memory port the tensor cores are saturating.
+__constant__ float c_bias[2][kMaxLayers][128];
+__constant__ float c_headw[2][9][128];
+
 // Network::rotate_nn_idx (Network.cpp:1348-1379): bit2 swaps x/y first, bit0 flips y, bit1 flips x.
 __device__ __forceinline__ int rotate_idx(int v, int s) {
     int x = v % kBoard, y = v / kBoard;
@@ -127,17 +133,18 @@ struct Walk {
 
 template <bool kPair>
 __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_constant__ TrunkParams P) {
+    constexpr int kStages = kPair ? kStagesPair : kStagesSingle;
+    constexpr int kStageBytes = kPair ? kStageBytesPair : kStageBytesSingle;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-    uint64_t* empty_bar = full_bar + kStages;
-    uint64_t* tfull_bar = empty_bar + kStages;   // [2] accumulator ready   (MMA -> epilogue)
-    uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulator drained (epilogue -> MMA)
-    uint64_t* pub_bar = tempty_bar + 2;          // [kPubDepth] tile stored (epilogue -> publisher)
-    uint64_t* pfull_bar = pub_bar + kPubDepth;   // [kStages] pair mode: the peer CTA's stage landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pfull_bar + kStages);
-    volatile uint32_t* pub_done = tmem_slot + 1; // tiles published so far by this CTA
-    float* bias_all = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);  // [kMaxLaunchJobs][128]
-    float* headw_all = bias_all + kMaxLaunchJobs * 128;                              // [2][9][128]
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tfull_bar = empty_bar + kMaxStages;  // [2] accumulator ready   (MMA -> epilogue)
+    uint64_t* tempty_bar = tfull_bar + 2;          // [2] accumulator drained (epilogue -> MMA)
+    uint64_t* pub_bar = tempty_bar + 2;            // [kPubDepth] tile stored (epilogue -> publisher)
+    uint64_t* pfull_bar = pub_bar + kPubDepth;     // [kStages] pair mode: the peer CTA's stage landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pfull_bar + kMaxStages);
+    volatile uint32_t* pub_done = tmem_slot + 1;   // tiles published so far by this CTA
+    uint32_t* deps_ready = tmem_slot + 2;          // items whose dependencies the scout warp has seen satisfied
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -150,22 +157,13 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         for (int i = 0; i < 2; i++) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, kPair ? 2 * kEpilogueWarps : kEpilogueWarps); }
         for (int i = 0; i < kPubDepth; i++) mbar_init(pub_bar + i, kEpilogueWarps);
         *pub_done = 0;
+        *deps_ready = 0;
         fence_mbar_init();
         fence_proxy_async_smem();
         for (int i = 0; i < kMaxTensorMaps; i++) tma_prefetch_desc(&P.tmaps[i]);
     }
     if (warp == 1) { if (kPair) tmem_alloc_pair<512>(tmem_slot); else tmem_alloc<512>(tmem_slot); }
     const LayerJob* __restrict__ jobs = P.jobs;
-    // every job's bias and both fused-head weight sets stay resident in smem for the whole launch
-    for (int i = threadIdx.x; i < P.n_jobs * 128; i += blockDim.x) {
-        const int jj = i >> 7, c = i & 127;
-        bias_all[i] = c < jobs[jj].n_out ? jobs[jj].bias[c] : 0.0f;
-    }
-    for (int jj = 0; jj < P.n_jobs; jj++) {
-        if (!jobs[jj].head_taps) continue;
-        float* dst = headw_all + jobs[jj].head_slot * (9 * 128);
-        for (int i = threadIdx.x; i < 9 * jobs[jj].n_out; i += blockDim.x) dst[i] = jobs[jj].head_w[i];
-    }
     tc_fence_before_sync();
     __syncthreads();
     if (kPair) cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
@@ -184,12 +182,9 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             const int tile = W.tile(q - J.item_base);
             const int halo = J.halo, ksize = J.ksize, n_out = J.n_out, n_slabs = J.n_slabs, tmap = J.tmap;
             if (lane == 0) { LB2_TRACE(pit, 0); if (P.trace && pit < (uint32_t)kTraceItems) P.trace[((size_t)blockIdx.x * kTraceItems + pit) * kTraceEvents + 15] = (unsigned long long)q; }
-            if (P.use_flags && J.dep_job >= 0) {
-                int lo, hi;
-                dependency_range(J, tile, lo, hi);
-                const uint32_t* flags = jobs[J.dep_job].flags;
-                if (lo + lane <= hi)
-                    while (ld_acquire_gpu(flags + lo + lane) != P.epoch) __nanosleep(32);
+            if (P.use_flags) {
+                // the scout warp polls the dependency flags ahead of us; wait for its go-ahead
+                while (ld_acquire_cta_shared(deps_ready) <= pit) {}
                 __syncwarp();
             }
             const int rows_halo = kTileRows + 2 * halo;
@@ -331,8 +326,8 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             __half* __restrict__ out = J.out;
             float* __restrict__ zbuf = J.zbuf;
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-            const float* bs = bias_all + j * 128;
-            const float* headw_s = headw_all + J.head_slot * (9 * 128);
+            const float* bs = &c_bias[J.net][J.layer][0];
+            const float* headw_s = &c_headw[J.net][0][0];
             if (warp == 2 && lane == 0) LB2_TRACE(it, 8);
             mbar_wait(tfull_bar + acc, acc_phase);
             tc_fence_after_sync();
@@ -375,7 +370,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                         // fused 1-channel 3x3 head: z[t] += sum_c w[t][c] * v[c]  (fp32, unrounded v)
 #pragma unroll
                         for (int t = 0; t < 9; t++) {
-                            const float* wt = headw_s + t * n_out + col0 + cc;
+                            const float* wt = headw_s + t * 128 + col0 + cc;
 #pragma unroll
                             for (int e = 0; e < 16; e += 4) {
                                 const float4 w4 = *reinterpret_cast<const float4*>(wt + e);
@@ -453,6 +448,27 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                 st_release_gpu(jobs[j].flags + W.tile(q - jobs[j].item_base), P.epoch);
                 LB2_TRACE(it, 12);
                 *pub_done = it + 1;
+            }
+        }
+    } else if (warp == 11) {
+        // ================================ dependency scout ============================
+        // Runs ahead of the producer: polls (acquire, gpu scope) the <= 3 tile flags of the previous
+        // layer that each upcoming item of this CTA needs, lanes in parallel, and publishes its
+        // progress in shared memory. Takes the L2 round trips of the polling off the load path.
+        if (P.use_flags) {
+            int j = 0; uint32_t it = 0;
+            for (int q = W.first; q < P.item_end; q += W.step, it++) {
+                while (q >= jobs[j].item_base + jobs[j].n_items) j++;
+                const LayerJob& J = jobs[j];
+                if (J.dep_job >= 0) {
+                    int lo, hi;
+                    dependency_range(J, W.tile(q - J.item_base), lo, hi);
+                    const uint32_t* flags = jobs[J.dep_job].flags;
+                    if (lo + lane <= hi)
+                        while (ld_acquire_gpu(flags + lo + lane) != P.epoch) __nanosleep(20);
+                }
+                __syncwarp();
+                if (lane == 0) st_release_cta_shared(deps_ready, it + 1);
             }
         }
     }
@@ -599,6 +615,25 @@ cudaError_t launch_expand(const uint32_t* planes, const uint8_t* rotation, int n
     const int rows = n * 441;
     expand_planes_kernel<<<(rows + 255) / 256, 256, 0, st>>>(planes, rotation, n, x0, chunk_rows);
     return cudaGetLastError();
+}
+
+cudaError_t upload_constants(int net, int layer, const float* bias, int n_out, cudaStream_t st) {
+    float tmp[128] = {0};
+    for (int i = 0; i < n_out && i < 128; i++) tmp[i] = bias[i];
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_bias, tmp, sizeof tmp, ((size_t)net * kMaxLayers + layer) * 128 * sizeof(float),
+                                            cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(st);  // tmp is a stack buffer
+}
+
+cudaError_t upload_head_weights(int net, const float* w_tc, int c_in, cudaStream_t st) {
+    float tmp[9][128] = {{0}};
+    for (int t = 0; t < 9; t++)
+        for (int c = 0; c < c_in && c < 128; c++) tmp[t][c] = w_tc[t * c_in + c];
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_headw, tmp, sizeof tmp, (size_t)net * 9 * 128 * sizeof(float),
+                                            cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(st);
 }
 
 cudaError_t trunk_kernel_setup() {

@@ -20,18 +20,24 @@ namespace lb2 {
 constexpr int kPoints = 361;
 constexpr int kBoard = 19;
 constexpr int kTileRows = 256;  // output rows per work item (two M=128 MMA halves)
-constexpr int kStages = 4;      // smem ring depth (A slab + B block per stage)
+constexpr int kStagesSingle = 4;  // smem ring depth (A slab + B block per stage), one CTA per item
+constexpr int kStagesPair = 6;    // CTA pairs stage only half of B, so the ring is deeper
 constexpr int kMaxHalo = 48;    // 5x5 conv in S=21 space needs 2*21+2 = 44 -> 48 (multiple of 8)
 constexpr int kASlabBytes = (kTileRows + 2 * kMaxHalo) * 32;  // rows x 16 ch x fp16
 constexpr int kBBlockBytes = 9 * 128 * 32;                    // up to 9 taps x N<=128 x 16 ch x fp16
-constexpr int kStageBytes = kASlabBytes + kBBlockBytes;       // 48,128
+constexpr int kStageBytesSingle = kASlabBytes + kBBlockBytes;      // 48,128
+constexpr int kStageBytesPair = kASlabBytes + kBBlockBytes / 2;    // 29,696
+constexpr int kMaxStages = 6;
 constexpr int kEpilogueWarps = 8;
-// warp0 TMA producer, warp1 MMA issuer, warps2-9 epilogue, warp10 tile publisher
-constexpr int kTrunkThreads = 64 + 32 * kEpilogueWarps + 32;
+// warp0 TMA producer, warp1 MMA issuer, warps2-9 epilogue, warp10 tile publisher, warp11 dependency scout
+constexpr int kTrunkThreads = 64 + 32 * kEpilogueWarps + 64;
 constexpr int kMaxLaunchJobs = 24;  // jobs whose biases are kept resident in smem
 constexpr int kPubDepth = 4;        // tiles that may be waiting for publication
-// stages | mbarriers + TMEM slot (256 B) | bias [jobs][128] f32 | fused-head weights [2 nets][9][128] f32
-constexpr int kTrunkSmemBytes = kStages * kStageBytes + 256 + kMaxLaunchJobs * 128 * 4 + 2 * 9 * 128 * 4;
+// stages | mbarriers, TMEM slot, progress counters (256 B)
+constexpr int kRingBytesSingle = kStagesSingle * kStageBytesSingle;   // 192,512
+constexpr int kRingBytesPair = kStagesPair * kStageBytesPair;         // 178,176
+constexpr int kTrunkSmemBytes = (kRingBytesSingle > kRingBytesPair ? kRingBytesSingle : kRingBytesPair) + 256;
+constexpr int kMaxLayers = 16;      // per net, for the constant-memory bias table
 constexpr int kMaxTensorMaps = 6;
 constexpr int kMaxJobs = 32;
 constexpr int kTraceItems = 96;
@@ -54,7 +60,8 @@ struct LayerJob {
     int32_t n_pos;           // positions in the batch
     int32_t out_chunk_rows;  // rows per chunk plane of the output buffer
     int32_t head_taps;       // 9: the net's final 3x3 conv to 1 channel is fused into this job's epilogue
-    int32_t head_slot;       // which resident head-weight slot (0 = policy, 1 = value)
+    int32_t net;             // 0 = policy, 1 = value: selects the constant-memory bias / head-weight tables
+    int32_t layer;           // layer index within the net
     const __half* wpk;       // packed weights: per (slab, tap group): [tap][2 chunks][n_out][8]
     const __half* wpk2;      // CTA-pair packing: per (slab, tap group): [rank][tap][2 chunks][n_out/2][8]
     const float* bias;       // [n_out]
@@ -86,5 +93,8 @@ cudaError_t launch_value_head(const float* zbuf, int chunk_rows, const float* bi
                               const float* ip1_b, int hidden, const float* ip2_w, const float* ip2_b, int n,
                               float* winrate, cudaStream_t st);
 cudaError_t trunk_kernel_setup();
+// per-device constant tables: biases [net][layer][128] and fused-head weights [net][9][128]
+cudaError_t upload_constants(int net, int layer, const float* bias, int n_out, cudaStream_t st);
+cudaError_t upload_head_weights(int net, const float* w_tc /*[9][c_in]*/, int c_in, cudaStream_t st);
 
 }  // namespace lb2
