@@ -158,27 +158,6 @@ struct lb2_ctx {
 
 namespace {
 
-// The bias / head-weight tables are __constant__ symbols, i.e. one instance per device and
-// process. Remember which context's nets they currently hold and reload on a switch.
-std::mutex g_const_mu;
-const void* g_const_owner[64][2] = {};
-
-int ensure_constants(lb2_ctx* ctx, DeviceState* d, bool run[2], cudaStream_t st) {
-    std::lock_guard<std::mutex> lk(g_const_mu);
-    for (int k = 0; k < 2; k++) {
-        if (!run[k] || d->id >= 64) continue;
-        const void* owner = ctx->nets[k].get();
-        if (g_const_owner[d->id][k] == owner) continue;
-        NetDev& nd = d->net[k];
-        CU_TRY(cudaStreamSynchronize(st));
-        for (size_t l = 0; l < nd.h_bias.size(); l++)
-            CU_TRY(lb2::upload_constants(k, (int)l, nd.h_bias[l].data(), (int)nd.h_bias[l].size(), st));
-        CU_TRY(lb2::upload_head_weights(k, nd.h_head_wt.data(), nd.head_c_in, st));
-        g_const_owner[d->id][k] = owner;
-    }
-    return LB2_OK;
-}
-
 // --------------------------------------------------------------------------------------------
 // weights
 // --------------------------------------------------------------------------------------------
@@ -422,10 +401,6 @@ JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2], bool 
 
 int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers[2], cudaStream_t st,
               JobPlan* plan_out) {
-    {
-        int rc = ensure_constants(ctx, d, run, st);
-        if (rc) return rc;
-    }
     const bool pair = ctx->cta_pair != 0 && d->sm_count >= 2;
     JobPlan pl = plan_jobs(d, run, n, limit_layers, pair);
     if (pl.jobs.empty()) return fail(LB2_ERR_STATE, "no trunk layers to run");
@@ -728,12 +703,6 @@ void lb2_destroy(lb2_ctx* ctx) {
     }
     ctx->q_cv.notify_all();
     if (ctx->worker.joinable()) ctx->worker.join();
-    {
-        std::lock_guard<std::mutex> lk(g_const_mu);
-        for (auto& d : ctx->dev)
-            for (int k = 0; k < 2; k++)
-                if (d.id < 64 && g_const_owner[d.id][k] == ctx->nets[k].get()) g_const_owner[d.id][k] = nullptr;
-    }
     for (auto& d : ctx->dev) {
         cudaSetDevice(d.id);
         cudaStreamSynchronize(d.stream);

@@ -16,12 +16,6 @@
 
 namespace lb2 {
 
-// Per-layer biases and the two fused-head weight sets live in constant memory: every lane of an
-// epilogue warp reads the same address (one row per lane, all channels), which the constant cache
-// broadcasts without touching the shared-memory port the tensor cores are saturating.
-__constant__ float c_bias[2][kMaxLayers][128];
-__constant__ float c_headw[2][9][128];
-
 // Network::rotate_nn_idx (Network.cpp:1348-1379): bit2 swaps x/y first, bit0 flips y, bit1 flips x.
 __device__ __forceinline__ int rotate_idx(int v, int s) {
     int x = v % kBoard, y = v / kBoard;
@@ -136,7 +130,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
     constexpr int kStages = kPair ? kStagesPair : kStagesSingle;
     constexpr int kStageBytes = kPair ? kStageBytesPair : kStageBytesSingle;
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kTrunkRingBytes);
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tfull_bar = empty_bar + kMaxStages;  // [2] accumulator ready   (MMA -> epilogue)
     uint64_t* tempty_bar = tfull_bar + 2;          // [2] accumulator drained (epilogue -> MMA)
@@ -145,6 +139,9 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pfull_bar + kMaxStages);
     volatile uint32_t* pub_done = tmem_slot + 1;   // tiles published so far by this CTA
     uint32_t* deps_ready = tmem_slot + 2;          // items whose dependencies the scout warp has seen satisfied
+    // broadcast reads (one wavefront per warp-wide LDS.128), resident for the whole launch
+    float* bias_all = reinterpret_cast<float*>(smem + kTrunkRingBytes + 256);   // [kMaxLaunchJobs][128]
+    float* headw_all = bias_all + kMaxLaunchJobs * 128;                         // [2 nets][9][128]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -164,6 +161,16 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
     }
     if (warp == 1) { if (kPair) tmem_alloc_pair<512>(tmem_slot); else tmem_alloc<512>(tmem_slot); }
     const LayerJob* __restrict__ jobs = P.jobs;
+    // every job's bias and both fused-head weight sets stay resident in smem for the whole launch
+    for (int i = threadIdx.x; i < P.n_jobs * 128; i += blockDim.x) {
+        const int jj = i >> 7, c = i & 127;
+        bias_all[i] = c < jobs[jj].n_out ? jobs[jj].bias[c] : 0.0f;
+    }
+    for (int jj = 0; jj < P.n_jobs; jj++) {
+        if (!jobs[jj].head_taps) continue;
+        float* dst = headw_all + jobs[jj].net * (9 * 128);
+        for (int i = threadIdx.x; i < 9 * jobs[jj].n_out; i += blockDim.x) dst[(i / jobs[jj].n_out) * 128 + i % jobs[jj].n_out] = jobs[jj].head_w[i];
+    }
     tc_fence_before_sync();
     __syncthreads();
     if (kPair) cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
@@ -326,8 +333,8 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             __half* __restrict__ out = J.out;
             float* __restrict__ zbuf = J.zbuf;
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-            const float* bs = &c_bias[J.net][J.layer][0];
-            const float* headw_s = &c_headw[J.net][0][0];
+            const float* bs = bias_all + j * 128;
+            const float* headw_s = headw_all + J.net * (9 * 128);
             if (warp == 2 && lane == 0) LB2_TRACE(it, 8);
             mbar_wait(tfull_bar + acc, acc_phase);
             tc_fence_after_sync();
@@ -615,25 +622,6 @@ cudaError_t launch_expand(const uint32_t* planes, const uint8_t* rotation, int n
     const int rows = n * 441;
     expand_planes_kernel<<<(rows + 255) / 256, 256, 0, st>>>(planes, rotation, n, x0, chunk_rows);
     return cudaGetLastError();
-}
-
-cudaError_t upload_constants(int net, int layer, const float* bias, int n_out, cudaStream_t st) {
-    float tmp[128] = {0};
-    for (int i = 0; i < n_out && i < 128; i++) tmp[i] = bias[i];
-    cudaError_t e = cudaMemcpyToSymbolAsync(c_bias, tmp, sizeof tmp, ((size_t)net * kMaxLayers + layer) * 128 * sizeof(float),
-                                            cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) return e;
-    return cudaStreamSynchronize(st);  // tmp is a stack buffer
-}
-
-cudaError_t upload_head_weights(int net, const float* w_tc, int c_in, cudaStream_t st) {
-    float tmp[9][128] = {{0}};
-    for (int t = 0; t < 9; t++)
-        for (int c = 0; c < c_in && c < 128; c++) tmp[t][c] = w_tc[t * c_in + c];
-    cudaError_t e = cudaMemcpyToSymbolAsync(c_headw, tmp, sizeof tmp, (size_t)net * 9 * 128 * sizeof(float),
-                                            cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) return e;
-    return cudaStreamSynchronize(st);
 }
 
 cudaError_t trunk_kernel_setup() {

@@ -36,8 +36,10 @@ constexpr int kPubDepth = 4;        // tiles that may be waiting for publication
 // stages | mbarriers, TMEM slot, progress counters (256 B)
 constexpr int kRingBytesSingle = kStagesSingle * kStageBytesSingle;   // 192,512
 constexpr int kRingBytesPair = kStagesPair * kStageBytesPair;         // 178,176
-constexpr int kTrunkSmemBytes = (kRingBytesSingle > kRingBytesPair ? kRingBytesSingle : kRingBytesPair) + 256;
-constexpr int kMaxLayers = 16;      // per net, for the constant-memory bias table
+constexpr int kTrunkRingBytes = kRingBytesSingle > kRingBytesPair ? kRingBytesSingle : kRingBytesPair;
+// ring | mbarriers etc. (256 B) | bias [jobs][128] f32 | fused-head weights [2 nets][9][128] f32
+constexpr int kTrunkSmemBytes = kTrunkRingBytes + 256 + kMaxLaunchJobs * 128 * 4 + 2 * 9 * 128 * 4;
+constexpr int kMaxLayers = 16;
 constexpr int kMaxTensorMaps = 6;
 constexpr int kMaxJobs = 32;
 constexpr int kTraceItems = 96;
@@ -93,8 +95,5 @@ cudaError_t launch_value_head(const float* zbuf, int chunk_rows, const float* bi
                               const float* ip1_b, int hidden, const float* ip2_w, const float* ip2_b, int n,
                               float* winrate, cudaStream_t st);
 cudaError_t trunk_kernel_setup();
-// per-device constant tables: biases [net][layer][128] and fused-head weights [net][9][128]
-cudaError_t upload_constants(int net, int layer, const float* bias, int n_out, cudaStream_t st);
-cudaError_t upload_head_weights(int net, const float* w_tc /*[9][c_in]*/, int c_in, cudaStream_t st);
 
 }  // namespace lb2
