@@ -479,7 +479,9 @@ int eval_on_device(lb2_ctx* ctx, DeviceState* d, const uint32_t* d_pol, const ui
         if (!run[k]) continue;
         NetDev& nd = d->net[k];
         if (nd.cap < n) return fail(LB2_ERR_STATE, "workspace too small");
-        CU_TRY(lb2::launch_expand(planes[k], d_rot, n, nd.x0, nd.rows5, st));
+        const bool pf = (k == 1 && nd.ip1_wt);
+        CU_TRY(lb2::launch_expand(planes[k], d_rot, n, nd.x0, nd.rows5, pf ? nd.ip1_wt : nullptr,
+                                  pf ? (size_t)lb2::kPoints * nd.hidden * sizeof(float) : 0, st));
         ctx->launches++;
     }
     JobPlan pl;
@@ -942,7 +944,7 @@ int lb2_debug_trunk(lb2_ctx* ctx, int kind, const uint32_t* planes, const uint8_
     if ((rc = ensure_workspace(&nd, kind, n))) return rc;
     CU_TRY(cudaMemcpyAsync(d->rot, rotation, n, cudaMemcpyHostToDevice, d->stream));
     CU_TRY(cudaMemcpyAsync(nd.planes, planes, (size_t)n * lb2::kPoints * sizeof(uint32_t), cudaMemcpyHostToDevice, d->stream));
-    CU_TRY(lb2::launch_expand(nd.planes, d->rot, n, nd.x0, nd.rows5, d->stream));
+    CU_TRY(lb2::launch_expand(nd.planes, d->rot, n, nd.x0, nd.rows5, nullptr, 0, d->stream));
     ctx->launches++;
     int limit[2] = {0, 0};
     limit[kind] = n_layers;

@@ -37,9 +37,16 @@ __device__ __forceinline__ float elu1(float v) { return v > 0.0f ? v : (__expf(v
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) expand_planes_kernel(const uint32_t* __restrict__ planes,
                                                             const uint8_t* __restrict__ rotation, int n,
-                                                            __half* __restrict__ x0, int chunk_rows) {
+                                                            __half* __restrict__ x0, int chunk_rows,
+                                                            const uint8_t* __restrict__ pf, size_t pf_bytes) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= n * 441) return;
+    if (row >= n * 441) {
+        // spare blocks pull a read-late buffer (the value head's 361xH matrix) into L2 while the
+        // trunk runs, keeping its HBM latency off the end of the step
+        const size_t i = (size_t)(row - n * 441) * 128;
+        if (i < pf_bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + i));
+        return;
+    }
     const int pos = row / 441, rem = row - pos * 441;
     const int y = rem / 21, x = rem - y * 21;
     uint32_t bits = 0;
@@ -548,7 +555,7 @@ __global__ void __launch_bounds__(384) policy_head_kernel(const float* __restric
 // 512 threads: thread (o, part) accumulates half of the 361 inputs of output o for all positions
 // of the group (more loads in flight), the halves are combined through shared memory.
 constexpr int kValueGroup = 4;
-constexpr int kValueThreads = 512;
+constexpr int kValueThreads = 1024;  // 4 slices of the 361 inputs per output (hidden <= 256)
 
 __global__ void __launch_bounds__(kValueThreads) value_head_kernel(const float* __restrict__ zbuf, int chunk_rows,
                                                                    const float* __restrict__ bias,
@@ -560,7 +567,7 @@ __global__ void __launch_bounds__(kValueThreads) value_head_kernel(const float* 
     extern __shared__ float hs[];
     float* v_s = hs;                              // [361][G]  (position fastest: float4 broadcast reads)
     float* h_s = v_s + kValueGroup * kPoints;     // [G][hidden]
-    float* part_s = h_s + kValueGroup * hidden;   // [G][hidden] partial sums of the second half
+    float* part_s = h_s + kValueGroup * hidden;   // [parts-1][G][hidden] partial sums of the other input slices
     const int tid = threadIdx.x;
     const int pos0 = blockIdx.x * kValueGroup;
     for (int i = tid; i < kValueGroup * kPoints; i += blockDim.x) {
@@ -573,36 +580,33 @@ __global__ void __launch_bounds__(kValueThreads) value_head_kernel(const float* 
         v_s[p * kValueGroup + g] = v;
     }
     __syncthreads();
-    const int o = tid % hidden, part = tid / hidden;   // hidden <= 256 -> part in {0, 1}
+    // thread (o, part): output o over input slice `part`; many independent loads in flight
+    const int o = tid % hidden, part = tid / hidden, n_parts = blockDim.x / hidden;
     float a[kValueGroup];
 #pragma unroll
     for (int g = 0; g < kValueGroup; g++) a[g] = 0.0f;
-    if (part < 2) {
-        const int i0 = part == 0 ? 0 : 181, i1 = part == 0 ? 181 : kPoints;
-#pragma unroll 8
+    if (part < n_parts) {
+        const int per = (kPoints + n_parts - 1) / n_parts;
+        const int i0 = part * per, i1 = min(kPoints, i0 + per);
+#pragma unroll 16
         for (int i = i0; i < i1; i++) {
-            const float wv = ip1_wt[(size_t)i * hidden + o];
+            const float wv = __ldg(ip1_wt + (size_t)i * hidden + o);
             const float4 v0 = *reinterpret_cast<const float4*>(v_s + i * kValueGroup);
             a[0] = fmaf(wv, v0.x, a[0]); a[1] = fmaf(wv, v0.y, a[1]); a[2] = fmaf(wv, v0.z, a[2]); a[3] = fmaf(wv, v0.w, a[3]);
         }
-        if (part == 1) {
+        if (part > 0) {
 #pragma unroll
-            for (int g = 0; g < kValueGroup; g++) part_s[g * hidden + o] = a[g];
+            for (int g = 0; g < kValueGroup; g++) part_s[((part - 1) * kValueGroup + g) * hidden + o] = a[g];
         }
     }
     __syncthreads();
     if (part == 0) {
-        const bool have2 = blockDim.x >= 2 * hidden;
-        if (!have2) {  // fewer than 2*hidden threads: finish the second half here
-            for (int i = 181; i < kPoints; i++) {
-                const float wv = ip1_wt[(size_t)i * hidden + o];
 #pragma unroll
-                for (int g = 0; g < kValueGroup; g++) a[g] = fmaf(wv, v_s[i * kValueGroup + g], a[g]);
-            }
+        for (int g = 0; g < kValueGroup; g++) {
+            float sum = a[g];
+            for (int p = 1; p < n_parts; p++) sum += part_s[((p - 1) * kValueGroup + g) * hidden + o];
+            h_s[g * hidden + o] = elu1(sum + ip1_b[o]);
         }
-#pragma unroll
-        for (int g = 0; g < kValueGroup; g++)
-            h_s[g * hidden + o] = elu1(a[g] + (have2 ? part_s[g * hidden + o] : 0.0f) + ip1_b[o]);
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
@@ -618,9 +622,10 @@ __global__ void __launch_bounds__(kValueThreads) value_head_kernel(const float* 
 // launchers
 // ------------------------------------------------------------------------------------------
 cudaError_t launch_expand(const uint32_t* planes, const uint8_t* rotation, int n, __half* x0, int chunk_rows,
-                          cudaStream_t st) {
-    const int rows = n * 441;
-    expand_planes_kernel<<<(rows + 255) / 256, 256, 0, st>>>(planes, rotation, n, x0, chunk_rows);
+                          const void* prefetch, size_t prefetch_bytes, cudaStream_t st) {
+    const size_t threads = (size_t)n * 441 + (prefetch_bytes + 127) / 128;
+    expand_planes_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(planes, rotation, n, x0, chunk_rows,
+                                                                           static_cast<const uint8_t*>(prefetch), prefetch_bytes);
     return cudaGetLastError();
 }
 
@@ -663,7 +668,7 @@ cudaError_t launch_policy_head(const float* zbuf, int chunk_rows, const float* b
 cudaError_t launch_value_head(const float* zbuf, int chunk_rows, const float* bias, const float* ip1_wt,
                               const float* ip1_b, int hidden, const float* ip2_w, const float* ip2_b, int n,
                               float* winrate, cudaStream_t st) {
-    const size_t smem = (kValueGroup * kPoints + 2 * kValueGroup * hidden) * sizeof(float);
+    const size_t smem = (kValueGroup * kPoints + 4 * kValueGroup * hidden) * sizeof(float);
     value_head_kernel<<<(n + kValueGroup - 1) / kValueGroup, kValueThreads, smem, st>>>(zbuf, chunk_rows, bias, ip1_wt, ip1_b, hidden,
                                                                              ip2_w, ip2_b, n, winrate);
     return cudaGetLastError();

@@ -87,7 +87,7 @@ struct TrunkParams {
 
 // launchers (lb2_kernels.cu)
 cudaError_t launch_expand(const uint32_t* planes, const uint8_t* rotation, int n, __half* x0, int chunk_rows,
-                          cudaStream_t st);
+                          const void* prefetch, size_t prefetch_bytes, cudaStream_t st);
 cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool pair, cudaStream_t st);
 cudaError_t launch_policy_head(const float* zbuf, int chunk_rows, const float* bias, const uint8_t* rotation, int n,
                                float temp, float* probs, cudaStream_t st);
