@@ -35,7 +35,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from leela_b200 import fileio, netdefs  # noqa: E402
+from leela_b200 import fileio, netdefs, shard  # noqa: E402
 
 METRIC = "nn_evals_per_sec_policy_plus_value_batch256"
 UNIT = "positions/s"
@@ -67,7 +67,7 @@ class ClockSampler:
         self.f = open(self.path, "w")
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-i", str(gpu_index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-i", str(gpu_index), "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
@@ -176,8 +176,7 @@ def run_ours(args):
     ev.set_option("max_batch", max(B, 512))
     pp, vp, rot = load_positions()
     n_sets = pp.shape[0] // B
-    # rank r starts at a different offset so ranks do not evaluate identical positions
-    order = [(rank + i) % n_sets for i in range(n_sets)]
+    order = shard.batch_order(n_sets, rank)
     d_pp = [torch.from_numpy(pp[s * B:(s + 1) * B].astype(np.int32)).to(dev) for s in order]
     d_vp = [torch.from_numpy(vp[s * B:(s + 1) * B].astype(np.int32)).to(dev) for s in order]
     d_rot = [torch.from_numpy(rot[s * B:(s + 1) * B].copy()).to(dev) for s in order]
@@ -246,15 +245,12 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop() if sampler else None
 
-    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = float(t[0]), float(t[1])
+    total_ms, e2e_ms = shard.max_over_ranks([total_ms, e2e_s * 1e3], dist if world > 1 else None, dev)
 
     if rank == 0:
         n_gpus = world
-        value = n_gpus * B * args.steps / (total_ms * 1e-3)
-        e2e_value = n_gpus * B * args.steps / (e2e_ms * 1e-3)
+        value = shard.aggregate_throughput(B, args.steps, n_gpus, total_ms)
+        e2e_value = shard.aggregate_throughput(B, args.steps, n_gpus, e2e_ms)
         peaks, peak_src = measured_peaks()
         trunk_s = trunk_ns * 1e-9 / args.steps
         achieved = TRUNK_FLOPS * B / trunk_s / 1e12 if trunk_s > 0 else 0.0
@@ -274,7 +270,7 @@ def run_ours(args):
                        "batch_per_gpu": B, "global_batch": B * n_gpus, "parallelism": f"replicas x{n_gpus}, positions sharded",
                        "weights": "synthetic U(+-sqrt(6/fan_in)), seed 20260001, policy gain 2 (in-repo weights missing)",
                        "positions": "Leela Playout self-play, 1024 distinct, cycled", "l2": "flushed between steps (256 MB write)",
-                       "trunk_mode": ev.get_option("trunk_mode"), "flops_per_position": netdefs.POLICY_FLOPS + netdefs.VALUE_FLOPS,
+                       "trunk_mode": ev.get_option("trunk_mode"), "cta_pair": ev.get_option("cta_pair"), "flops_per_position": netdefs.POLICY_FLOPS + netdefs.VALUE_FLOPS,
                        "pct_of_bf16_peak_whole_step": 100.0 * (netdefs.POLICY_FLOPS + netdefs.VALUE_FLOPS) * value / n_gpus / (peak * 1e12)},
             "roofline": {"bound": "tensor", "kernel": "trunk_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": f"{peak_src} burst (MEASURED_PEAKS.json bf16_tflops)",
@@ -298,8 +294,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

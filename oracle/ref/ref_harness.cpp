@@ -22,6 +22,7 @@
 
 #include "GameState.h"
 #include "Zobrist.h"
+#include "../../leela_b200/host/b200_network.h"
 #include "Matcher.h"
 #include "ThreadPool.h"
 
@@ -381,6 +382,82 @@ int cmd_steps(int argc, char** argv) {
     return 0;
 }
 
+/* Drop-in check at the API level: the UNMODIFIED reference engine supplies live game states,
+ * feature planes (gather_features_*) and its own answers (get_scored_moves / get_value through
+ * the public API, all three ensembles); the B200 evaluator answers the same calls through the
+ * host mirror leela_b200/host/b200_network.h on top of the C ABI. Needs a B200. Prints JSON. */
+int cmd_apicheck(int argc, char** argv) {
+    if (argc < 4) { fprintf(stderr, "usage: apicheck <n> <seed>\n"); return 2; }
+    const int n = atoi(argv[2]);
+    const uint32_t seed = (uint32_t)strtoul(argv[3], nullptr, 10);
+    init_reference(1);
+    leela_b200::B200Network net;
+    try {
+        net.initialize();
+        net.push_convolve(LB2_POLICY, 5, conv1_w, conv1_b);   net.push_convolve(LB2_POLICY, 3, conv2_w, conv2_b);
+        net.push_convolve(LB2_POLICY, 3, conv3_w, conv3_b);   net.push_convolve(LB2_POLICY, 3, conv4_w, conv4_b);
+        net.push_convolve(LB2_POLICY, 3, conv5_w, conv5_b);   net.push_convolve(LB2_POLICY, 3, conv6_w, conv6_b);
+        net.push_convolve(LB2_POLICY, 3, conv7_w, conv7_b);   net.push_convolve(LB2_POLICY, 3, conv8_w, conv8_b);
+        net.push_convolve(LB2_POLICY, 3, conv9_w, conv9_b);   net.push_convolve(LB2_POLICY, 3, conv10_w, conv10_b);
+        net.push_convolve(LB2_POLICY, 3, conv11_w, conv11_b); net.push_convolve(LB2_POLICY, 3, conv12_w, conv12_b);
+        net.push_convolve(LB2_POLICY, 3, conv13_w, conv13_b);
+        net.push_convolve(LB2_VALUE, 5, val_conv1_w, val_conv1_b);   net.push_convolve(LB2_VALUE, 3, val_conv2_w, val_conv2_b);
+        net.push_convolve(LB2_VALUE, 3, val_conv3_w, val_conv3_b);   net.push_convolve(LB2_VALUE, 3, val_conv4_w, val_conv4_b);
+        net.push_convolve(LB2_VALUE, 3, val_conv5_w, val_conv5_b);   net.push_convolve(LB2_VALUE, 3, val_conv6_w, val_conv6_b);
+        net.push_convolve(LB2_VALUE, 3, val_conv7_w, val_conv7_b);   net.push_convolve(LB2_VALUE, 3, val_conv8_w, val_conv8_b);
+        net.push_convolve(LB2_VALUE, 3, val_conv9_w, val_conv9_b);   net.push_convolve(LB2_VALUE, 3, val_conv10_w, val_conv10_b);
+        net.push_convolve(LB2_VALUE, 3, val_conv11_w, val_conv11_b); net.push_convolve(LB2_VALUE, 3, val_conv12_w, val_conv12_b);
+        net.push_innerproduct(LB2_VALUE, val_ip13_w, val_ip13_b);
+        net.push_innerproduct(LB2_VALUE, val_ip14_w, val_ip14_b);
+        net.finalize();
+    } catch (const std::exception& e) {
+        printf("{\"error\": \"%s\"}\n", e.what());
+        return 1;
+    }
+    double max_dp = 0, max_dv = 0, max_dp_avg = 0, max_dv_avg = 0;
+    int top1_same = 0, order_mismatch = 0, cases = 0, ladder_zeroed = 0;
+    auto rng_fixed = [](int r) { return [r]() { return r; }; };
+    auto hook = [&](FastState& s, int i) {
+        Network::NNPlanes pp, vp;
+        Network::BoardPlane* ladder = nullptr;
+        Network::gather_features_policy(&s, pp, &ladder);
+        Network::gather_features_value(&s, vp);
+        const int r = i % 8;
+        auto compare = [&](const Network::Netresult& a, const leela_b200::B200Network::Netresult& b, double& worst) {
+            if (a.size() != b.size()) { order_mismatch++; return; }
+            size_t ba = 0, bb = 0;
+            for (size_t k = 0; k < a.size(); k++) {
+                if (a[k].second != b[k].second) { order_mismatch++; return; }
+                worst = std::max(worst, (double)std::fabs(a[k].first - b[k].first));
+                if (a[k].first > a[ba].first) ba = k;
+                if (b[k].first > b[bb].first) bb = k;
+                if (a[k].first == 0.0f && b[k].first == 0.0f) ladder_zeroed++;
+            }
+            if (a.empty() || ba == bb || std::fabs(a[ba].first - a[bb].first) < 6e-3) top1_same++;
+        };
+        auto ref_d = Network::get_scored_moves(&s, Network::DIRECT, r);
+        auto our_d = net.get_scored_moves(&s, pp, ladder, leela_b200::B200Network::DIRECT, r, cfg_softmax_temp, rng_fixed(0));
+        compare(ref_d, our_d, max_dp);
+        max_dv = std::max(max_dv, (double)std::fabs(Network::get_value(&s, Network::DIRECT) -
+                                                    net.get_value(&s, vp, leela_b200::B200Network::DIRECT, rng_fixed(0))));
+        if (i % 4 == 0) {
+            auto ref_a = Network::get_scored_moves(&s, Network::AVERAGE_ALL);
+            auto our_a = net.get_scored_moves(&s, pp, ladder, leela_b200::B200Network::AVERAGE_ALL, -1, cfg_softmax_temp, rng_fixed(0));
+            compare(ref_a, our_a, max_dp_avg);
+            max_dv_avg = std::max(max_dv_avg, (double)std::fabs(Network::get_value(&s, Network::AVERAGE_ALL) -
+                                                                net.get_value(&s, vp, leela_b200::B200Network::AVERAGE_ALL, rng_fixed(0))));
+            cases++;
+        }
+        cases++;
+    };
+    generate(n, seed, hook);
+    printf("{\"positions\": %d, \"cases\": %d, \"max_dp_direct\": %.6g, \"max_dv_direct\": %.6g, \"max_dp_average_all\": %.6g, "
+           "\"max_dv_average_all\": %.6g, \"top1_agree_or_near_tie\": %d, \"order_mismatch\": %d, \"ladder_zeroed_points\": %d, "
+           "\"backend\": \"%s\"}\n",
+           n, cases, max_dp, max_dv, max_dp_avg, max_dv_avg, top1_same, order_mismatch, ladder_zeroed, net.get_backend().c_str());
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -395,6 +472,7 @@ int main(int argc, char** argv) {
     if (cmd == "layer") return cmd_layer(argc, argv);
     if (cmd == "bench") return cmd_bench(argc, argv);
     if (cmd == "steps") return cmd_steps(argc, argv);
+    if (cmd == "apicheck") return cmd_apicheck(argc, argv);
     fprintf(stderr, "unknown command %s\n", cmd.c_str());
     return 2;
 }

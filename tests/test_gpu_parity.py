@@ -263,3 +263,21 @@ def test_async_submit_coalesces(ev, ref_golden):
     assert len(status) == 2 * n and all(s == 0 for s in status)
     for i in range(n):
         assert np.array_equal(outs_p[i][0], want_p[i]) and outs_v[i][0] == want_v[i]
+
+
+def test_api_level_dropin_against_live_reference_engine():
+    """The unmodified reference engine (oracle/_ref, built from /root/reference) plays self-play,
+    gathers feature planes and answers Network::get_scored_moves / get_value (DIRECT and
+    AVERAGE_ALL); the same calls go through the C++ host mirror leela_b200/host/b200_network.h on
+    the C ABI. Same vertices in the same order, probabilities/winrates within tolerance, ladder
+    points zeroed in both."""
+    import json
+    from oracle import reference
+    if not reference.available():
+        pytest.skip("reference harness not built")
+    r = json.loads(reference.run(["apicheck", 48, 4321]))
+    assert "error" not in r, r
+    assert r["order_mismatch"] == 0
+    assert r["max_dp_direct"] < TOL_P and r["max_dp_average_all"] < TOL_P
+    assert r["max_dv_direct"] < TOL_V and r["max_dv_average_all"] < TOL_V
+    assert r["top1_agree_or_near_tie"] == r["cases"]
