@@ -114,6 +114,7 @@ struct DeviceState {
     uint32_t epoch = 0;
     unsigned long long* trace = nullptr;   // debug timeline buffer (option "trace")
     std::vector<cudaEvent_t> prof_events;  // (start, stop) pairs around trunk launches
+    std::vector<cudaEvent_t> seg_events;   // profile_trunk == 2: one event after every launch, 5 per eval
     long plan_key[8] = {-1, -1, -1, -1, -1, -1, -1, -1};  // n, run0, run1, limit0, limit1, workspace pointers
 };
 
@@ -473,6 +474,13 @@ int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers
 int eval_on_device(lb2_ctx* ctx, DeviceState* d, const uint32_t* d_pol, const uint32_t* d_val, const uint8_t* d_rot,
                    int n, float temp, float* d_probs, float* d_win, cudaStream_t st) {
     bool run[2] = {d_probs != nullptr, d_win != nullptr};
+    // profile_trunk == 2: an event after every launch -> per-segment device times (debug)
+    auto mark = [&]() {
+        if (ctx->profile_trunk != 2) return;
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); d->seg_events.push_back(e); }
+    };
+    mark();
     const uint32_t* planes[2] = {d_pol, d_val};
     int limit[2] = {1 << 20, 1 << 20};
     for (int k = 0; k < 2; k++) {
@@ -484,20 +492,24 @@ int eval_on_device(lb2_ctx* ctx, DeviceState* d, const uint32_t* d_pol, const ui
                                   pf ? (size_t)lb2::kPoints * nd.hidden * sizeof(float) : 0, st));
         ctx->launches++;
     }
+    mark();
     JobPlan pl;
     int rc = run_trunk(ctx, d, run, n, limit, st, &pl);
     if (rc) return rc;
+    mark();
     if (run[0]) {
         NetDev& nd = d->net[0];
         CU_TRY(lb2::launch_policy_head(nd.zbuf, nd.rows3, nd.head_b, d_rot, n, temp, d_probs, st));
         ctx->launches++;
     }
+    mark();
     if (run[1]) {
         NetDev& nd = d->net[1];
         CU_TRY(lb2::launch_value_head(nd.zbuf, nd.rows3, nd.head_b, nd.ip1_wt, nd.ip1_b, nd.hidden, nd.ip2_w, nd.ip2_b, n,
                                       d_win, st));
         ctx->launches++;
     }
+    mark();
     return LB2_OK;
 }
 
@@ -875,7 +887,7 @@ int lb2_set_option(lb2_ctx* ctx, const char* name, long value) {
     } else if (!strcmp(name, "cta_pair")) {
         ctx->cta_pair = value ? 1 : 0;
     } else if (!strcmp(name, "profile_trunk")) {
-        ctx->profile_trunk = value ? 1 : 0;
+        ctx->profile_trunk = value;
     } else if (!strcmp(name, "max_batch")) {
         if (value < 1 || value > 65536) return fail(LB2_ERR_INVALID, "max_batch out of range");
         ctx->max_batch = value;
@@ -891,6 +903,22 @@ long lb2_get_option(lb2_ctx* ctx, const char* name) {
     if (!strcmp(name, "max_batch")) return ctx->max_batch;
     if (!strcmp(name, "cta_pair")) return ctx->cta_pair;
     if (!strcmp(name, "sm_count")) return ctx->dev.empty() ? 0 : ctx->dev[0].sm_count;
+    if (!strncmp(name, "seg", 3) && name[3] >= '0' && name[3] <= '3') {
+        // mean ns of segment k over the evals recorded with profile_trunk == 2:
+        // seg0 expand, seg1 trunk, seg2 policy head, seg3 value head; "seg3" also clears the record
+        std::lock_guard<std::mutex> lk(ctx->eval_mu);
+        DeviceState& d = ctx->dev[0];
+        cudaSetDevice(d.id);
+        cudaDeviceSynchronize();
+        const int k = name[3] - '0';
+        double ms_total = 0; long cnt = 0;
+        for (size_t i = 0; i + 4 < d.seg_events.size() + 1 && i + 4 < d.seg_events.size(); i += 5) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, d.seg_events[i + k], d.seg_events[i + k + 1]) == cudaSuccess) { ms_total += ms; cnt++; }
+        }
+        if (k == 3) { for (auto e : d.seg_events) cudaEventDestroy(e); d.seg_events.clear(); }
+        return cnt ? (long)(ms_total * 1e6 / cnt) : 0;
+    }
     if (!strcmp(name, "trunk_ns") || !strcmp(name, "trunk_launches_timed")) {
         // device time spent in trunk launches since the last query (profile_trunk = 1); resets
         std::lock_guard<std::mutex> lk(ctx->eval_mu);

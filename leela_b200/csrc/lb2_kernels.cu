@@ -550,12 +550,13 @@ __global__ void __launch_bounds__(384) policy_head_kernel(const float* __restric
     if (tid < kPoints) probs[(size_t)pos * kPoints + tid] = sm[rev_rotate_idx(tid, rotation[pos] & 7)];
 }
 
-// value head: kValueGroup positions per CTA so the 361xH inner-product matrix is read once per
-// group. v = ELU(b + conv) [361]; h = ELU(W1 v + b1); out = (1 + tanh(w2.h + b2)) / 2.
-// 512 threads: thread (o, part) accumulates half of the 361 inputs of output o for all positions
-// of the group (more loads in flight), the halves are combined through shared memory.
+// value head: kValueGroup positions per CTA. v = ELU(b + conv) [361]; h = ELU(W1 v + b1);
+// out = (1 + tanh(w2.h + b2)) / 2. The 361 x H matrix W1 (fp32, 370 KB) is streamed through a
+// 4-slot shared-memory ring with bulk copies (19 tiles of 19 input rows) so the kernel runs at
+// copy bandwidth instead of one L2/HBM round trip per unrolled load batch.
 constexpr int kValueGroup = 4;
-constexpr int kValueThreads = 1024;  // 4 slices of the 361 inputs per output (hidden <= 256)
+constexpr int kValueThreads = 1024;  // thread (o, part): output o, input rows part, part+4, ... of each tile
+constexpr int kVTileRows = 19, kVTiles = 19, kVSlots = 4;
 
 __global__ void __launch_bounds__(kValueThreads) value_head_kernel(const float* __restrict__ zbuf, int chunk_rows,
                                                                    const float* __restrict__ bias,
@@ -564,12 +565,24 @@ __global__ void __launch_bounds__(kValueThreads) value_head_kernel(const float* 
                                                                    const float* __restrict__ ip2_w,
                                                                    const float* __restrict__ ip2_b, int n,
                                                                    float* __restrict__ winrate) {
-    extern __shared__ float hs[];
-    float* v_s = hs;                              // [361][G]  (position fastest: float4 broadcast reads)
-    float* h_s = v_s + kValueGroup * kPoints;     // [G][hidden]
-    float* part_s = h_s + kValueGroup * hidden;   // [parts-1][G][hidden] partial sums of the other input slices
+    extern __shared__ __align__(128) uint8_t vsm[];
+    float* w_s = reinterpret_cast<float*>(vsm);                       // [kVSlots][19][hidden]
+    float* v_s = w_s + kVSlots * kVTileRows * hidden;                 // [361][G]
+    float* h_s = v_s + kValueGroup * kPoints;                         // [G][hidden]
+    float* part_s = h_s + kValueGroup * hidden;                       // [3][G][hidden]
+    uint64_t* full = reinterpret_cast<uint64_t*>(part_s + 3 * kValueGroup * hidden);  // [kVSlots]
     const int tid = threadIdx.x;
     const int pos0 = blockIdx.x * kValueGroup;
+    const uint32_t tile_bytes = kVTileRows * hidden * sizeof(float);
+    if (tid == 0) {
+        for (int i = 0; i < kVSlots; i++) mbar_init(full + i, 1);
+        fence_mbar_init();
+        fence_proxy_async_smem();
+        for (int t = 0; t < kVSlots - 1; t++) {  // prefetch distance 3
+            mbar_arrive_expect_tx(full + t, tile_bytes);
+            bulk_load_1d(w_s + t * kVTileRows * hidden, ip1_wt + (size_t)t * kVTileRows * hidden, tile_bytes, full + t);
+        }
+    }
     for (int i = tid; i < kValueGroup * kPoints; i += blockDim.x) {
         const int g = i / kPoints, p = i - g * kPoints;
         float v = 0.0f;
@@ -580,24 +593,35 @@ __global__ void __launch_bounds__(kValueThreads) value_head_kernel(const float* 
         v_s[p * kValueGroup + g] = v;
     }
     __syncthreads();
-    // thread (o, part): output o over input slice `part`; many independent loads in flight
-    const int o = tid % hidden, part = tid / hidden, n_parts = blockDim.x / hidden;
+    const int o = tid % hidden, part = tid / hidden, n_parts = min((int)blockDim.x / hidden, 4);
     float a[kValueGroup];
 #pragma unroll
     for (int g = 0; g < kValueGroup; g++) a[g] = 0.0f;
-    if (part < n_parts) {
-        const int per = (kPoints + n_parts - 1) / n_parts;
-        const int i0 = part * per, i1 = min(kPoints, i0 + per);
-#pragma unroll 16
-        for (int i = i0; i < i1; i++) {
-            const float wv = __ldg(ip1_wt + (size_t)i * hidden + o);
-            const float4 v0 = *reinterpret_cast<const float4*>(v_s + i * kValueGroup);
-            a[0] = fmaf(wv, v0.x, a[0]); a[1] = fmaf(wv, v0.y, a[1]); a[2] = fmaf(wv, v0.z, a[2]); a[3] = fmaf(wv, v0.w, a[3]);
-        }
-        if (part > 0) {
+    for (int t = 0; t < kVTiles; t++) {
+        const int slot = t % kVSlots;
+        mbar_wait(full + slot, (t / kVSlots) & 1);
+        if (part < n_parts) {
+            const float* wt = w_s + slot * kVTileRows * hidden + o;
 #pragma unroll
-            for (int g = 0; g < kValueGroup; g++) part_s[((part - 1) * kValueGroup + g) * hidden + o] = a[g];
+            for (int r = 0; r < 5; r++) {
+                const int row = part + r * n_parts;   // n_parts == 4 for hidden == 256
+                if (row < kVTileRows) {
+                    const float wv = wt[row * hidden];
+                    const float4 v0 = *reinterpret_cast<const float4*>(v_s + (t * kVTileRows + row) * kValueGroup);
+                    a[0] = fmaf(wv, v0.x, a[0]); a[1] = fmaf(wv, v0.y, a[1]); a[2] = fmaf(wv, v0.z, a[2]); a[3] = fmaf(wv, v0.w, a[3]);
+                }
+            }
         }
+        __syncthreads();  // everyone is done with this slot's predecessor: refill it
+        if (tid == 0 && t + kVSlots - 1 < kVTiles) {
+            const int tn = t + kVSlots - 1, sn = tn % kVSlots;
+            mbar_arrive_expect_tx(full + sn, tile_bytes);
+            bulk_load_1d(w_s + sn * kVTileRows * hidden, ip1_wt + (size_t)tn * kVTileRows * hidden, tile_bytes, full + sn);
+        }
+    }
+    if (part > 0 && part < n_parts) {
+#pragma unroll
+        for (int g = 0; g < kValueGroup; g++) part_s[((part - 1) * kValueGroup + g) * hidden + o] = a[g];
     }
     __syncthreads();
     if (part == 0) {
@@ -632,7 +656,9 @@ cudaError_t launch_expand(const uint32_t* planes, const uint8_t* rotation, int n
 cudaError_t trunk_kernel_setup() {
     cudaError_t e = cudaFuncSetAttribute(trunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytes);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(trunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytes);
+    e = cudaFuncSetAttribute(trunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(value_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
 }
 
 cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool pair, cudaStream_t st) {
@@ -668,7 +694,7 @@ cudaError_t launch_policy_head(const float* zbuf, int chunk_rows, const float* b
 cudaError_t launch_value_head(const float* zbuf, int chunk_rows, const float* bias, const float* ip1_wt,
                               const float* ip1_b, int hidden, const float* ip2_w, const float* ip2_b, int n,
                               float* winrate, cudaStream_t st) {
-    const size_t smem = (kValueGroup * kPoints + 4 * kValueGroup * hidden) * sizeof(float);
+    const size_t smem = ((size_t)kVSlots * kVTileRows * hidden + kValueGroup * kPoints + 4 * kValueGroup * hidden) * sizeof(float) + 64;
     value_head_kernel<<<(n + kValueGroup - 1) / kValueGroup, kValueThreads, smem, st>>>(zbuf, chunk_rows, bias, ip1_wt, ip1_b, hidden,
                                                                              ip2_w, ip2_b, n, winrate);
     return cudaGetLastError();

@@ -35,4 +35,12 @@ for mode in (1, 0, 2):
         e1.record(st); torch.cuda.synchronize()
         print(f"flags={os.environ.get('LB2_DEBUG_FLAGS','0')} mode={mode}{'(single-cta)' if mode == 2 else ''} {which:6s} B={B}: step {e0.elapsed_time(e1)/20*1e3:8.1f} us, "
               f"trunk {ev.get_option('trunk_ns')/20/1e3:8.1f} us", flush=True)
+        ev.set_option("profile_trunk", 2)
+        for _ in range(20):
+            ev.eval_both_device(*a, stream=st.cuda_stream)
+        torch.cuda.synchronize()
+        if which == "both" and mode == 1:
+            print("   segments (us): expand %.1f  trunk %.1f  policy head %.1f  value head %.1f" % tuple(ev.get_option(f"seg{k}") / 1e3 for k in range(4)), flush=True)
+        else:
+            ev.get_option("seg3")
         ev.set_option("profile_trunk", 0)
