@@ -114,7 +114,7 @@ struct DeviceState {
     uint32_t epoch = 0;
     unsigned long long* trace = nullptr;   // debug timeline buffer (option "trace")
     std::vector<cudaEvent_t> prof_events;  // (start, stop) pairs around trunk launches
-    std::vector<cudaEvent_t> seg_events;   // profile_trunk == 2: one event after every launch, 5 per eval
+    std::vector<cudaEvent_t> seg_events;   // profile_trunk == 2: one event around every launch, 4 per eval
     long plan_key[8] = {-1, -1, -1, -1, -1, -1, -1, -1};  // n, run0, run1, limit0, limit1, workspace pointers
 };
 
@@ -483,32 +483,45 @@ int eval_on_device(lb2_ctx* ctx, DeviceState* d, const uint32_t* d_pol, const ui
     mark();
     const uint32_t* planes[2] = {d_pol, d_val};
     int limit[2] = {1 << 20, 1 << 20};
+    lb2::ExpandArgs ea;
+    memset(&ea, 0, sizeof ea);
+    ea.rotation = d_rot;
+    ea.n = n;
     for (int k = 0; k < 2; k++) {
         if (!run[k]) continue;
         NetDev& nd = d->net[k];
         if (nd.cap < n) return fail(LB2_ERR_STATE, "workspace too small");
-        const bool pf = (k == 1 && nd.ip1_wt);
-        CU_TRY(lb2::launch_expand(planes[k], d_rot, n, nd.x0, nd.rows5, pf ? nd.ip1_wt : nullptr,
-                                  pf ? (size_t)lb2::kPoints * nd.hidden * sizeof(float) : 0, st));
-        ctx->launches++;
+        ea.planes[ea.n_nets] = planes[k];
+        ea.x0[ea.n_nets] = nd.x0;
+        ea.chunk_rows[ea.n_nets] = nd.rows5;
+        ea.n_nets++;
+        if (k == 1 && nd.ip1_wt) {  // pull the value head's matrix into L2 while the trunk runs
+            ea.pf = reinterpret_cast<const uint8_t*>(nd.ip1_wt);
+            ea.pf_bytes = (size_t)lb2::kPoints * nd.hidden * sizeof(float);
+        }
     }
+    CU_TRY(lb2::launch_expand(ea, st));
+    ctx->launches++;
     mark();
     JobPlan pl;
     int rc = run_trunk(ctx, d, run, n, limit, st, &pl);
     if (rc) return rc;
     mark();
+    lb2::HeadArgs ha;
+    memset(&ha, 0, sizeof ha);
+    ha.rotation = d_rot;
+    ha.temp = temp;
     if (run[0]) {
         NetDev& nd = d->net[0];
-        CU_TRY(lb2::launch_policy_head(nd.zbuf, nd.rows3, nd.head_b, d_rot, n, temp, d_probs, st));
-        ctx->launches++;
+        ha.p_zbuf = nd.zbuf; ha.p_chunk_rows = nd.rows3; ha.p_bias = nd.head_b; ha.probs = d_probs; ha.n_policy = n;
     }
-    mark();
     if (run[1]) {
         NetDev& nd = d->net[1];
-        CU_TRY(lb2::launch_value_head(nd.zbuf, nd.rows3, nd.head_b, nd.ip1_wt, nd.ip1_b, nd.hidden, nd.ip2_w, nd.ip2_b, n,
-                                      d_win, st));
-        ctx->launches++;
+        ha.v_zbuf = nd.zbuf; ha.v_chunk_rows = nd.rows3; ha.v_bias = nd.head_b; ha.ip1_wt = nd.ip1_wt; ha.ip1_b = nd.ip1_b;
+        ha.hidden = nd.hidden; ha.ip2_w = nd.ip2_w; ha.ip2_b = nd.ip2_b; ha.winrate = d_win; ha.n_value = n;
     }
+    CU_TRY(lb2::launch_heads(ha, st));
+    ctx->launches++;
     mark();
     return LB2_OK;
 }
@@ -905,14 +918,14 @@ long lb2_get_option(lb2_ctx* ctx, const char* name) {
     if (!strcmp(name, "sm_count")) return ctx->dev.empty() ? 0 : ctx->dev[0].sm_count;
     if (!strncmp(name, "seg", 3) && name[3] >= '0' && name[3] <= '3') {
         // mean ns of segment k over the evals recorded with profile_trunk == 2:
-        // seg0 expand, seg1 trunk, seg2 policy head, seg3 value head; "seg3" also clears the record
+        // seg0 expand, seg1 trunk, seg2 heads; "seg3" only clears the record
         std::lock_guard<std::mutex> lk(ctx->eval_mu);
         DeviceState& d = ctx->dev[0];
         cudaSetDevice(d.id);
         cudaDeviceSynchronize();
         const int k = name[3] - '0';
         double ms_total = 0; long cnt = 0;
-        for (size_t i = 0; i + 4 < d.seg_events.size() + 1 && i + 4 < d.seg_events.size(); i += 5) {
+        for (size_t i = 0; k < 3 && i + 3 < d.seg_events.size(); i += 4) {
             float ms = 0;
             if (cudaEventElapsedTime(&ms, d.seg_events[i + k], d.seg_events[i + k + 1]) == cudaSuccess) { ms_total += ms; cnt++; }
         }
@@ -972,7 +985,11 @@ int lb2_debug_trunk(lb2_ctx* ctx, int kind, const uint32_t* planes, const uint8_
     if ((rc = ensure_workspace(&nd, kind, n))) return rc;
     CU_TRY(cudaMemcpyAsync(d->rot, rotation, n, cudaMemcpyHostToDevice, d->stream));
     CU_TRY(cudaMemcpyAsync(nd.planes, planes, (size_t)n * lb2::kPoints * sizeof(uint32_t), cudaMemcpyHostToDevice, d->stream));
-    CU_TRY(lb2::launch_expand(nd.planes, d->rot, n, nd.x0, nd.rows5, nullptr, 0, d->stream));
+    lb2::ExpandArgs ea;
+    memset(&ea, 0, sizeof ea);
+    ea.rotation = d->rot; ea.n = n; ea.n_nets = 1;
+    ea.planes[0] = nd.planes; ea.x0[0] = nd.x0; ea.chunk_rows[0] = nd.rows5;
+    CU_TRY(lb2::launch_expand(ea, d->stream));
     ctx->launches++;
     int limit[2] = {0, 0};
     limit[kind] = n_layers;

@@ -33,28 +33,30 @@ __device__ __forceinline__ int rev_rotate_idx(int v, int s) {
 __device__ __forceinline__ float elu1(float v) { return v > 0.0f ? v : (__expf(v) - 1.0f); }
 
 // ------------------------------------------------------------------------------------------
-// expand: one thread per row of the S=21 row space; writes 32 channels = 4 chunks of 8 fp16.
+// expand: one thread per row of the S=21 row space of either net; writes 32 channels = 4 chunks of
+// 8 fp16. Spare threads prefetch a read-late buffer into L2.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) expand_planes_kernel(const uint32_t* __restrict__ planes,
-                                                            const uint8_t* __restrict__ rotation, int n,
-                                                            __half* __restrict__ x0, int chunk_rows,
-                                                            const uint8_t* __restrict__ pf, size_t pf_bytes) {
-    const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= n * 441) {
-        // spare blocks pull a read-late buffer (the value head's 361xH matrix) into L2 while the
-        // trunk runs, keeping its HBM latency off the end of the step
-        const size_t i = (size_t)(row - n * 441) * 128;
-        if (i < pf_bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + i));
+__global__ void __launch_bounds__(256) expand_planes_kernel(const ExpandArgs A) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t per_net = (size_t)A.n * 441;
+    const size_t total = per_net * A.n_nets;
+    if (t >= total) {
+        const size_t i = (t - total) * 128;
+        if (i < A.pf_bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.pf + i));
         return;
     }
+    const int k = (int)(t / per_net);
+    const int row = (int)(t - (size_t)k * per_net);
     const int pos = row / 441, rem = row - pos * 441;
     const int y = rem / 21, x = rem - y * 21;
     uint32_t bits = 0;
     if (x < kBoard && y < kBoard) {
-        const int src = rotate_idx(y * kBoard + x, rotation[pos] & 7);
-        bits = planes[(size_t)pos * kPoints + src];
+        const int src = rotate_idx(y * kBoard + x, A.rotation[pos] & 7);
+        bits = A.planes[k][(size_t)pos * kPoints + src];
     }
     const uint32_t one = 0x3C00u;  // fp16 1.0
+    __half* x0 = A.x0[k];
+    const int chunk_rows = A.chunk_rows[k];
 #pragma unroll
     for (int c8 = 0; c8 < 4; c8++) {
         uint32_t b = bits >> (8 * c8);
@@ -521,13 +523,13 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // policy head: one CTA per position. logit = ELU(b + conv), softmax with temperature over the
 // 361 points (Network.cpp:450-469), un-rotate (Network.cpp:820-823).
-__global__ void __launch_bounds__(384) policy_head_kernel(const float* __restrict__ zbuf, int chunk_rows,
-                                                          const float* __restrict__ bias,
-                                                          const uint8_t* __restrict__ rotation, float temp,
-                                                          float* __restrict__ probs) {
-    __shared__ float sm[kPoints];
-    __shared__ float red[12];
-    const int pos = blockIdx.x, tid = threadIdx.x;
+__device__ __forceinline__ void policy_head_body(const float* __restrict__ zbuf, int chunk_rows,
+                                                 const float* __restrict__ bias, const uint8_t* __restrict__ rotation,
+                                                 float temp, float* __restrict__ probs, int pos, float* smem_f) {
+    float* sm = smem_f;            // [361]
+    float* red = smem_f + 368;     // [12]
+    const int tid = threadIdx.x;
+    if (tid >= 384) return;        // 12 warps do the work (no block-wide barrier below this point involves the rest)
     float logit = -INFINITY;
     if (tid < kPoints) {
         const int y = tid / kBoard, x = tid - y * kBoard;
@@ -535,18 +537,18 @@ __global__ void __launch_bounds__(384) policy_head_kernel(const float* __restric
     }
     float m = warp_max(logit);
     if ((tid & 31) == 0) red[tid >> 5] = m;
-    __syncthreads();
+    named_bar_sync(3, 384);
     m = red[0];
     for (int i = 1; i < 12; i++) m = fmaxf(m, red[i]);
-    __syncthreads();
+    named_bar_sync(3, 384);
     const float e = (tid < kPoints) ? expf(logit / temp - m / temp) : 0.0f;
     float s = warp_sum(e);
     if ((tid & 31) == 0) red[tid >> 5] = s;
-    __syncthreads();
+    named_bar_sync(3, 384);
     s = 0.0f;
     for (int i = 0; i < 12; i++) s += red[i];
     if (tid < kPoints) sm[tid] = e / s;
-    __syncthreads();
+    named_bar_sync(3, 384);
     if (tid < kPoints) probs[(size_t)pos * kPoints + tid] = sm[rev_rotate_idx(tid, rotation[pos] & 7)];
 }
 
@@ -558,21 +560,19 @@ constexpr int kValueGroup = 4;
 constexpr int kValueThreads = 1024;  // thread (o, part): output o, input rows part, part+4, ... of each tile
 constexpr int kVTileRows = 19, kVTiles = 19, kVSlots = 4;
 
-__global__ void __launch_bounds__(kValueThreads) value_head_kernel(const float* __restrict__ zbuf, int chunk_rows,
-                                                                   const float* __restrict__ bias,
-                                                                   const float* __restrict__ ip1_wt /*[361][hidden]*/,
-                                                                   const float* __restrict__ ip1_b, int hidden,
-                                                                   const float* __restrict__ ip2_w,
-                                                                   const float* __restrict__ ip2_b, int n,
-                                                                   float* __restrict__ winrate) {
-    extern __shared__ __align__(128) uint8_t vsm[];
+__device__ __forceinline__ void value_head_body(const float* __restrict__ zbuf, int chunk_rows,
+                                                const float* __restrict__ bias,
+                                                const float* __restrict__ ip1_wt /*[361][hidden]*/,
+                                                const float* __restrict__ ip1_b, int hidden,
+                                                const float* __restrict__ ip2_w, const float* __restrict__ ip2_b, int n,
+                                                float* __restrict__ winrate, int block, uint8_t* vsm) {
     float* w_s = reinterpret_cast<float*>(vsm);                       // [kVSlots][19][hidden]
     float* v_s = w_s + kVSlots * kVTileRows * hidden;                 // [361][G]
     float* h_s = v_s + kValueGroup * kPoints;                         // [G][hidden]
     float* part_s = h_s + kValueGroup * hidden;                       // [3][G][hidden]
     uint64_t* full = reinterpret_cast<uint64_t*>(part_s + 3 * kValueGroup * hidden);  // [kVSlots]
     const int tid = threadIdx.x;
-    const int pos0 = blockIdx.x * kValueGroup;
+    const int pos0 = block * kValueGroup;
     const uint32_t tile_bytes = kVTileRows * hidden * sizeof(float);
     if (tid == 0) {
         for (int i = 0; i < kVSlots; i++) mbar_init(full + i, 1);
@@ -642,14 +642,25 @@ __global__ void __launch_bounds__(kValueThreads) value_head_kernel(const float* 
     }
 }
 
+// Both heads in one launch: blocks [0, value_blocks) run the value head, the rest the policy head
+// (one position per block, first 384 threads).
+__global__ void __launch_bounds__(kValueThreads) heads_kernel(const HeadArgs A) {
+    extern __shared__ __align__(128) uint8_t hsm[];
+    const int value_blocks = (A.n_value + kValueGroup - 1) / kValueGroup;
+    if ((int)blockIdx.x < value_blocks)
+        value_head_body(A.v_zbuf, A.v_chunk_rows, A.v_bias, A.ip1_wt, A.ip1_b, A.hidden, A.ip2_w, A.ip2_b, A.n_value,
+                        A.winrate, blockIdx.x, hsm);
+    else
+        policy_head_body(A.p_zbuf, A.p_chunk_rows, A.p_bias, A.rotation, A.temp, A.probs, blockIdx.x - value_blocks,
+                         reinterpret_cast<float*>(hsm));
+}
+
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-cudaError_t launch_expand(const uint32_t* planes, const uint8_t* rotation, int n, __half* x0, int chunk_rows,
-                          const void* prefetch, size_t prefetch_bytes, cudaStream_t st) {
-    const size_t threads = (size_t)n * 441 + (prefetch_bytes + 127) / 128;
-    expand_planes_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(planes, rotation, n, x0, chunk_rows,
-                                                                           static_cast<const uint8_t*>(prefetch), prefetch_bytes);
+cudaError_t launch_expand(const ExpandArgs& a, cudaStream_t st) {
+    const size_t threads = (size_t)a.n * 441 * a.n_nets + (a.pf_bytes + 127) / 128;
+    expand_planes_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -658,7 +669,7 @@ cudaError_t trunk_kernel_setup() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(trunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytes);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(value_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    return cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
 }
 
 cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool pair, cudaStream_t st) {
@@ -685,18 +696,14 @@ cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool 
     return pair ? cudaLaunchKernelEx(&cfg, trunk_kernel<true>, p) : cudaLaunchKernelEx(&cfg, trunk_kernel<false>, p);
 }
 
-cudaError_t launch_policy_head(const float* zbuf, int chunk_rows, const float* bias, const uint8_t* rotation, int n,
-                               float temp, float* probs, cudaStream_t st) {
-    policy_head_kernel<<<n, 384, 0, st>>>(zbuf, chunk_rows, bias, rotation, temp, probs);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_value_head(const float* zbuf, int chunk_rows, const float* bias, const float* ip1_wt,
-                              const float* ip1_b, int hidden, const float* ip2_w, const float* ip2_b, int n,
-                              float* winrate, cudaStream_t st) {
-    const size_t smem = ((size_t)kVSlots * kVTileRows * hidden + kValueGroup * kPoints + 4 * kValueGroup * hidden) * sizeof(float) + 64;
-    value_head_kernel<<<(n + kValueGroup - 1) / kValueGroup, kValueThreads, smem, st>>>(zbuf, chunk_rows, bias, ip1_wt, ip1_b, hidden,
-                                                                             ip2_w, ip2_b, n, winrate);
+cudaError_t launch_heads(const HeadArgs& a, cudaStream_t st) {
+    const int value_blocks = (a.n_value + kValueGroup - 1) / kValueGroup;
+    const int blocks = value_blocks + a.n_policy;
+    if (blocks == 0) return cudaSuccess;
+    size_t smem = 2048;  // policy head scratch
+    if (a.n_value)
+        smem = ((size_t)kVSlots * kVTileRows * a.hidden + kValueGroup * kPoints + 4 * kValueGroup * a.hidden) * sizeof(float) + 64;
+    heads_kernel<<<blocks, kValueThreads, smem, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -85,15 +85,29 @@ struct TrunkParams {
                           // bit3 = no B loads, bit4 = no A loads, bit5 = only the first M half of 3x3 layers
 };
 
+struct ExpandArgs {
+    const uint32_t* planes[2];   // packed bit-planes of up to two nets
+    __half* x0[2];               // their first-conv input buffers (S=21 row space)
+    int32_t chunk_rows[2];
+    const uint8_t* rotation;
+    int32_t n, n_nets;
+    const uint8_t* pf;           // optional buffer to pull into L2
+    size_t pf_bytes;
+};
+
+struct HeadArgs {
+    // policy head (n_policy positions, 0 = skip)
+    const float* p_zbuf; int32_t p_chunk_rows; const float* p_bias; const uint8_t* rotation; float temp; float* probs;
+    int32_t n_policy;
+    // value head (n_value positions, 0 = skip)
+    const float* v_zbuf; int32_t v_chunk_rows; const float* v_bias; const float* ip1_wt; const float* ip1_b; int32_t hidden;
+    const float* ip2_w; const float* ip2_b; float* winrate; int32_t n_value;
+};
+
 // launchers (lb2_kernels.cu)
-cudaError_t launch_expand(const uint32_t* planes, const uint8_t* rotation, int n, __half* x0, int chunk_rows,
-                          const void* prefetch, size_t prefetch_bytes, cudaStream_t st);
+cudaError_t launch_expand(const ExpandArgs& a, cudaStream_t st);
 cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool pair, cudaStream_t st);
-cudaError_t launch_policy_head(const float* zbuf, int chunk_rows, const float* bias, const uint8_t* rotation, int n,
-                               float temp, float* probs, cudaStream_t st);
-cudaError_t launch_value_head(const float* zbuf, int chunk_rows, const float* bias, const float* ip1_wt,
-                              const float* ip1_b, int hidden, const float* ip2_w, const float* ip2_b, int n,
-                              float* winrate, cudaStream_t st);
+cudaError_t launch_heads(const HeadArgs& a, cudaStream_t st);
 cudaError_t trunk_kernel_setup();
 
 }  // namespace lb2

@@ -40,7 +40,7 @@ for mode in (1, 0, 2):
             ev.eval_both_device(*a, stream=st.cuda_stream)
         torch.cuda.synchronize()
         if which == "both" and mode == 1:
-            print("   segments (us): expand %.1f  trunk %.1f  policy head %.1f  value head %.1f" % tuple(ev.get_option(f"seg{k}") / 1e3 for k in range(4)), flush=True)
+            print("   segments (us): expand %.1f  trunk %.1f  heads %.1f" % tuple(ev.get_option(f"seg{k}") / 1e3 for k in range(3)), flush=True); ev.get_option("seg3")
         else:
             ev.get_option("seg3")
         ev.set_option("profile_trunk", 0)
