@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
     // broadcast reads (one wavefront per warp-wide LDS.128), resident for the whole launch
     float* bias_all = reinterpret_cast<float*>(smem + kTrunkRingBytes + 256);   // [kMaxLaunchJobs][128]
     float* headw_all = bias_all + kMaxLaunchJobs * 128;                         // [2 nets][9][128]
+    LayerJob* jobs_s = reinterpret_cast<LayerJob*>(headw_all + 2 * 9 * 128);    // [kMaxLaunchJobs] job table copy
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -169,8 +170,14 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         for (int i = 0; i < kMaxTensorMaps; i++) tma_prefetch_desc(&P.tmaps[i]);
     }
     if (warp == 1) { if (kPair) tmem_alloc_pair<512>(tmem_slot); else tmem_alloc<512>(tmem_slot); }
-    const LayerJob* __restrict__ jobs = P.jobs;
-    // every job's bias and both fused-head weight sets stay resident in smem for the whole launch
+    // the job table, every job's bias and both fused-head weight sets stay resident in smem for the
+    // whole launch (the per-item descriptor reads would otherwise cost an L2 round trip per role)
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.jobs);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(jobs_s);
+        for (int i = threadIdx.x; i < P.n_jobs * (int)(sizeof(LayerJob) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    const LayerJob* jobs = P.jobs;
     for (int i = threadIdx.x; i < P.n_jobs * 128; i += blockDim.x) {
         const int jj = i >> 7, c = i & 127;
         bias_all[i] = c < jobs[jj].n_out ? jobs[jj].bias[c] : 0.0f;
@@ -185,6 +192,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
     if (kPair) cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    jobs = jobs_s;  // from here on every role reads the shared-memory copy
 
     if (warp == 0) {
         // ================================ TMA producer ================================

@@ -37,8 +37,8 @@ constexpr int kPubDepth = 4;        // tiles that may be waiting for publication
 constexpr int kRingBytesSingle = kStagesSingle * kStageBytesSingle;   // 192,512
 constexpr int kRingBytesPair = kStagesPair * kStageBytesPair;         // 178,176
 constexpr int kTrunkRingBytes = kRingBytesSingle > kRingBytesPair ? kRingBytesSingle : kRingBytesPair;
-// ring | mbarriers etc. (256 B) | bias [jobs][128] f32 | fused-head weights [2 nets][9][128] f32
-constexpr int kTrunkSmemBytes = kTrunkRingBytes + 256 + kMaxLaunchJobs * 128 * 4 + 2 * 9 * 128 * 4;
+// ring | mbarriers etc. (256 B) | bias [jobs][128] f32 | fused-head weights [2 nets][9][128] f32 | job table
+constexpr int kTrunkSmemBytes = kTrunkRingBytes + 256 + kMaxLaunchJobs * 128 * 4 + 2 * 9 * 128 * 4 + kMaxLaunchJobs * 160;
 constexpr int kMaxLayers = 16;
 constexpr int kMaxTensorMaps = 6;
 constexpr int kMaxJobs = 32;
@@ -111,3 +111,4 @@ cudaError_t launch_heads(const HeadArgs& a, cudaStream_t st);
 cudaError_t trunk_kernel_setup();
 
 }  // namespace lb2
+static_assert(sizeof(lb2::LayerJob) <= 160 && sizeof(lb2::LayerJob) % 4 == 0, "job table slot size");
