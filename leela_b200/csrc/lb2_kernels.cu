@@ -160,7 +160,8 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 127u) __trap();  // TMA destinations need 128-byte alignment
-        for (int i = 0; i < kStages; i++) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); mbar_init(pfull_bar + i, 1); }
+        // pair mode: the leader's "stage full" barrier also counts the peer's "my half landed" arrive
+        for (int i = 0; i < kStages; i++) { mbar_init(full_bar + i, (kPair && leader) ? 2 : 1); mbar_init(empty_bar + i, 1); }
         for (int i = 0; i < 2; i++) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, kPair ? 2 * kEpilogueWarps : kEpilogueWarps); }
         for (int i = 0; i < kPubDepth; i++) mbar_init(pub_bar + i, kEpilogueWarps);
         *pub_done = 0;
@@ -193,6 +194,10 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     jobs = jobs_s;  // from here on every role reads the shared-memory copy
+    if (P.trace && threadIdx.x == 0) {  // effective SM clock: cycle and wall timestamps at both ends
+        unsigned long long* t = P.trace + ((size_t)blockIdx.x * kTraceItems + (kTraceItems - 1)) * kTraceEvents;
+        t[0] = global_ns(); t[1] = (unsigned long long)clock64();
+    }
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -255,86 +260,91 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                 const int n_st = jobs[j].n_slabs * n_tap_groups(jobs[j].ksize);
                 for (int s = 0; s < n_st; s++) {
                     mbar_wait(full_bar + stage, phase);
-                    mbar_arrive_remote(pfull_bar + stage, 0);
+                    mbar_arrive_remote(full_bar + stage, 0);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
-        // The whole warp walks the pipeline; one elected lane issues the tcgen05 instructions.
-        int stage = 0; uint32_t phase = 0; int j = 0; uint32_t it = 0;
-        for (int q = W.first; q < P.item_end; q += W.step, it++) {
-            while (q >= jobs[j].item_base + jobs[j].n_items) j++;
-            const LayerJob& J = jobs[j];
-            const int ksize = J.ksize, n_out = J.n_out, n_slabs = J.n_slabs, halo = J.halo;
-            const int S = (P.debug_flags & 2) ? 0 : J.S, DX = (P.debug_flags & 2) ? 0 : 1;
-            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-            if (lane == 0) LB2_TRACE(it, 4);
-            mbar_wait(tempty_bar + acc, acc_phase ^ 1);
-            tc_fence_after_sync();
-            if (lane == 0) LB2_TRACE(it, 5);
-            const uint32_t idesc = umma_idesc_f16(kPair ? 256 : 128, n_out);
-            const int rows_halo = kTileRows + 2 * halo;
-            const int n_mine = kPair ? (n_out >> 1) : n_out;   // B rows held per CTA
-            // descriptor = hi32 (SBO = 128 B, version 1) : lo32 (LBO << 16 | start address >> 4)
-            const uint32_t desc_hi = (128u >> 4) | (1u << 14);
-            const uint32_t a_lo_base = ((uint32_t)(rows_halo * 16) >> 4) << 16;
-            const uint32_t b_lo_base = ((uint32_t)(n_mine * 16) >> 4) << 16;
-            const uint32_t b_step = (uint32_t)(n_mine * 32) >> 4;  // one tap of B, in 16-byte units
-            const uint32_t d0 = tmem_base + (acc * 2 + 0) * 128;
-            const uint32_t d1 = tmem_base + (acc * 2 + 1) * 128;
-            const int ng = n_tap_groups(ksize);
-            const int pad = ksize >> 1;
-            uint32_t accumulate = 0;
-            for (int s = 0; s < n_slabs; s++) {
-                for (int g = 0; g < ng; g++) {
-                    mbar_wait(full_bar + stage, phase);
-                    if (kPair) mbar_wait(pfull_bar + stage, phase);
+        // One elected lane runs the whole pipeline. The tensor pipe only queues a few MMAs, so the
+        // time between the last MMA of one stage and the first of the next must stay short: the
+        // readiness of the NEXT stage is probed (non-blocking) before this stage's MMAs are issued,
+        // so its latency is hidden behind them.
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0; int j = 0; uint32_t it = 0;
+            bool next_ready = false;  // full_bar[stage] already observed complete for `phase`
+            for (int q = W.first; q < P.item_end; q += W.step, it++) {
+                while (q >= jobs[j].item_base + jobs[j].n_items) j++;
+                const LayerJob& J = jobs[j];
+                const int ksize = J.ksize, n_out = J.n_out, n_slabs = J.n_slabs, halo = J.halo;
+                const int S = (P.debug_flags & 2) ? 0 : J.S, DX = (P.debug_flags & 2) ? 0 : 1;
+                const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+                LB2_TRACE(it, 4);
+                mbar_wait(tempty_bar + acc, acc_phase ^ 1);
+                LB2_TRACE(it, 5);
+                const uint32_t idesc = umma_idesc_f16(kPair ? 256 : 128, n_out);
+                const int rows_halo = kTileRows + 2 * halo;
+                const int n_mine = kPair ? (n_out >> 1) : n_out;   // B rows held per CTA
+                // descriptor = hi32 (SBO = 128 B, version 1) : lo32 (LBO << 16 | start address >> 4)
+                const uint64_t desc_hi = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;
+                const uint32_t a_lo_base = ((uint32_t)(rows_halo * 16) >> 4) << 16;
+                const uint32_t b_lo_base = ((uint32_t)(n_mine * 16) >> 4) << 16;
+                const uint32_t b_step = (uint32_t)(n_mine * 32) >> 4;  // one tap of B, in 16-byte units
+                const uint32_t d0 = tmem_base + (acc * 2 + 0) * 128;
+                const uint32_t d1 = tmem_base + (acc * 2 + 1) * 128;
+                const int ng = n_tap_groups(ksize);
+                const int pad = ksize >> 1;
+                const int n_st = n_slabs * ng;
+                uint32_t accumulate = 0;
+                int g = 0;
+                for (int s = 0; s < n_st; s++) {
+                    if (!next_ready) mbar_wait(full_bar + stage, phase);
                     tc_fence_after_sync();
-                    if (lane == 0 && s == 0 && g == 0) LB2_TRACE(it, 6);
-                    __syncwarp();
-                    if (elect_one()) {
-                        const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
-                        // (address of row `halo` of the A slab) >> 4; a tap shifts it by dy*S+dx rows
-                        const uint32_t a16 = (a_addr >> 4) + halo;
-                        uint32_t b16 = (a_addr + kASlabBytes) >> 4;
-                        if (ksize == 3) {
+                    if (s == 0) LB2_TRACE(it, 6);
+                    // probe the following stage now; the answer is consumed after this stage's MMAs
+                    int nstage = stage + 1; uint32_t nphase = phase;
+                    if (nstage == kStages) { nstage = 0; nphase ^= 1; }
+                    next_ready = mbar_try_wait(full_bar + nstage, nphase);
+                    const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+                    // (address of row `halo` of the A slab) >> 4; a tap shifts it by dy*S+dx rows
+                    const uint32_t a16 = (a_addr >> 4) + halo;
+                    uint32_t b16 = (a_addr + kASlabBytes) >> 4;
+                    if (ksize == 3) {
 #pragma unroll
-                            for (int t = 0; t < 9; t++) {
-                                const int off = (t / 3 - 1) * S + (t % 3 - 1) * DX;
-                                const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo_base | (b16 & 0x3FFFu));
-                                const uint32_t a0 = a16 + off;
-                                umma_f16<kPair>(d0, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo_base | (a0 & 0x3FFFu)), bdesc, idesc, accumulate);
-                                if (!(P.debug_flags & 32))
-                                    umma_f16<kPair>(d1, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo_base | ((a0 + 128) & 0x3FFFu)), bdesc, idesc, accumulate);
-                                accumulate = 1;
-                                b16 += b_step;
-                            }
-                        } else {
-                            const int t0 = tap_group_begin(g), t1 = tap_group_end(ksize, g);
-                            int kr = t0 / 5, kc = t0 - kr * 5;
-                            for (int t = t0; t < t1; t++) {
-                                const int off = (kr - pad) * S + (kc - pad) * DX;
-                                const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo_base | (b16 & 0x3FFFu));
-                                const uint32_t a0 = a16 + off;
-                                umma_f16<kPair>(d0, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo_base | (a0 & 0x3FFFu)), bdesc, idesc, accumulate);
-                                umma_f16<kPair>(d1, (static_cast<uint64_t>(desc_hi) << 32) | (a_lo_base | ((a0 + 128) & 0x3FFFu)), bdesc, idesc, accumulate);
-                                accumulate = 1;
-                                b16 += b_step;
-                                if (++kc == 5) { kc = 0; kr++; }
-                            }
+                        for (int t = 0; t < 9; t++) {
+                            const int off = (t / 3 - 1) * S + (t % 3 - 1) * DX;
+                            const uint64_t bdesc = desc_hi | (b_lo_base | (b16 & 0x3FFFu));
+                            const uint32_t a0 = a16 + off;
+                            umma_f16<kPair>(d0, desc_hi | (a_lo_base | (a0 & 0x3FFFu)), bdesc, idesc, accumulate);
+                            if (!(P.debug_flags & 32))
+                                umma_f16<kPair>(d1, desc_hi | (a_lo_base | ((a0 + 128) & 0x3FFFu)), bdesc, idesc, accumulate);
+                            accumulate = 1;
+                            b16 += b_step;
                         }
-                        umma_commit<kPair>(empty_bar + stage);  // frees the smem stage (in both CTAs) when these MMAs finish
+                    } else {
+                        const int t0 = tap_group_begin(g), t1 = tap_group_end(ksize, g);
+                        int kr = t0 / 5, kc = t0 - kr * 5;
+                        for (int t = t0; t < t1; t++) {
+                            const int off = (kr - pad) * S + (kc - pad) * DX;
+                            const uint64_t bdesc = desc_hi | (b_lo_base | (b16 & 0x3FFFu));
+                            const uint32_t a0 = a16 + off;
+                            umma_f16<kPair>(d0, desc_hi | (a_lo_base | (a0 & 0x3FFFu)), bdesc, idesc, accumulate);
+                            umma_f16<kPair>(d1, desc_hi | (a_lo_base | ((a0 + 128) & 0x3FFFu)), bdesc, idesc, accumulate);
+                            accumulate = 1;
+                            b16 += b_step;
+                            if (++kc == 5) { kc = 0; kr++; }
+                        }
+                        if (++g == ng) g = 0;
                     }
-                    __syncwarp();
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    umma_commit<kPair>(empty_bar + stage);  // frees the smem stage (in both CTAs) when these MMAs finish
+                    stage = nstage; phase = nphase;
                 }
+                umma_commit<kPair>(tfull_bar + acc);  // accumulator complete -> epilogue (both CTAs)
+                LB2_TRACE(it, 7);
             }
-            if (elect_one()) umma_commit<kPair>(tfull_bar + acc);  // accumulator complete -> epilogue (both CTAs)
-            if (lane == 0) LB2_TRACE(it, 7);
-            __syncwarp();
         }
+        __syncwarp();
     } else if (warp < 2 + kEpilogueWarps) {
         // ================================ epilogue ====================================
         const int ew = warp - 2;          // 0..7
@@ -359,7 +369,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             const int cols = n_out >> 1;          // columns handled by this warp
             const int col0 = half * cols;
 #pragma unroll 1
-            for (int h = 0; h < 2; h++) {
+            for (int h = 0; h < ((P.debug_flags & 64) ? 0 : 2); h++) {
                 const int row = tile * kTileRows + h * 128 + quad * 32 + lane;
                 int pos, y, x;
                 if (wide) { pos = row / 441; const int rem = row - pos * 441; y = rem / 21; x = rem - y * 21; }
@@ -499,6 +509,10 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
 
     tc_fence_before_sync();
     __syncthreads();
+    if (P.trace && threadIdx.x == 0) {
+        unsigned long long* t = P.trace + ((size_t)blockIdx.x * kTraceItems + (kTraceItems - 1)) * kTraceEvents;
+        t[2] = global_ns(); t[3] = (unsigned long long)clock64();
+    }
     if (kPair) cluster_sync_all();  // nobody exits (or frees TMEM) while its peer may still signal it
     if (warp == 1) { if (kPair) tmem_dealloc_pair<512>(tmem_base); else tmem_dealloc<512>(tmem_base); }
 }

@@ -82,7 +82,7 @@ struct TrunkParams {
     int32_t use_flags;  // 1: cross-CTA dataflow through flags (single persistent launch)
     unsigned long long* trace;  // optional timeline buffer [cta][kTraceItems][kTraceEvents] of %globaltimer ns
     int32_t debug_flags;  // timing experiments only (results wrong): bit1 = all tap offsets 0, bit2 = no epilogue math,
-                          // bit3 = no B loads, bit4 = no A loads, bit5 = only the first M half of 3x3 layers
+                          // bit3 = no B loads, bit4 = no A loads, bit5 = only the first M half of 3x3 layers, bit6 = epilogue does nothing
 };
 
 struct ExpandArgs {

@@ -27,6 +27,10 @@ ev.eval_both_device(*a, stream=st.cuda_stream)
 torch.cuda.synchronize()
 T = ev.read_trace().astype(np.int64)          # [cta, item, event]
 np.save(os.path.join(ROOT, "gpurun_out", f"trace_{which}_{B}.npy"), T)
+clk = T[:, -1, :4]
+mhz = (clk[:, 3] - clk[:, 1]) / np.maximum(clk[:, 2] - clk[:, 0], 1) * 1e3
+print(f"effective SM clock during the kernel: median {np.median(mhz):.0f} MHz (min {mhz.min():.0f}, max {mhz.max():.0f})")
+T = T.copy(); T[:, -1, :] = 0
 valid = T[:, :, 7] > 0
 t0 = T[:, :, 0][T[:, :, 0] > 0].min()
 tend = T[:, :, 12].max()
