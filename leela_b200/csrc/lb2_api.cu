@@ -534,6 +534,14 @@ int check_ready(lb2_ctx* ctx, bool need[2]) {
     return LB2_OK;
 }
 
+// true when `p` is page-locked host memory the device can DMA from/to directly
+bool is_pinned(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 int check_rotations(const uint8_t* rot, int n) {
     for (int i = 0; i < n; i++)
         if (rot[i] > 7) return fail(LB2_ERR_INVALID, "rotation[%d] = %d out of range 0..7", i, (int)rot[i]);
@@ -553,6 +561,10 @@ int eval_host(lb2_ctx* ctx, const uint32_t* pol, const uint32_t* val, const uint
     if (need[0] && !(temp > 0.0f)) return fail(LB2_ERR_INVALID, "softmax temperature must be > 0");
     if ((rc = check_rotations(rot, n))) return rc;
     std::lock_guard<std::mutex> lk(ctx->eval_mu);
+    // caller buffers that are already page-locked are used directly; pageable ones go through the
+    // context's pinned staging buffers
+    const bool pin_in[2] = {is_pinned(pol), is_pinned(val)};
+    const bool pin_rot = is_pinned(rot), pin_probs = is_pinned(probs), pin_win = is_pinned(win);
     const int ndev = (int)ctx->dev.size();
     const int per = (n + ndev - 1) / ndev;
     const int chunk = (int)std::min<long>(ctx->max_batch, per);
@@ -570,31 +582,36 @@ int eval_host(lb2_ctx* ctx, const uint32_t* pol, const uint32_t* val, const uint
             for (int k = 0; k < 2; k++)
                 if (need[k] && (rc = ensure_workspace(&d->net[k], k, std::max(chunk, cnt[di])))) return rc;
             const size_t pbytes = (size_t)cnt[di] * lb2::kPoints * sizeof(uint32_t);
-            memcpy(d->h_rot, rot + lo, cnt[di]);
-            CU_TRY(cudaMemcpyAsync(d->rot, d->h_rot, cnt[di], cudaMemcpyHostToDevice, d->stream));
+            if (pin_rot) {
+                CU_TRY(cudaMemcpyAsync(d->rot, rot + lo, cnt[di], cudaMemcpyHostToDevice, d->stream));
+            } else {
+                memcpy(d->h_rot, rot + lo, cnt[di]);
+                CU_TRY(cudaMemcpyAsync(d->rot, d->h_rot, cnt[di], cudaMemcpyHostToDevice, d->stream));
+            }
             const uint32_t* src[2] = {pol, val};
             for (int k = 0; k < 2; k++) {
                 if (!need[k]) continue;
-                memcpy(d->h_planes[k], src[k] + (size_t)lo * lb2::kPoints, pbytes);
-                CU_TRY(cudaMemcpyAsync(d->net[k].planes, d->h_planes[k], pbytes, cudaMemcpyHostToDevice, d->stream));
+                const uint32_t* from = src[k] + (size_t)lo * lb2::kPoints;
+                if (!pin_in[k]) { memcpy(d->h_planes[k], from, pbytes); from = d->h_planes[k]; }
+                CU_TRY(cudaMemcpyAsync(d->net[k].planes, from, pbytes, cudaMemcpyHostToDevice, d->stream));
             }
             rc = eval_on_device(ctx, d, d->net[0].planes, d->net[1].planes, d->rot, cnt[di], temp,
                                 need[0] ? d->net[0].out : nullptr, need[1] ? d->net[1].out : nullptr, d->stream);
             if (rc) return rc;
             if (need[0])
-                CU_TRY(cudaMemcpyAsync(d->h_probs, d->net[0].out, (size_t)cnt[di] * lb2::kPoints * sizeof(float),
-                                       cudaMemcpyDeviceToHost, d->stream));
+                CU_TRY(cudaMemcpyAsync(pin_probs ? probs + (size_t)lo * lb2::kPoints : d->h_probs, d->net[0].out,
+                                       (size_t)cnt[di] * lb2::kPoints * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
             if (need[1])
-                CU_TRY(cudaMemcpyAsync(d->h_win, d->net[1].out, (size_t)cnt[di] * sizeof(float), cudaMemcpyDeviceToHost,
-                                       d->stream));
+                CU_TRY(cudaMemcpyAsync(pin_win ? win + lo : d->h_win, d->net[1].out, (size_t)cnt[di] * sizeof(float),
+                                       cudaMemcpyDeviceToHost, d->stream));
         }
         for (int di = 0; di < ndev; di++) {
             if (!cnt[di]) continue;
             DeviceState* d = &ctx->dev[di];
             CU_TRY(cudaSetDevice(d->id));
             CU_TRY(cudaStreamSynchronize(d->stream));
-            if (need[0]) memcpy(probs + (size_t)off[di] * lb2::kPoints, d->h_probs, (size_t)cnt[di] * lb2::kPoints * sizeof(float));
-            if (need[1]) memcpy(win + off[di], d->h_win, (size_t)cnt[di] * sizeof(float));
+            if (need[0] && !pin_probs) memcpy(probs + (size_t)off[di] * lb2::kPoints, d->h_probs, (size_t)cnt[di] * lb2::kPoints * sizeof(float));
+            if (need[1] && !pin_win) memcpy(win + off[di], d->h_win, (size_t)cnt[di] * sizeof(float));
         }
     }
     return LB2_OK;

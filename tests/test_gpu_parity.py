@@ -281,3 +281,23 @@ def test_api_level_dropin_against_live_reference_engine():
     assert r["max_dp_direct"] < TOL_P and r["max_dp_average_all"] < TOL_P
     assert r["max_dv_direct"] < TOL_V and r["max_dv_average_all"] < TOL_V
     assert r["top1_agree_or_near_tie"] == r["cases"]
+
+
+def test_in_process_multi_device_sharding(ref_golden):
+    """lb2_init with several devices: weights replicated, each call sharded in contiguous slices,
+    no collective; results identical to one device (skipped on a single-GPU box)."""
+    import torch
+    from leela_b200 import capi, synth
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    g = ref_golden
+    pw, vw = synth.policy_weights(), synth.value_weights()
+    one = capi.Evaluator(policy=pw, value=vw, devices=[0])
+    p1, v1 = one.eval_both(g["policy_planes"], g["value_planes"], g["rotation"], TEMP)
+    one.close()
+    many = capi.Evaluator(policy=pw, value=vw, devices=list(range(min(n_dev, 8))))
+    for n in (96, 5, 1):
+        pm, vm = many.eval_both(g["policy_planes"][:n], g["value_planes"][:n], g["rotation"][:n], TEMP)
+        assert np.array_equal(pm, p1[:n]) and np.array_equal(vm, v1[:n])
+    many.close()
