@@ -173,7 +173,7 @@ def run_ours(args):
     B = args.batch
 
     ev = capi.Evaluator(policy=synth.policy_weights(), value=synth.value_weights(), devices=[local])
-    ev.set_option("max_batch", max(B, 512))
+    ev.set_option("max_batch", max(B, 256))
     pp, vp, rot = load_positions()
     n_sets = pp.shape[0] // B
     order = shard.batch_order(n_sets, rank)

@@ -141,7 +141,7 @@ def test_batch_and_slot_invariance(ev, ref_golden):
     try:
         p3, v3 = ev.eval_both(pp, vp, rot, TEMP)
     finally:
-        ev.set_option("max_batch", 512)
+        ev.set_option("max_batch", 256)
     assert np.array_equal(p3, full_p) and np.array_equal(v3, full_v)
 
 
