@@ -104,6 +104,7 @@ struct DeviceState {
     NetDev net[2];
     uint8_t* rot = nullptr;
     lb2::LayerJob* jobs_dev = nullptr;
+    uint32_t* item_counter = nullptr;  // dynamic scheduling counter, cleared by the expand kernel of each step
     // pinned staging
     uint32_t* h_planes[2] = {nullptr, nullptr};
     uint8_t* h_rot = nullptr;
@@ -147,6 +148,7 @@ struct lb2_ctx {
     long max_batch = 256;  // batch-256 chunks keep both nets' ping-pong activations L2-resident (measured best)
     long profile_trunk = 0;
     long cta_pair = 1;
+    long dynamic_items = 1;
     std::atomic<long> launches{0};
     std::mutex eval_mu;
     // async submission
@@ -444,6 +446,7 @@ int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers
         P.item_begin = 0;
         P.item_end = pl.total_items;
         P.use_flags = 1;
+        P.next_item = ctx->dynamic_items ? d->item_counter : nullptr;
         const int grid = pair ? std::min(d->sm_count & ~1, 2 * pl.total_items) : std::min(d->sm_count, pl.total_items);
         CU_TRY(lb2::launch_trunk(P, grid, true, pair, st));
         ctx->launches++;
@@ -487,6 +490,7 @@ int eval_on_device(lb2_ctx* ctx, DeviceState* d, const uint32_t* d_pol, const ui
     memset(&ea, 0, sizeof ea);
     ea.rotation = d_rot;
     ea.n = n;
+    ea.zero_word = d->item_counter;
     for (int k = 0; k < 2; k++) {
         if (!run[k]) continue;
         NetDev& nd = d->net[k];
@@ -726,6 +730,8 @@ int lb2_init(const int* device_ids, int n_devices, lb2_ctx** ctx_out) {
         d.sm_count = prop.multiProcessorCount;
         CU_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
         CU_TRY(cudaMalloc(&d.jobs_dev, lb2::kMaxJobs * sizeof(lb2::LayerJob)));
+        CU_TRY(cudaMalloc(&d.item_counter, sizeof(uint32_t)));
+        CU_TRY(cudaMemset(d.item_counter, 0, sizeof(uint32_t)));
         CU_TRY(cudaMallocHost(&d.h_jobs, lb2::kMaxJobs * sizeof(lb2::LayerJob)));
         CU_TRY(lb2::trunk_kernel_setup());
         if (ctx->backend.empty()) ctx->backend = std::string("B200 tcgen05: ") + prop.name;
@@ -757,7 +763,7 @@ void lb2_destroy(lb2_ctx* ctx) {
             cudaFree(nd.ip2_w); cudaFree(nd.ip2_b);
             free_workspace(&nd);
         }
-        cudaFree(d.rot); cudaFree(d.jobs_dev);
+        cudaFree(d.rot); cudaFree(d.jobs_dev); cudaFree(d.item_counter);
         cudaFreeHost(d.h_planes[0]); cudaFreeHost(d.h_planes[1]); cudaFreeHost(d.h_rot);
         cudaFreeHost(d.h_probs); cudaFreeHost(d.h_win); cudaFreeHost(d.h_jobs);
         cudaStreamDestroy(d.stream);
@@ -916,6 +922,8 @@ int lb2_set_option(lb2_ctx* ctx, const char* name, long value) {
         }
     } else if (!strcmp(name, "cta_pair")) {
         ctx->cta_pair = value ? 1 : 0;
+    } else if (!strcmp(name, "dynamic_items")) {
+        ctx->dynamic_items = value ? 1 : 0;
     } else if (!strcmp(name, "profile_trunk")) {
         ctx->profile_trunk = value;
     } else if (!strcmp(name, "max_batch")) {
@@ -932,6 +940,7 @@ long lb2_get_option(lb2_ctx* ctx, const char* name) {
     if (!strcmp(name, "trunk_mode")) return ctx->trunk_mode;
     if (!strcmp(name, "max_batch")) return ctx->max_batch;
     if (!strcmp(name, "cta_pair")) return ctx->cta_pair;
+    if (!strcmp(name, "dynamic_items")) return ctx->dynamic_items;
     if (!strcmp(name, "sm_count")) return ctx->dev.empty() ? 0 : ctx->dev[0].sm_count;
     if (!strncmp(name, "seg", 3) && name[3] >= '0' && name[3] <= '3') {
         // mean ns of segment k over the evals recorded with profile_trunk == 2:
@@ -1004,7 +1013,7 @@ int lb2_debug_trunk(lb2_ctx* ctx, int kind, const uint32_t* planes, const uint8_
     CU_TRY(cudaMemcpyAsync(nd.planes, planes, (size_t)n * lb2::kPoints * sizeof(uint32_t), cudaMemcpyHostToDevice, d->stream));
     lb2::ExpandArgs ea;
     memset(&ea, 0, sizeof ea);
-    ea.rotation = d->rot; ea.n = n; ea.n_nets = 1;
+    ea.rotation = d->rot; ea.n = n; ea.n_nets = 1; ea.zero_word = d->item_counter;
     ea.planes[0] = nd.planes; ea.x0[0] = nd.x0; ea.chunk_rows[0] = nd.rows5;
     CU_TRY(lb2::launch_expand(ea, d->stream));
     ctx->launches++;

@@ -38,6 +38,7 @@ __device__ __forceinline__ float elu1(float v) { return v > 0.0f ? v : (__expf(v
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) expand_planes_kernel(const ExpandArgs A) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0 && A.zero_word) *A.zero_word = 0;
     const size_t per_net = (size_t)A.n * 441;
     const size_t total = per_net * A.n_nets;
     if (t >= total) {
@@ -120,18 +121,36 @@ __device__ __forceinline__ float elu_fast(float v) {
     return fmaxf(v, fminf(e - 1.0f, 0.0f));  // v>0: e-1>0 -> max(v,0)=v; v<=0: e-1 in (-1,0] and e-1 >= v
 }
 
+constexpr int kClaimRing = 8;   // claimed-but-unfinished items per cluster (dynamic scheduling)
+constexpr int kClaimAhead = 4;  // how far ahead of the last published item the claimer may run
+
 // Work geometry of one CTA for one launch: which items it walks and which 256-row tile of an
 // item is its own. Single mode: item == tile, CTA b takes items b, b+G, ... Pair mode
 // (cta_group::2): item == two adjacent tiles, cluster c takes items c, c+G/2, ...; the CTA with
 // cluster rank r owns tile 2*item + r.
 template <bool kPair>
 struct Walk {
-    int first, step, rank;
-    __device__ __forceinline__ Walk(const TrunkParams& P) {
+    int first, step, rank, end;
+    bool dynamic;
+    const uint32_t* claim_count;  // smem: number of items claimed so far for this cluster
+    const uint32_t* claim_ring;   // smem: [kClaimRing] claimed item indices
+    __device__ __forceinline__ Walk(const TrunkParams& P, const uint32_t* cc, const uint32_t* cr) {
         if (kPair) { rank = (int)cluster_ctarank(); first = P.item_begin + (blockIdx.x >> 1); step = gridDim.x >> 1; }
         else { rank = 0; first = P.item_begin + blockIdx.x; step = gridDim.x; }
+        end = P.item_end;
+        dynamic = P.next_item != nullptr;
+        claim_count = cc; claim_ring = cr;
     }
     __device__ __forceinline__ int tile(int item_in_job) const { return kPair ? 2 * item_in_job + rank : item_in_job; }
+    // k-th item of this CTA, or -1 when there is none. Static: round robin over the launch's item
+    // list. Dynamic: whatever the cluster's claimer (leader scout warp) took from the global
+    // in-order counter — greedy list scheduling, still strictly increasing per cluster.
+    __device__ __forceinline__ int item(uint32_t k) const {
+        if (!dynamic) { const int q = first + (int)k * step; return q < end ? q : -1; }
+        while (ld_acquire_cluster_shared(claim_count) <= k) {}
+        const int q = (int)claim_ring[k % kClaimRing];
+        return q < end ? q : -1;
+    }
 };
 
 template <bool kPair>
@@ -148,6 +167,8 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pfull_bar + kMaxStages);
     volatile uint32_t* pub_done = tmem_slot + 1;   // tiles published so far by this CTA
     uint32_t* deps_ready = tmem_slot + 2;          // items whose dependencies the scout warp has seen satisfied
+    uint32_t* claim_count = tmem_slot + 3;         // dynamic scheduling: items claimed for this cluster
+    uint32_t* claim_ring = tmem_slot + 4;          // [kClaimRing] their indices
     // broadcast reads (one wavefront per warp-wide LDS.128), resident for the whole launch
     float* bias_all = reinterpret_cast<float*>(smem + kTrunkRingBytes + 256);   // [kMaxLaunchJobs][128]
     float* headw_all = bias_all + kMaxLaunchJobs * 128;                         // [2 nets][9][128]
@@ -155,7 +176,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const Walk<kPair> W(P);
+    const Walk<kPair> W(P, claim_count, claim_ring);
     const bool leader = (W.rank == 0);
 
     if (threadIdx.x == 0) {
@@ -166,6 +187,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         for (int i = 0; i < kPubDepth; i++) mbar_init(pub_bar + i, kEpilogueWarps);
         *pub_done = 0;
         *deps_ready = 0;
+        *claim_count = 0;
         fence_mbar_init();
         fence_proxy_async_smem();
         for (int i = 0; i < kMaxTensorMaps; i++) tma_prefetch_desc(&P.tmaps[i]);
@@ -205,7 +227,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         // elected lane issues the copies. In pair mode each CTA loads the A slab of its own tile
         // and its half of the output channels of the B block.
         int stage = 0; uint32_t phase = 0; int j = 0; uint32_t pit = 0;
-        for (int q = W.first; q < P.item_end; q += W.step, pit++) {
+        for (int q; (q = W.item(pit)) >= 0; pit++) {
             while (q >= jobs[j].item_base + jobs[j].n_items) j++;
             const LayerJob& J = jobs[j];
             const int tile = W.tile(q - J.item_base);
@@ -254,8 +276,8 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         // No MMAs are issued here (the leader's tcgen05.mma.cta_group::2 drives both SMs); this
         // warp only tells the leader when each of OUR stages has landed.
         if (lane == 0) {
-            int stage = 0; uint32_t phase = 0; int j = 0;
-            for (int q = W.first; q < P.item_end; q += W.step) {
+            int stage = 0; uint32_t phase = 0; int j = 0; uint32_t fit = 0;
+            for (int q; (q = W.item(fit)) >= 0; fit++) {
                 while (q >= jobs[j].item_base + jobs[j].n_items) j++;
                 const int n_st = jobs[j].n_slabs * n_tap_groups(jobs[j].ksize);
                 for (int s = 0; s < n_st; s++) {
@@ -274,7 +296,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0; int j = 0; uint32_t it = 0;
             bool next_ready = false;  // full_bar[stage] already observed complete for `phase`
-            for (int q = W.first; q < P.item_end; q += W.step, it++) {
+            for (int q; (q = W.item(it)) >= 0; it++) {
                 while (q >= jobs[j].item_base + jobs[j].n_items) j++;
                 const LayerJob& J = jobs[j];
                 const int ksize = J.ksize, n_out = J.n_out, n_slabs = J.n_slabs, halo = J.halo;
@@ -351,7 +373,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         const int quad = warp & 3;        // TMEM lane quadrant this warp may read
         const int half = ew >> 2;         // which half of the output channels
         int j = 0; uint32_t it = 0;
-        for (int q = W.first; q < P.item_end; q += W.step, it++) {
+        for (int q; (q = W.item(it)) >= 0; it++) {
             while (q >= jobs[j].item_base + jobs[j].n_items) j++;
             const LayerJob& J = jobs[j];
             const int tile = W.tile(q - J.item_base);
@@ -474,7 +496,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         // then release its flag for the consumers' acquire (cumulative over the mbarrier sync).
         if (P.use_flags && lane == 0) {
             int j = 0; uint32_t it = 0;
-            for (int q = W.first; q < P.item_end; q += W.step, it++) {
+            for (int q; (q = W.item(it)) >= 0; it++) {
                 while (q >= jobs[j].item_base + jobs[j].n_items) j++;
                 mbar_wait(pub_bar + (it % kPubDepth), (it / kPubDepth) & 1);
                 LB2_TRACE(it, 11);
@@ -491,7 +513,25 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         // progress in shared memory. Takes the L2 round trips of the polling off the load path.
         if (P.use_flags) {
             int j = 0; uint32_t it = 0;
-            for (int q = W.first; q < P.item_end; q += W.step, it++) {
+            for (;; it++) {
+                int q;
+                if (W.dynamic && leader) {
+                    // claim the cluster's next item from the global in-order counter, a few items
+                    // ahead of what has been published, and hand it to every role of both CTAs
+                    if (lane == 0) {
+                        while (it >= *pub_done + kClaimAhead) __nanosleep(20);
+                        q = P.item_begin + (int)atomicAdd(P.next_item, 1u);
+                        claim_ring[it % kClaimRing] = (uint32_t)q;
+                        if (kPair) st_remote_shared(claim_ring + it % kClaimRing, 1, (uint32_t)q);
+                        st_release_cluster_shared(claim_count, it + 1);
+                        if (kPair) st_release_remote_shared(claim_count, 1, it + 1);
+                    }
+                    q = __shfl_sync(0xffffffffu, q, 0);
+                    if (q >= P.item_end) break;
+                } else {
+                    q = W.item(it);
+                    if (q < 0) break;
+                }
                 while (q >= jobs[j].item_base + jobs[j].n_items) j++;
                 const LayerJob& J = jobs[j];
                 if (J.dep_job >= 0) {

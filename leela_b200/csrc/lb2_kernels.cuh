@@ -80,6 +80,7 @@ struct TrunkParams {
     int32_t item_begin, item_end;  // launch-wide item index range handled by this launch
     uint32_t epoch;
     int32_t use_flags;  // 1: cross-CTA dataflow through flags (single persistent launch)
+    uint32_t* next_item;        // dynamic scheduling: global in-order item counter (zero at launch), or null
     unsigned long long* trace;  // optional timeline buffer [cta][kTraceItems][kTraceEvents] of %globaltimer ns
     int32_t debug_flags;  // timing experiments only (results wrong): bit1 = all tap offsets 0, bit2 = no epilogue math,
                           // bit3 = no B loads, bit4 = no A loads, bit5 = only the first M half of 3x3 layers, bit6 = epilogue does nothing
@@ -93,6 +94,7 @@ struct ExpandArgs {
     int32_t n, n_nets;
     const uint8_t* pf;           // optional buffer to pull into L2
     size_t pf_bytes;
+    uint32_t* zero_word;         // optional word to clear (the trunk's dynamic-scheduling counter)
 };
 
 struct HeadArgs {

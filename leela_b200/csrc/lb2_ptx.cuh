@@ -97,6 +97,31 @@ __device__ __forceinline__ uint32_t ld_acquire_cta_shared(const uint32_t* p) {
     return v;
 }
 
+// cluster-scope shared-memory signalling (dynamic scheduling: the leader CTA publishes claimed
+// items into both CTAs' shared memory)
+__device__ __forceinline__ uint32_t ld_acquire_cluster_shared(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.cluster.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_cluster_shared(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.cluster.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_remote_shared(uint32_t* p, uint32_t cta, uint32_t v) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "st.shared::cluster.u32 [ra], %2;\n\t}\n" ::"r"(smem_u32(p)), "r"(cta), "r"(v)
+        : "memory");
+}
+__device__ __forceinline__ void st_release_remote_shared(uint32_t* p, uint32_t cta, uint32_t v) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "st.release.cluster.shared::cluster.u32 [ra], %2;\n\t}\n" ::"r"(smem_u32(p)), "r"(cta), "r"(v)
+        : "memory");
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
