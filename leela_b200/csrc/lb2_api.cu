@@ -433,6 +433,22 @@ int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers
             for (int i = 0; i < 3; i++) P.tmaps[pl.tmap_base[k] + i] = d->net[1 - k].tm_x0;
     P.jobs = d->jobs_dev;
     P.n_jobs = (int)pl.jobs.size();
+    // rounds: jobs of equal depth, their items interleaved in the launch-wide order
+    P.n_rounds = 0;
+    P.round_base[0] = 0;
+    for (size_t i = 0; i < pl.jobs.size();) {
+        size_t e = i;
+        while (e < pl.jobs.size() && pl.round_of[e] == pl.round_of[i]) e++;
+        if (P.n_rounds >= lb2::kMaxRounds || e - i > 2) return fail(LB2_ERR_UNSUPPORTED, "too many layers");
+        P.round_a[P.n_rounds] = (int16_t)i;
+        P.round_b[P.n_rounds] = e - i == 2 ? (int16_t)(i + 1) : (int16_t)-1;
+        int items = 0;
+        for (size_t k = i; k < e; k++) items += pl.jobs[k].n_items;
+        P.round_base[P.n_rounds + 1] = P.round_base[P.n_rounds] + items;
+        P.n_rounds++;
+        i = e;
+    }
+    for (int r = P.n_rounds + 1; r <= lb2::kMaxRounds; r++) P.round_base[r] = 0x7fffffff;
     P.epoch = ++d->epoch;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (ctx->profile_trunk) {
@@ -452,17 +468,13 @@ int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers
         ctx->launches++;
     } else {
         P.use_flags = 0;
-        size_t i = 0;
-        while (i < pl.jobs.size()) {
-            size_t e = i;
-            while (e < pl.jobs.size() && pl.round_of[e] == pl.round_of[i]) e++;
-            P.item_begin = pl.jobs[i].item_base;
-            P.item_end = pl.jobs[e - 1].item_base + pl.jobs[e - 1].n_items;
+        for (int r = 0; r < P.n_rounds; r++) {
+            P.item_begin = P.round_base[r];
+            P.item_end = P.round_base[r + 1];
             const int items = P.item_end - P.item_begin;
             const int grid = pair ? std::min(d->sm_count & ~1, 2 * items) : std::min(d->sm_count, items);
             CU_TRY(lb2::launch_trunk(P, grid, false, pair, st));
             ctx->launches++;
-            i = e;
         }
     }
     if (ev0) {

@@ -121,6 +121,20 @@ __device__ __forceinline__ float elu_fast(float v) {
     return fmaxf(v, fminf(e - 1.0f, 0.0f));  // v>0: e-1>0 -> max(v,0)=v; v<=0: e-1 in (-1,0] and e-1 >= v
 }
 
+// Item index -> (job, item within the job). Rounds are consecutive in the launch-wide order; inside
+// a round the items of its two jobs (policy layer l, value layer l) alternate, so that at any time
+// every cluster works on a mix of wide/long and narrow/short items instead of the whole GPU
+// switching between the two regimes. `r` is the caller's monotonically advancing round cursor.
+__device__ __forceinline__ void locate_item(const TrunkParams& P, const LayerJob* jobs, int q, int& r, int& job, int& idx) {
+    while (q >= P.round_base[r + 1]) r++;
+    const int local = q - P.round_base[r];
+    const int a = P.round_a[r], b = P.round_b[r];
+    const int na = jobs[a].n_items, nb = b >= 0 ? jobs[b].n_items : 0;
+    const int m = na < nb ? na : nb;
+    if (local < 2 * m) { job = (local & 1) ? b : a; idx = local >> 1; }
+    else { job = na > nb ? a : b; idx = local - m; }
+}
+
 constexpr int kClaimRing = 8;   // claimed-but-unfinished items per cluster (dynamic scheduling)
 constexpr int kClaimAhead = 4;  // how far ahead of the last published item the claimer may run
 
@@ -228,9 +242,10 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         // and its half of the output channels of the B block.
         int stage = 0; uint32_t phase = 0; int j = 0; uint32_t pit = 0;
         for (int q; (q = W.item(pit)) >= 0; pit++) {
-            while (q >= jobs[j].item_base + jobs[j].n_items) j++;
-            const LayerJob& J = jobs[j];
-            const int tile = W.tile(q - J.item_base);
+            int jj, idx;
+            locate_item(P, jobs, q, j, jj, idx);
+            const LayerJob& J = jobs[jj];
+            const int tile = W.tile(idx);
             const int halo = J.halo, ksize = J.ksize, n_out = J.n_out, n_slabs = J.n_slabs, tmap = J.tmap;
             if (lane == 0) { LB2_TRACE(pit, 0); if (P.trace && pit < (uint32_t)kTraceItems) P.trace[((size_t)blockIdx.x * kTraceItems + pit) * kTraceEvents + 15] = (unsigned long long)q; }
             if (P.use_flags) {
@@ -278,8 +293,9 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0; int j = 0; uint32_t fit = 0;
             for (int q; (q = W.item(fit)) >= 0; fit++) {
-                while (q >= jobs[j].item_base + jobs[j].n_items) j++;
-                const int n_st = jobs[j].n_slabs * n_tap_groups(jobs[j].ksize);
+                int jj, idx;
+                locate_item(P, jobs, q, j, jj, idx);
+                const int n_st = jobs[jj].n_slabs * n_tap_groups(jobs[jj].ksize);
                 for (int s = 0; s < n_st; s++) {
                     mbar_wait(full_bar + stage, phase);
                     mbar_arrive_remote(full_bar + stage, 0);
@@ -297,8 +313,9 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             int stage = 0; uint32_t phase = 0; int j = 0; uint32_t it = 0;
             bool next_ready = false;  // full_bar[stage] already observed complete for `phase`
             for (int q; (q = W.item(it)) >= 0; it++) {
-                while (q >= jobs[j].item_base + jobs[j].n_items) j++;
-                const LayerJob& J = jobs[j];
+                int jj, idx;
+                locate_item(P, jobs, q, j, jj, idx);
+                const LayerJob& J = jobs[jj];
                 const int ksize = J.ksize, n_out = J.n_out, n_slabs = J.n_slabs, halo = J.halo;
                 const int S = (P.debug_flags & 2) ? 0 : J.S, DX = (P.debug_flags & 2) ? 0 : 1;
                 const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -374,15 +391,16 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         const int half = ew >> 2;         // which half of the output channels
         int j = 0; uint32_t it = 0;
         for (int q; (q = W.item(it)) >= 0; it++) {
-            while (q >= jobs[j].item_base + jobs[j].n_items) j++;
-            const LayerJob& J = jobs[j];
-            const int tile = W.tile(q - J.item_base);
+            int jj, idx;
+            locate_item(P, jobs, q, j, jj, idx);
+            const LayerJob& J = jobs[jj];
+            const int tile = W.tile(idx);
             const int n_out = J.n_out, chunk_rows = J.out_chunk_rows, n_pos = J.n_pos;
             const bool head = J.head_taps != 0, remap = J.remap != 0, wide = (J.S == 21);
             __half* __restrict__ out = J.out;
             float* __restrict__ zbuf = J.zbuf;
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-            const float* bs = bias_all + j * 128;
+            const float* bs = bias_all + jj * 128;
             const float* headw_s = headw_all + J.net * (9 * 128);
             if (warp == 2 && lane == 0) LB2_TRACE(it, 8);
             mbar_wait(tfull_bar + acc, acc_phase);
@@ -497,11 +515,12 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         if (P.use_flags && lane == 0) {
             int j = 0; uint32_t it = 0;
             for (int q; (q = W.item(it)) >= 0; it++) {
-                while (q >= jobs[j].item_base + jobs[j].n_items) j++;
+                int jj, idx;
+                locate_item(P, jobs, q, j, jj, idx);
                 mbar_wait(pub_bar + (it % kPubDepth), (it / kPubDepth) & 1);
                 LB2_TRACE(it, 11);
                 fence_proxy_async();  // generic-proxy stores -> visible to other CTAs' TMA loads
-                st_release_gpu(jobs[j].flags + W.tile(q - jobs[j].item_base), P.epoch);
+                st_release_gpu(jobs[jj].flags + W.tile(idx), P.epoch);
                 LB2_TRACE(it, 12);
                 *pub_done = it + 1;
             }
@@ -532,11 +551,12 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                     q = W.item(it);
                     if (q < 0) break;
                 }
-                while (q >= jobs[j].item_base + jobs[j].n_items) j++;
-                const LayerJob& J = jobs[j];
+                int jj, idx;
+                locate_item(P, jobs, q, j, jj, idx);
+                const LayerJob& J = jobs[jj];
                 if (J.dep_job >= 0) {
                     int lo, hi;
-                    dependency_range(J, W.tile(q - J.item_base), lo, hi);
+                    dependency_range(J, W.tile(idx), lo, hi);
                     const uint32_t* flags = jobs[J.dep_job].flags;
                     if (lo + lane <= hi)
                         while (ld_acquire_gpu(flags + lo + lane) != P.epoch) __nanosleep(20);

@@ -42,6 +42,7 @@ constexpr int kTrunkSmemBytes = kTrunkRingBytes + 256 + kMaxLaunchJobs * 128 * 4
 constexpr int kMaxLayers = 16;
 constexpr int kMaxTensorMaps = 6;
 constexpr int kMaxJobs = 32;
+constexpr int kMaxRounds = 16;  // a round = the jobs of equal depth (one per net); their items are interleaved
 constexpr int kTraceItems = 96;
 constexpr int kTraceEvents = 16;
 
@@ -78,6 +79,9 @@ struct TrunkParams {
     const LayerJob* jobs;
     int32_t n_jobs;
     int32_t item_begin, item_end;  // launch-wide item index range handled by this launch
+    int32_t n_rounds;
+    int32_t round_base[kMaxRounds + 1];             // first item index of each round
+    int16_t round_a[kMaxRounds], round_b[kMaxRounds];  // its jobs (round_b = -1 if only one)
     uint32_t epoch;
     int32_t use_flags;  // 1: cross-CTA dataflow through flags (single persistent launch)
     uint32_t* next_item;        // dynamic scheduling: global in-order item counter (zero at launch), or null
