@@ -135,7 +135,7 @@ __device__ __forceinline__ void locate_item(const TrunkParams& P, const LayerJob
     else { job = na > nb ? a : b; idx = local - m; }
 }
 
-constexpr int kClaimRing = 8;   // claimed-but-unfinished items per cluster (dynamic scheduling)
+constexpr int kClaimRing = 16;  // claimed-but-unfinished items per cluster (dynamic scheduling)
 constexpr int kClaimAhead = 4;  // how far ahead of the last published item the claimer may run
 
 // Work geometry of one CTA for one launch: which items it walks and which 256-row tile of an
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
     uint32_t* claim_count = tmem_slot + 3;         // dynamic scheduling: items claimed for this cluster
     uint32_t* claim_ring = tmem_slot + 4;          // [kClaimRing] their indices
     // broadcast reads (one wavefront per warp-wide LDS.128), resident for the whole launch
-    float* bias_all = reinterpret_cast<float*>(smem + kTrunkRingBytes + 256);   // [kMaxLaunchJobs][128]
+    float* bias_all = reinterpret_cast<float*>(smem + kTrunkRingBytes + kCtrlBytes);   // [kMaxLaunchJobs][128]
     float* headw_all = bias_all + kMaxLaunchJobs * 128;                         // [2 nets][9][128]
     LayerJob* jobs_s = reinterpret_cast<LayerJob*>(headw_all + 2 * 9 * 128);    // [kMaxLaunchJobs] job table copy
 

@@ -38,7 +38,8 @@ constexpr int kRingBytesSingle = kStagesSingle * kStageBytesSingle;   // 192,512
 constexpr int kRingBytesPair = kStagesPair * kStageBytesPair;         // 178,176
 constexpr int kTrunkRingBytes = kRingBytesSingle > kRingBytesPair ? kRingBytesSingle : kRingBytesPair;
 // ring | mbarriers etc. (256 B) | bias [jobs][128] f32 | fused-head weights [2 nets][9][128] f32 | job table
-constexpr int kTrunkSmemBytes = kTrunkRingBytes + 256 + kMaxLaunchJobs * 128 * 4 + 2 * 9 * 128 * 4 + kMaxLaunchJobs * 160;
+constexpr int kCtrlBytes = 384;  // mbarriers, TMEM slot, progress counters, claim ring
+constexpr int kTrunkSmemBytes = kTrunkRingBytes + kCtrlBytes + kMaxLaunchJobs * 128 * 4 + 2 * 9 * 128 * 4 + kMaxLaunchJobs * 160;
 constexpr int kMaxLayers = 16;
 constexpr int kMaxTensorMaps = 6;
 constexpr int kMaxJobs = 32;
