@@ -27,11 +27,13 @@ def needs_build() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB, csrc: str = CSRC) -> str:
+    """`defines`, `out`, `csrc` exist for tools/ab_variants.py (tuning builds side by side); the product is LIB."""
+    if out == LIB and not force and not needs_build():
         return LIB
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-Xcompiler", "-fPIC", "-shared", "-o", out] + [f"-D{d}" for d in defines] + \
+          [os.path.join(csrc, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     env = dict(os.environ)

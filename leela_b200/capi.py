@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libleela_b200.so")
+# LB2_LIB: tuning builds of the same library (tools/ab_variants.py); the product is the in-tree one
+LIB_PATH = os.environ.get("LB2_LIB") or os.path.join(HERE, "libleela_b200.so")
 
 POLICY, VALUE = 0, 1
 P = 361

@@ -305,7 +305,7 @@ int ensure_workspace(NetDev* nd, int kind, int cap) {
     CU_TRY(cudaMemset(nd->act[1], 0, act_bytes));
     const size_t out_elems = kind == LB2_POLICY ? (size_t)cap * lb2::kPoints : (size_t)cap;
     CU_TRY(cudaMalloc(&nd->out, out_elems * sizeof(float)));
-    CU_TRY(cudaMalloc(&nd->zbuf, (size_t)18 * nd->rows3 * sizeof(float)));
+    CU_TRY(cudaMalloc(&nd->zbuf, (size_t)9 * lb2::kColParts * nd->rows3 * sizeof(float)));
     nd->flags_stride = nd->rows5 / lb2::kTileRows + 2;
     CU_TRY(cudaMalloc(&nd->flags, (size_t)lb2::kMaxJobs * nd->flags_stride * sizeof(uint32_t)));
     CU_TRY(cudaMemset(nd->flags, 0, (size_t)lb2::kMaxJobs * nd->flags_stride * sizeof(uint32_t)));

@@ -135,37 +135,57 @@ __device__ __forceinline__ void locate_item(const TrunkParams& P, const LayerJob
     else { job = na > nb ? a : b; idx = local - m; }
 }
 
-constexpr int kClaimRing = 16;  // claimed-but-unfinished items per cluster (dynamic scheduling)
-constexpr int kClaimAhead = 4;  // how far ahead of the last published item the claimer may run
+// tuning knobs (tools/ab_variants.py builds variants side by side)
+#ifndef LB2_PROBE_TAP
+#define LB2_PROBE_TAP 4   // tap after which the MMA issuer probes the next stage; < 0: before the stage's MMAs
+#endif
+#ifndef LB2_RING_SLEEP
+#define LB2_RING_SLEEP 64 // ns between polls of the work-item ring by the scout / publisher / stage forwarder
+#endif
+#ifndef LB2_EPI_GROUP
+#define LB2_EPI_GROUP 2   // 8-column TMEM loads the epilogue issues back to back
+#endif
+constexpr int kEpiGroup = LB2_EPI_GROUP;
+#ifndef LB2_EPI_PIPE
+#define LB2_EPI_PIPE 1    // epilogue keeps the TMEM loads of the next two units in flight
+#endif
+constexpr int kClaimRing = 16;  // work-item ring entries per CTA (claimed-but-unpublished items)
+constexpr int kClaimAhead = 4;  // how far ahead of the last published item the scout may hand out items
+constexpr uint32_t kEndJob = 31;  // job field of the ring entry that ends a CTA's walk
 
-// Work geometry of one CTA for one launch: which items it walks and which 256-row tile of an
-// item is its own. Single mode: item == tile, CTA b takes items b, b+G, ... Pair mode
-// (cta_group::2): item == two adjacent tiles, cluster c takes items c, c+G/2, ...; the CTA with
-// cluster rank r owns tile 2*item + r.
-template <bool kPair>
-struct Walk {
-    int first, step, rank, end;
-    bool dynamic;
-    const uint32_t* claim_count;  // smem: number of items claimed so far for this cluster
-    const uint32_t* claim_ring;   // smem: [kClaimRing] claimed item indices
-    __device__ __forceinline__ Walk(const TrunkParams& P, const uint32_t* cc, const uint32_t* cr) {
-        if (kPair) { rank = (int)cluster_ctarank(); first = P.item_begin + (blockIdx.x >> 1); step = gridDim.x >> 1; }
-        else { rank = 0; first = P.item_begin + blockIdx.x; step = gridDim.x; }
-        end = P.item_end;
-        dynamic = P.next_item != nullptr;
-        claim_count = cc; claim_ring = cr;
-    }
-    __device__ __forceinline__ int tile(int item_in_job) const { return kPair ? 2 * item_in_job + rank : item_in_job; }
-    // k-th item of this CTA, or -1 when there is none. Static: round robin over the launch's item
-    // list. Dynamic: whatever the cluster's claimer (leader scout warp) took from the global
-    // in-order counter — greedy list scheduling, still strictly increasing per cluster.
-    __device__ __forceinline__ int item(uint32_t k) const {
-        if (!dynamic) { const int q = first + (int)k * step; return q < end ? q : -1; }
-        while (ld_acquire_cluster_shared(claim_count) <= k) {}
-        const int q = (int)claim_ring[k % kClaimRing];
-        return q < end ? q : -1;
-    }
-};
+// Work-item ring. The scout warp of the cluster leader decides which item the cluster processes
+// k-th (static: round robin over the launch's item list; dynamic: the next one of a global in-order
+// counter — greedy list scheduling, still strictly increasing per cluster), resolves it to
+// (job, index within the job) ONCE and writes a 32-bit entry [tag:6 | job:5 | index:21] into the
+// ring of every CTA of the cluster. All other roles just read entry k: one shared-memory load,
+// no search through the round table, no acquire fence (tag and payload share the word).
+__device__ __forceinline__ uint32_t item_tag(uint32_t k) { return ((k / kClaimRing) & 31u) + 1u; }
+__device__ __forceinline__ uint32_t item_pack(uint32_t k, uint32_t job, uint32_t idx) {
+    return (item_tag(k) << 26) | (job << 21) | idx;
+}
+__device__ __forceinline__ bool item_peek(const uint32_t* ring, uint32_t k, uint32_t& v) {
+    v = ld_volatile_shared(ring + k % kClaimRing);
+    return (v >> 26) == item_tag(k);
+}
+// blocking read of entry k; false at the end marker. `relaxed`: roles off the critical path back off
+// between polls so their spinning stays off the shared-memory port the tensor core reads through.
+template <bool relaxed = false>
+__device__ __forceinline__ bool item_get(const uint32_t* ring, uint32_t k, int& job, int& idx) {
+    uint32_t v;
+    while (!item_peek(ring, k, v)) { if (relaxed && LB2_RING_SLEEP) __nanosleep(LB2_RING_SLEEP); }
+    job = (int)((v >> 21) & 31u);
+    idx = (int)(v & 0x1fffffu);
+    return job != (int)kEndJob;
+}
+
+// The MMA issuer's own ring: everything it needs to know about item k in one word
+// [tag:6 | end:1 | 5x5:1 | halo/8:4 | c_in/16:6 | c_out/8:6 | S:8], so that a single shared-memory
+// load separates the last MMA of one item from the first of the next.
+__device__ __forceinline__ uint32_t geom_pack(uint32_t k, const LayerJob* J) {
+    if (!J) return (item_tag(k) << 26) | (1u << 25);
+    return (item_tag(k) << 26) | ((J->ksize == 5 ? 1u : 0u) << 24) | ((uint32_t)(J->halo >> 3) << 20) |
+           ((uint32_t)J->n_slabs << 14) | ((uint32_t)(J->n_out >> 3) << 8) | (uint32_t)J->S;
+}
 
 template <bool kPair>
 __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_constant__ TrunkParams P) {
@@ -181,8 +201,8 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pfull_bar + kMaxStages);
     volatile uint32_t* pub_done = tmem_slot + 1;   // tiles published so far by this CTA
     uint32_t* deps_ready = tmem_slot + 2;          // items whose dependencies the scout warp has seen satisfied
-    uint32_t* claim_count = tmem_slot + 3;         // dynamic scheduling: items claimed for this cluster
-    uint32_t* claim_ring = tmem_slot + 4;          // [kClaimRing] their indices
+    uint32_t* item_ring = tmem_slot + 4;           // [kClaimRing] work-item entries (see item_pack)
+    uint32_t* geom_ring = item_ring + kClaimRing;  // [kClaimRing] the MMA issuer's view of them (see geom_pack)
     // broadcast reads (one wavefront per warp-wide LDS.128), resident for the whole launch
     float* bias_all = reinterpret_cast<float*>(smem + kTrunkRingBytes + kCtrlBytes);   // [kMaxLaunchJobs][128]
     float* headw_all = bias_all + kMaxLaunchJobs * 128;                         // [2 nets][9][128]
@@ -190,8 +210,11 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const Walk<kPair> W(P, claim_count, claim_ring);
-    const bool leader = (W.rank == 0);
+    // Pair mode (cta_group::2): an item is two adjacent 256-row tiles; the CTA with cluster rank r
+    // owns tile 2*item + r. Single mode: item == tile.
+    const int rank = kPair ? (int)cluster_ctarank() : 0;
+    const bool leader = (rank == 0);
+    auto tile_of = [&](int idx) { return kPair ? 2 * idx + rank : idx; };
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 127u) __trap();  // TMA destinations need 128-byte alignment
@@ -201,7 +224,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         for (int i = 0; i < kPubDepth; i++) mbar_init(pub_bar + i, kEpilogueWarps);
         *pub_done = 0;
         *deps_ready = 0;
-        *claim_count = 0;
+        for (int i = 0; i < 2 * kClaimRing; i++) item_ring[i] = 0;
         fence_mbar_init();
         fence_proxy_async_smem();
         for (int i = 0; i < kMaxTensorMaps; i++) tma_prefetch_desc(&P.tmaps[i]);
@@ -226,7 +249,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (kPair) cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
+    if (kPair) cluster_sync_all();  // the peer's barriers and ring are initialised before anyone signals them
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     jobs = jobs_s;  // from here on every role reads the shared-memory copy
@@ -237,22 +260,17 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        // The whole warp walks the item list; lanes poll the dependency flags in parallel, one
-        // elected lane issues the copies. In pair mode each CTA loads the A slab of its own tile
-        // and its half of the output channels of the B block.
-        int stage = 0; uint32_t phase = 0; int j = 0; uint32_t pit = 0;
-        for (int q; (q = W.item(pit)) >= 0; pit++) {
-            int jj, idx;
-            locate_item(P, jobs, q, j, jj, idx);
+        // The whole warp walks the item ring; one elected lane issues the copies. In pair mode each
+        // CTA loads the A slab of its own tile and its half of the output channels of the B block.
+        int stage = 0; uint32_t phase = 0; uint32_t pit = 0;
+        for (int jj, idx; item_get(item_ring, pit, jj, idx); pit++) {
             const LayerJob& J = jobs[jj];
-            const int tile = W.tile(idx);
+            const int tile = tile_of(idx);
             const int halo = J.halo, ksize = J.ksize, n_out = J.n_out, n_slabs = J.n_slabs, tmap = J.tmap;
-            if (lane == 0) { LB2_TRACE(pit, 0); if (P.trace && pit < (uint32_t)kTraceItems) P.trace[((size_t)blockIdx.x * kTraceItems + pit) * kTraceEvents + 15] = (unsigned long long)q; }
-            if (P.use_flags) {
-                // the scout warp polls the dependency flags ahead of us; wait for its go-ahead
-                while (ld_acquire_cta_shared(deps_ready) <= pit) {}
-                __syncwarp();
-            }
+            if (lane == 0) { LB2_TRACE(pit, 0); if (P.trace && pit < (uint32_t)kTraceItems) P.trace[((size_t)blockIdx.x * kTraceItems + pit) * kTraceEvents + 15] = (unsigned long long)((jj << 21) | idx); }
+            // the scout warp polls the dependency flags ahead of us; wait for its go-ahead
+            while (ld_acquire_cta_shared(deps_ready) <= pit) {}
+            __syncwarp();
             const int rows_halo = kTileRows + 2 * halo;
             const uint32_t a_bytes = rows_halo * 32;
             const int row0_8 = (tile * kTileRows - halo) / 8;  // exact: both multiples of 8
@@ -271,7 +289,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                         const bool skip_b = (P.debug_flags & 8) != 0, skip_a = (P.debug_flags & 16) != 0;
                         mbar_arrive_expect_tx(full_bar + st, (skip_a ? 0u : a_bytes) + (skip_b ? 0u : b_bytes));
                         if (!skip_a) tma_load_3d(sa, &P.tmaps[tmap], full_bar + st, 0, row0_8, 2 * s);
-                        if (!skip_b) bulk_load_1d(sa + kASlabBytes, wsrc + (kPair ? W.rank * b_bytes : 0u), b_bytes, full_bar + st);
+                        if (!skip_b) bulk_load_1d(sa + kASlabBytes, wsrc + (kPair ? rank * b_bytes : 0u), b_bytes, full_bar + st);
                         wsrc += kPair ? 2 * b_bytes : b_bytes;
                         if (++st == kStages) { st = 0; ph ^= 1; }
                         if (s == 0 && g == 0) LB2_TRACE(pit, 2);
@@ -291,10 +309,8 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         // No MMAs are issued here (the leader's tcgen05.mma.cta_group::2 drives both SMs); this
         // warp only tells the leader when each of OUR stages has landed.
         if (lane == 0) {
-            int stage = 0; uint32_t phase = 0; int j = 0; uint32_t fit = 0;
-            for (int q; (q = W.item(fit)) >= 0; fit++) {
-                int jj, idx;
-                locate_item(P, jobs, q, j, jj, idx);
+            int stage = 0; uint32_t phase = 0; uint32_t fit = 0;
+            for (int jj, idx; item_get<true>(item_ring, fit, jj, idx); fit++) {
                 const int n_st = jobs[jj].n_slabs * n_tap_groups(jobs[jj].ksize);
                 for (int s = 0; s < n_st; s++) {
                     mbar_wait(full_bar + stage, phase);
@@ -306,18 +322,20 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
         // One elected lane runs the whole pipeline. The tensor pipe only queues a few MMAs, so the
-        // time between the last MMA of one stage and the first of the next must stay short: the
-        // readiness of the NEXT stage is probed (non-blocking) before this stage's MMAs are issued,
-        // so its latency is hidden behind them.
+        // time between the last MMA of one stage (or item) and the first of the next must stay
+        // short: the geometry of the NEXT item is fetched while this item's MMAs are in flight,
+        // and the readiness of the NEXT stage is probed (non-blocking) in the middle of this
+        // stage's MMAs, so both latencies hide behind queued tensor work.
         if (elect_one()) {
-            int stage = 0; uint32_t phase = 0; int j = 0; uint32_t it = 0;
+            int stage = 0; uint32_t phase = 0; uint32_t it = 0;
             bool next_ready = false;  // full_bar[stage] already observed complete for `phase`
-            for (int q; (q = W.item(it)) >= 0; it++) {
-                int jj, idx;
-                locate_item(P, jobs, q, j, jj, idx);
-                const LayerJob& J = jobs[jj];
-                const int ksize = J.ksize, n_out = J.n_out, n_slabs = J.n_slabs, halo = J.halo;
-                const int S = (P.debug_flags & 2) ? 0 : J.S, DX = (P.debug_flags & 2) ? 0 : 1;
+            for (;; it++) {
+                uint32_t gw;
+                while (!item_peek(geom_ring, it, gw)) {}
+                if (gw & (1u << 25)) break;
+                const int ksize = (gw & (1u << 24)) ? 5 : 3, halo = (int)((gw >> 20) & 15u) << 3;
+                const int n_slabs = (int)((gw >> 14) & 63u), n_out = (int)((gw >> 8) & 63u) << 3;
+                const int S = (P.debug_flags & 2) ? 0 : (int)(gw & 255u), DX = (P.debug_flags & 2) ? 0 : 1;
                 const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
                 LB2_TRACE(it, 4);
                 mbar_wait(tempty_bar + acc, acc_phase ^ 1);
@@ -341,10 +359,9 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                     if (!next_ready) mbar_wait(full_bar + stage, phase);
                     tc_fence_after_sync();
                     if (s == 0) LB2_TRACE(it, 6);
-                    // probe the following stage now; the answer is consumed after this stage's MMAs
                     int nstage = stage + 1; uint32_t nphase = phase;
                     if (nstage == kStages) { nstage = 0; nphase ^= 1; }
-                    next_ready = mbar_try_wait(full_bar + nstage, nphase);
+                    if (LB2_PROBE_TAP < 0) next_ready = mbar_try_wait(full_bar + nstage, nphase);
                     const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
                     // (address of row `halo` of the A slab) >> 4; a tap shifts it by dy*S+dx rows
                     const uint32_t a16 = (a_addr >> 4) + halo;
@@ -360,6 +377,8 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                                 umma_f16<kPair>(d1, desc_hi | (a_lo_base | ((a0 + 128) & 0x3FFFu)), bdesc, idesc, accumulate);
                             accumulate = 1;
                             b16 += b_step;
+                            // probe the following stage while the tensor pipe has work queued
+                            if (t == LB2_PROBE_TAP) next_ready = mbar_test_wait(full_bar + nstage, nphase);
                         }
                     } else {
                         const int t0 = tap_group_begin(g), t1 = tap_group_end(ksize, g);
@@ -373,6 +392,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                             accumulate = 1;
                             b16 += b_step;
                             if (++kc == 5) { kc = 0; kr++; }
+                            if (t == t0 + LB2_PROBE_TAP) next_ready = mbar_test_wait(full_bar + nstage, nphase);
                         }
                         if (++g == ng) g = 0;
                     }
@@ -386,15 +406,18 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         __syncwarp();
     } else if (warp < 2 + kEpilogueWarps) {
         // ================================ epilogue ====================================
-        const int ew = warp - 2;          // 0..7
+        // Warp w drains TMEM lane quadrant w%4 (32 rows per 128-row half tile) and one part of the
+        // output channels, 8 columns (one 16-byte chunk row) at a time: bias + ELU, then either the
+        // fp16 store or the fused head's partial dot products. kEpiGroup TMEM loads are issued back
+        // to back; with LB2_EPI_PIPE the next group's loads are in flight while this one is processed.
+        const int ew = warp - 2;
         const int quad = warp & 3;        // TMEM lane quadrant this warp may read
-        const int half = ew >> 2;         // which half of the output channels
-        int j = 0; uint32_t it = 0;
-        for (int q; (q = W.item(it)) >= 0; it++) {
-            int jj, idx;
-            locate_item(P, jobs, q, j, jj, idx);
+        const int part = ew >> 2;         // which part of the output channels
+        constexpr int G = kEpiGroup;
+        uint32_t it = 0;
+        for (int jj, idx; item_get(item_ring, it, jj, idx); it++) {
             const LayerJob& J = jobs[jj];
-            const int tile = W.tile(idx);
+            const int tile = tile_of(idx);
             const int n_out = J.n_out, chunk_rows = J.out_chunk_rows, n_pos = J.n_pos;
             const bool head = J.head_taps != 0, remap = J.remap != 0, wide = (J.S == 21);
             __half* __restrict__ out = J.out;
@@ -402,94 +425,125 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             const float* bs = bias_all + jj * 128;
             const float* headw_s = headw_all + J.net * (9 * 128);
-            if (warp == 2 && lane == 0) LB2_TRACE(it, 8);
-            mbar_wait(tfull_bar + acc, acc_phase);
-            tc_fence_after_sync();
-            if (warp == 2 && lane == 0) LB2_TRACE(it, 9);
-            const int cols = n_out >> 1;          // columns handled by this warp
-            const int col0 = half * cols;
-#pragma unroll 1
-            for (int h = 0; h < ((P.debug_flags & 64) ? 0 : 2); h++) {
+            const int cols = n_out / kColParts;   // columns handled by this warp
+            const int col0 = part * cols;
+            const int upc = cols >> 3;            // 8-column units per 128-row half tile
+            const int n_units = (P.debug_flags & 64) ? 0 : 2 * upc;
+            // this thread's row in each of the two half tiles
+            int out_row2[2]; bool valid2[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
                 const int row = tile * kTileRows + h * 128 + quad * 32 + lane;
                 int pos, y, x;
                 if (wide) { pos = row / 441; const int rem = row - pos * 441; y = rem / 21; x = rem - y * 21; }
                 else      { pos = row / 400; const int rem = row - pos * 400; y = rem / 20; x = rem - y * 20; }
-                const bool valid = (x < kBoard) && (y < kBoard);
-                int out_row = row;
-                bool store = !head;
-                if (remap) { out_row = pos * 400 + y * 20 + x; store = valid && pos < n_pos; }
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (acc * 2 + h) * 128 + col0;
-                float z[9];
-#pragma unroll
-                for (int t = 0; t < 9; t++) z[t] = 0.0f;
+                valid2[h] = (x < kBoard) && (y < kBoard) && (!remap || pos < n_pos);
+                out_row2[h] = remap ? pos * 400 + y * 20 + x : row;
+            }
+            const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256 + col0;
+            auto unit_addr = [&](int u) { const int h = u >= upc ? 1 : 0; return tbase + h * 128 + (u - h * upc) * 8; };
 
-                // bias + ELU on 16 accumulator columns, then either the fused head's partial dot
-                // products or the fp16 store of two 8-channel chunks
-                auto finish16 = [&](const uint32_t (&r)[16], int cc) {
-                    float v[16];
-                    const float* bp = bs + col0 + cc;
+            // bias + ELU of one unit
+            auto activate = [&](const uint32_t (&r)[8], int cc, float (&v)[8]) {
+                const float* bp = bs + col0 + cc;
+                const float4 b0 = *reinterpret_cast<const float4*>(bp), b1 = *reinterpret_cast<const float4*>(bp + 4);
+                v[0] = __uint_as_float(r[0]) + b0.x; v[1] = __uint_as_float(r[1]) + b0.y;
+                v[2] = __uint_as_float(r[2]) + b0.z; v[3] = __uint_as_float(r[3]) + b0.w;
+                v[4] = __uint_as_float(r[4]) + b1.x; v[5] = __uint_as_float(r[5]) + b1.y;
+                v[6] = __uint_as_float(r[6]) + b1.z; v[7] = __uint_as_float(r[7]) + b1.w;
+                if (!(P.debug_flags & 4)) {
 #pragma unroll
-                    for (int e = 0; e < 16; e += 4) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(bp + e);
-                        v[e + 0] = __uint_as_float(r[e + 0]) + b4.x;
-                        v[e + 1] = __uint_as_float(r[e + 1]) + b4.y;
-                        v[e + 2] = __uint_as_float(r[e + 2]) + b4.z;
-                        v[e + 3] = __uint_as_float(r[e + 3]) + b4.w;
-                    }
-                    if (!(P.debug_flags & 4)) {
+                    for (int e = 0; e < 8; e++) v[e] = elu_fast(v[e]);
+                }
+            };
+            // ordinary layer: pack to fp16 and store one 16-byte chunk row. Padding rows/columns of
+            // the row space are written as zeros (whole sectors: partial-sector writes cost L2 fills);
+            // layer 1 re-addresses S=21 rows into the S=20 space and must skip them instead.
+            auto store_unit = [&](const uint32_t (&r)[8], int u) {
+                const int h = u >= upc ? 1 : 0;
+                const int cc = (u - h * upc) * 8;
+                const bool valid = h ? valid2[1] : valid2[0];
+                const int out_row = h ? out_row2[1] : out_row2[0];
+                float v[8];
+                activate(r, cc, v);
+                if (valid || !remap) {
+                    uint32_t pk[4];
 #pragma unroll
-                        for (int e = 0; e < 16; e++) v[e] = elu_fast(v[e]);
+                    for (int e = 0; e < 4; e++) {
+                        __half2 hh = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                        pk[e] = valid ? *reinterpret_cast<uint32_t*>(&hh) : 0u;
                     }
-                    if (head) {
-                        // fused 1-channel 3x3 head: z[t] += sum_c w[t][c] * v[c]  (fp32, unrounded v)
+                    const int c8 = (col0 + cc) >> 3;
+                    *reinterpret_cast<uint4*>(out + ((size_t)c8 * chunk_rows + out_row) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+            };
+
+            if (warp == 2 && lane == 0) LB2_TRACE(it, 8);
+            mbar_wait(tfull_bar + acc, acc_phase);
+            tc_fence_after_sync();
+            if (warp == 2 && lane == 0) LB2_TRACE(it, 9);
+            if (head) {
+                // last trunk layer: the net's final 3x3 conv to ONE channel is folded in here as nine
+                // per-tap dot products over this warp's channels, z[t] += sum_c w[t][c] * v[c] (fp32,
+                // unrounded v); the heads kernel gathers them. zbuf[part][t][row]; padding rows give 0.
+#pragma unroll 1
+                for (int h = 0; h < 2 && n_units; h++) {
+                    float z[9];
+#pragma unroll
+                    for (int t = 0; t < 9; t++) z[t] = 0.0f;
+#pragma unroll 1
+                    for (int k = 0; k < upc; k++) {
+                        uint32_t r[8]; float v[8];
+                        tmem_ld_32x8(unit_addr(h * upc + k), r);
+                        tmem_ld_wait();
+                        activate(r, k * 8, v);
 #pragma unroll
                         for (int t = 0; t < 9; t++) {
-                            const float* wt = headw_s + t * 128 + col0 + cc;
-#pragma unroll
-                            for (int e = 0; e < 16; e += 4) {
-                                const float4 w4 = *reinterpret_cast<const float4*>(wt + e);
-                                z[t] = fmaf(v[e + 0], w4.x, z[t]);
-                                z[t] = fmaf(v[e + 1], w4.y, z[t]);
-                                z[t] = fmaf(v[e + 2], w4.z, z[t]);
-                                z[t] = fmaf(v[e + 3], w4.w, z[t]);
-                            }
+                            const float* wt = headw_s + t * 128 + col0 + k * 8;
+                            const float4 w0 = *reinterpret_cast<const float4*>(wt), w1 = *reinterpret_cast<const float4*>(wt + 4);
+                            z[t] = fmaf(v[0], w0.x, z[t]); z[t] = fmaf(v[1], w0.y, z[t]);
+                            z[t] = fmaf(v[2], w0.z, z[t]); z[t] = fmaf(v[3], w0.w, z[t]);
+                            z[t] = fmaf(v[4], w1.x, z[t]); z[t] = fmaf(v[5], w1.y, z[t]);
+                            z[t] = fmaf(v[6], w1.z, z[t]); z[t] = fmaf(v[7], w1.w, z[t]);
                         }
-                    } else if (store) {
-                        uint32_t pk[8];
-#pragma unroll
-                        for (int e = 0; e < 8; e++) {
-                            __half2 hh = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-                            pk[e] = valid ? *reinterpret_cast<uint32_t*>(&hh) : 0u;
-                        }
-                        const int c8 = (col0 + cc) >> 3;
-                        __half* o = out + ((size_t)c8 * chunk_rows + out_row) * 8;
-                        *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        *reinterpret_cast<uint4*>(o + (size_t)chunk_rows * 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                     }
-                };
-
-                int cc = 0;
-#pragma unroll 1
-                for (; cc + 32 <= cols; cc += 32) {   // two TMEM loads in flight
-                    uint32_t r0[16], r1[16];
-                    tmem_ld_32x16(taddr + cc, r0);
-                    tmem_ld_32x16(taddr + cc + 16, r1);
-                    tmem_ld_wait();
-                    finish16(r0, cc);
-                    finish16(r1, cc + 16);
-                }
-                if (cc < cols) {
-                    uint32_t r0[16];
-                    tmem_ld_32x16(taddr + cc, r0);
-                    tmem_ld_wait();
-                    finish16(r0, cc);
-                }
-                if (head) {
-                    // partial sums of this channel half: zbuf[half][t][row]; padding rows contribute 0
-                    float* zb = zbuf + (size_t)half * 9 * chunk_rows + out_row;
+                    float* zb = zbuf + (size_t)part * 9 * chunk_rows + out_row2[h];
 #pragma unroll
-                    for (int t = 0; t < 9; t++) zb[(size_t)t * chunk_rows] = valid ? z[t] : 0.0f;
+                    for (int t = 0; t < 9; t++) zb[(size_t)t * chunk_rows] = valid2[h] ? z[t] : 0.0f;
                 }
+            } else if (n_units) {
+                auto load_group = [&](int u, uint32_t (&r)[G][8]) {
+#pragma unroll
+                    for (int g = 0; g < G; g++)
+                        if (u + g < n_units) tmem_ld_32x8(unit_addr(u + g), r[g]);
+                };
+                auto store_group = [&](int u, const uint32_t (&r)[G][8]) {
+#pragma unroll
+                    for (int g = 0; g < G; g++)
+                        if (u + g < n_units) store_unit(r[g], u + g);
+                };
+#if LB2_EPI_PIPE
+                uint32_t ra[G][8], rb[G][8];
+                load_group(0, ra);
+                tmem_ld_wait();
+#pragma unroll 1
+                for (int u = 0; u < n_units; u += 2 * G) {
+                    load_group(u + G, rb);
+                    store_group(u, ra);
+                    tmem_ld_wait();
+                    load_group(u + 2 * G, ra);
+                    store_group(u + G, rb);
+                    tmem_ld_wait();
+                }
+#else
+#pragma unroll 1
+                for (int u = 0; u < n_units; u += G) {
+                    uint32_t ra[G][8];
+                    load_group(u, ra);
+                    tmem_ld_wait();
+                    store_group(u, ra);
+                }
+#endif
             }
             // accumulator drained: hand it back to the MMA warp (of the leader CTA in pair mode)
             tc_fence_before_sync();
@@ -499,71 +553,71 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                 else mbar_arrive(tempty_bar + acc);
             }
             if (warp == 2 && lane == 0) LB2_TRACE(it, 10);
-            if (P.use_flags) {
-                // hand the tile to the publisher warp: this warp's stores happen-before its arrive
-                if (lane == 0) {
-                    while (it >= *pub_done + kPubDepth) __nanosleep(32);  // ring slot free? (normally yes)
-                    mbar_arrive(pub_bar + (it % kPubDepth));
-                }
+            // hand the tile to the publisher warp: this warp's stores happen-before its arrive
+            if (lane == 0) {
+                while (it >= *pub_done + kPubDepth) __nanosleep(32);  // ring slot free? (normally yes)
+                mbar_arrive(pub_bar + (it % kPubDepth));
             }
         }
-    } else if (warp == 10) {
+    } else if (warp == 2 + kEpilogueWarps) {
         // ================================ tile publisher ==============================
         // Keeps the gpu-scope release (which waits for the tile's stores to land in L2) off the
         // epilogue's critical path. One lane: wait until all 8 epilogue warps stored tile `it`,
         // then release its flag for the consumers' acquire (cumulative over the mbarrier sync).
-        if (P.use_flags && lane == 0) {
-            int j = 0; uint32_t it = 0;
-            for (int q; (q = W.item(it)) >= 0; it++) {
-                int jj, idx;
-                locate_item(P, jobs, q, j, jj, idx);
+        // Its progress counter also bounds how far ahead the scout hands out items.
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int jj, idx; item_get<true>(item_ring, it, jj, idx); it++) {
                 mbar_wait(pub_bar + (it % kPubDepth), (it / kPubDepth) & 1);
                 LB2_TRACE(it, 11);
-                fence_proxy_async();  // generic-proxy stores -> visible to other CTAs' TMA loads
-                st_release_gpu(jobs[jj].flags + W.tile(idx), P.epoch);
+                if (P.use_flags) {
+                    fence_proxy_async();  // generic-proxy stores -> visible to other CTAs' TMA loads
+                    st_release_gpu(jobs[jj].flags + tile_of(idx), P.epoch);
+                }
                 LB2_TRACE(it, 12);
                 *pub_done = it + 1;
             }
         }
-    } else if (warp == 11) {
-        // ================================ dependency scout ============================
-        // Runs ahead of the producer: polls (acquire, gpu scope) the <= 3 tile flags of the previous
-        // layer that each upcoming item of this CTA needs, lanes in parallel, and publishes its
-        // progress in shared memory. Takes the L2 round trips of the polling off the load path.
-        if (P.use_flags) {
-            int j = 0; uint32_t it = 0;
-            for (;; it++) {
-                int q;
-                if (W.dynamic && leader) {
-                    // claim the cluster's next item from the global in-order counter, a few items
-                    // ahead of what has been published, and hand it to every role of both CTAs
-                    if (lane == 0) {
-                        while (it >= *pub_done + kClaimAhead) __nanosleep(20);
-                        q = P.item_begin + (int)atomicAdd(P.next_item, 1u);
-                        claim_ring[it % kClaimRing] = (uint32_t)q;
-                        if (kPair) st_remote_shared(claim_ring + it % kClaimRing, 1, (uint32_t)q);
-                        st_release_cluster_shared(claim_count, it + 1);
-                        if (kPair) st_release_remote_shared(claim_count, 1, it + 1);
-                    }
-                    q = __shfl_sync(0xffffffffu, q, 0);
-                    if (q >= P.item_end) break;
-                } else {
-                    q = W.item(it);
-                    if (q < 0) break;
+    } else if (warp == 3 + kEpilogueWarps) {
+        // ================================ scout ========================================
+        // Leader: hands out the cluster's items (see item_pack) a few items ahead of what has been
+        // published. Every CTA: polls (acquire, gpu scope, lanes in parallel) the <= 3 tile flags of
+        // the previous layer that cover an item's rows +- halo ahead of the producer and publishes
+        // its progress in shared memory — the L2 round trips of the polling stay off the load path.
+        const bool dynamic = P.next_item != nullptr;
+        const int first = P.item_begin + (kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x);
+        const int step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+        int j = 0;
+        for (uint32_t it = 0;; it++) {
+            int jj = (int)kEndJob, idx = 0;
+            if (leader) {
+                int q = 0;
+                if (lane == 0) {
+                    while (it >= *pub_done + kClaimAhead) __nanosleep(20);
+                    q = dynamic ? P.item_begin + (int)atomicAdd(P.next_item, 1u) : first + (int)it * step;
                 }
-                int jj, idx;
-                locate_item(P, jobs, q, j, jj, idx);
-                const LayerJob& J = jobs[jj];
-                if (J.dep_job >= 0) {
-                    int lo, hi;
-                    dependency_range(J, W.tile(idx), lo, hi);
-                    const uint32_t* flags = jobs[J.dep_job].flags;
-                    if (lo + lane <= hi)
-                        while (ld_acquire_gpu(flags + lo + lane) != P.epoch) __nanosleep(20);
+                q = __shfl_sync(0xffffffffu, q, 0);
+                if (q < P.item_end) locate_item(P, jobs, q, j, jj, idx);
+                if (lane == 0) {
+                    st_volatile_shared(geom_ring + it % kClaimRing, geom_pack(it, jj == (int)kEndJob ? nullptr : &jobs[jj]));
+                    const uint32_t e = item_pack(it, (uint32_t)jj, (uint32_t)idx);
+                    if (kPair) st_remote_shared(item_ring + it % kClaimRing, 1, e);
+                    st_volatile_shared(item_ring + it % kClaimRing, e);
                 }
-                __syncwarp();
-                if (lane == 0) st_release_cta_shared(deps_ready, it + 1);
+            } else {
+                item_get<true>(item_ring, it, jj, idx);
             }
+            if (jj == (int)kEndJob) break;
+            const LayerJob& J = jobs[jj];
+            if (P.use_flags && J.dep_job >= 0) {
+                int lo, hi;
+                dependency_range(J, tile_of(idx), lo, hi);
+                const uint32_t* flags = jobs[J.dep_job].flags;
+                if (lo + lane <= hi)
+                    while (ld_acquire_gpu(flags + lo + lane) != P.epoch) __nanosleep(20);
+            }
+            __syncwarp();
+            if (lane == 0) st_release_cta_shared(deps_ready, it + 1);
         }
     }
 
@@ -587,8 +641,8 @@ __device__ __forceinline__ float head_gather(const float* __restrict__ zbuf, int
     for (int t = 0; t < 9; t++) {
         const int row = base_row + (y + t / 3 - 1) * 20 + (x + t % 3 - 1);
         if (row >= 0) {  // rows above the first position are implicit zero padding
-            acc += zbuf[(size_t)t * chunk_rows + row];
-            acc += zbuf[(size_t)(9 + t) * chunk_rows + row];
+#pragma unroll
+            for (int p = 0; p < kColParts; p++) acc += zbuf[(size_t)(p * 9 + t) * chunk_rows + row];
         }
     }
     return acc;

@@ -28,7 +28,11 @@ constexpr int kBBlockBytes = 9 * 128 * 32;                    // up to 9 taps x 
 constexpr int kStageBytesSingle = kASlabBytes + kBBlockBytes;      // 48,128
 constexpr int kStageBytesPair = kASlabBytes + kBBlockBytes / 2;    // 29,696
 constexpr int kMaxStages = 6;
-constexpr int kEpilogueWarps = 8;
+#ifndef LB2_EPI_WARPS
+#define LB2_EPI_WARPS 8
+#endif
+constexpr int kEpilogueWarps = LB2_EPI_WARPS;  // 8 or 16: TMEM lane quadrant (w % 4) x column part (w / 4)
+constexpr int kColParts = kEpilogueWarps / 4;     // parts the output channels of a tile are split into
 // warp0 TMA producer, warp1 MMA issuer, warps2-9 epilogue, warp10 tile publisher, warp11 dependency scout
 constexpr int kTrunkThreads = 64 + 32 * kEpilogueWarps + 64;
 constexpr int kMaxLaunchJobs = 24;  // jobs whose biases are kept resident in smem
@@ -72,7 +76,7 @@ struct LayerJob {
     __half* out;             // output activation buffer
     uint32_t* flags;         // [n_items] completion flags (value = launch epoch)
     const float* head_w;     // fused head weights [9 taps][n_out] fp32
-    float* zbuf;             // fused head output [2 channel halves][9 taps][out_chunk_rows] fp32
+    float* zbuf;             // fused head output [kColParts channel parts][9 taps][out_chunk_rows] fp32
 };
 
 struct TrunkParams {

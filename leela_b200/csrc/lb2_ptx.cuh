@@ -48,6 +48,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the thread for a while when the phase is not complete)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
@@ -97,28 +109,21 @@ __device__ __forceinline__ uint32_t ld_acquire_cta_shared(const uint32_t* p) {
     return v;
 }
 
-// cluster-scope shared-memory signalling (dynamic scheduling: the leader CTA publishes claimed
-// items into both CTAs' shared memory)
-__device__ __forceinline__ uint32_t ld_acquire_cluster_shared(const uint32_t* p) {
+// work-item ring signalling: tag and payload travel in ONE 32-bit word, so plain (volatile)
+// accesses suffice and no cluster-scope acquire (an L1 invalidate) sits on any role's path
+__device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t* p) {
     uint32_t v;
-    asm volatile("ld.acquire.cluster.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_cluster_shared(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.cluster.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+__device__ __forceinline__ void st_volatile_shared(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 __device__ __forceinline__ void st_remote_shared(uint32_t* p, uint32_t cta, uint32_t v) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "st.shared::cluster.u32 [ra], %2;\n\t}\n" ::"r"(smem_u32(p)), "r"(cta), "r"(v)
-        : "memory");
-}
-__device__ __forceinline__ void st_release_remote_shared(uint32_t* p, uint32_t cta, uint32_t v) {
-    asm volatile(
-        "{\n\t.reg .b32 ra;\n\t"
-        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "st.release.cluster.shared::cluster.u32 [ra], %2;\n\t}\n" ::"r"(smem_u32(p)), "r"(cta), "r"(v)
+        "st.volatile.shared::cluster.u32 [ra], %2;\n\t}\n" ::"r"(smem_u32(p)), "r"(cta), "r"(v)
         : "memory");
 }
 
@@ -231,6 +236,14 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+// 32 lanes x 8 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
         : "r"(taddr)
         : "memory");
 }
