@@ -119,7 +119,9 @@ int lb2_device_count(lb2_ctx* ctx);
  *   "dynamic_items": 1 = clusters claim work items from a global in-order counter (default), 0 = round robin
  *   "max_batch":  positions per device pass (larger calls are chunked), default 256
  *   "profile_trunk": 1 = bracket every trunk launch with CUDA events; lb2_get_option("trunk_ns")
- *                 then returns the device nanoseconds accumulated since the last query */
+ *                 then returns the device nanoseconds accumulated since the last query
+ *   read-only: "stat_positions", "stat_batches", "stat_requests" = positions, device batches and
+ *                 requests that went through lb2_submit_* so far (mean batch = positions / batches) */
 int lb2_set_option(lb2_ctx* ctx, const char* name, long value);
 long lb2_get_option(lb2_ctx* ctx, const char* name);
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */

@@ -150,6 +150,7 @@ struct lb2_ctx {
     long cta_pair = 1;
     long dynamic_items = 1;
     std::atomic<long> launches{0};
+    std::atomic<long> stat_positions{0}, stat_batches{0}, stat_requests{0};  // async queue: positions, device batches, requests
     std::mutex eval_mu;
     // async submission
     std::mutex q_mu;
@@ -657,6 +658,7 @@ void worker_loop(lb2_ctx* ctx) {
         }
         int total = 0;
         for (auto& r : batch) total += r.n;
+        ctx->stat_positions += total; ctx->stat_batches++; ctx->stat_requests += (long)batch.size();
         std::vector<uint32_t> planes((size_t)total * lb2::kPoints);
         std::vector<uint8_t> rot(total);
         int o = 0;
@@ -954,6 +956,9 @@ long lb2_get_option(lb2_ctx* ctx, const char* name) {
     if (!strcmp(name, "cta_pair")) return ctx->cta_pair;
     if (!strcmp(name, "dynamic_items")) return ctx->dynamic_items;
     if (!strcmp(name, "sm_count")) return ctx->dev.empty() ? 0 : ctx->dev[0].sm_count;
+    if (!strcmp(name, "stat_positions")) return ctx->stat_positions.load();
+    if (!strcmp(name, "stat_batches")) return ctx->stat_batches.load();
+    if (!strcmp(name, "stat_requests")) return ctx->stat_requests.load();
     if (!strncmp(name, "seg", 3) && name[3] >= '0' && name[3] <= '3') {
         // mean ns of segment k over the evals recorded with profile_trunk == 2:
         // seg0 expand, seg1 trunk, seg2 heads; "seg3" only clears the record

@@ -85,3 +85,25 @@ def read_outputs(path) -> RefOutputs:
     pavg = body[o:o + n_avg * P].reshape(n_avg, P).copy(); o += n_avg * P
     vavg = body[o:o + n_avg].copy()
     return RefOutputs(temp, pol, val, pavg, vavg)
+
+
+def write_weights(path, nets) -> None:
+    """Weights file of the drop-in engine (engine/network_b200.cpp:load_weights), "LB2WGT01".
+
+    `nets`: {kind: NetWeights} with kind 0 = policy, 1 = value. Per net: the conv arrays in OIHW
+    order with their biases, then the inner products [n_out][n_in] — the layout of the reference's
+    extern weight arrays (Network.cpp:54-137), in the order Network::initialize pushes them."""
+    with open(path, "wb") as f:
+        f.write(b"LB2WGT01")
+        f.write(np.array([len(nets)], dtype=np.int32).tobytes())
+        for kind in sorted(nets):
+            w = nets[kind]
+            f.write(np.array([kind, len(w.convs), len(w.ips)], dtype=np.int32).tobytes())
+            for c, cw, cb in zip(w.convs, w.conv_w, w.conv_b):
+                f.write(np.array([c.k, c.c_in, c.c_out], dtype=np.int32).tobytes())
+                f.write(np.ascontiguousarray(cw, dtype=np.float32).tobytes())
+                f.write(np.ascontiguousarray(cb, dtype=np.float32).tobytes())
+            for p, pw, pb in zip(w.ips, w.ip_w, w.ip_b):
+                f.write(np.array([p.n_in, p.n_out], dtype=np.int32).tobytes())
+                f.write(np.ascontiguousarray(pw, dtype=np.float32).tobytes())
+                f.write(np.ascontiguousarray(pb, dtype=np.float32).tobytes())

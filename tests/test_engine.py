@@ -1,0 +1,98 @@
+"""The drop-in engine (engine/): the reference's own GTP engine sources with this repository's
+Network implementation (engine/network_b200.cpp) behind them.
+
+CPU part: the from-scratch feature-plane builder must reproduce the reference's
+gather_features_policy / _value (Network.cpp:883-1201) bit for bit on seeded self-play positions
+(the reference side is oracle/_ref/ref_harness = the unmodified reference code).
+GPU part: a GTP session — heatmap (AVERAGE_ALL through the async queue) against the reference's
+API-level golden for the same position, value-net winrate, and a search with the asynchronous
+leaf-evaluation queue that must return a legal move and fill device batches."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from leela_b200 import fileio
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ENGINE = os.path.join(ROOT, "engine", "_build", "leela_b200_engine")
+WEIGHTS = os.path.join(ROOT, "engine", "_build", "weights_synth.lb2w")
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+
+needs_engine = pytest.mark.skipif(not os.path.exists(ENGINE), reason="engine not built (needs the reference sources at build time)")
+
+
+@needs_engine
+@pytest.mark.skipif(not os.path.exists(HARNESS), reason="reference harness not built")
+@pytest.mark.parametrize("n,seed", [(300, 7), (1500, 99)])
+def test_feature_planes_bit_identical_to_reference(tmp_path, n, seed):
+    from oracle import reference
+    ours, ref = str(tmp_path / "ours.pos"), str(tmp_path / "ref")
+    subprocess.run([ENGINE, "-q", "--dump-planes", ours, str(n), str(seed)], check=True, timeout=300)
+    subprocess.run([HARNESS, "planes", ref, str(n), str(seed)], check=True, timeout=300, env=reference._env())
+    a, b = fileio.read_positions(ours), fileio.read_positions(ref + ".pos")
+    assert a.n == b.n == n
+    np.testing.assert_array_equal(a.to_move, b.to_move)      # same games were played
+    np.testing.assert_array_equal(a.movenum, b.movenum)
+    np.testing.assert_array_equal(a.policy_planes, b.policy_planes)
+    np.testing.assert_array_equal(a.value_planes, b.value_planes)
+    # the walk reaches late-game positions with ladders, captures and (in the larger set) kos
+    assert (a.policy_planes >> 25 & 1).sum() > 0 and (a.policy_planes >> 26 & 1).sum() > 0
+    assert n < 1000 or (a.policy_planes >> 27 & 1).sum() > 0
+    assert a.movenum.max() > 150
+
+
+def test_weights_file_round_trip(tmp_path):
+    from leela_b200 import synth
+    path = str(tmp_path / "w.lb2w")
+    pw, vw = synth.policy_weights(), synth.value_weights()
+    fileio.write_weights(path, {0: pw, 1: vw})
+    raw = np.fromfile(path, dtype=np.uint8)
+    assert raw[:8].tobytes() == b"LB2WGT01"
+    n_floats = sum(w.size for w in pw.conv_w + pw.conv_b + vw.conv_w + vw.conv_b + vw.ip_w + vw.ip_b)
+    n_ints = 1 + 2 * 3 + 3 * (len(pw.convs) + len(vw.convs)) + 2 * len(vw.ips)
+    assert raw.size == 8 + 4 * (n_floats + n_ints)
+    first = raw[8 + 4 * (1 + 3 + 3):][:4 * pw.conv_w[0].size].view(np.float32)
+    np.testing.assert_array_equal(first, pw.conv_w[0].ravel())
+
+
+def gtp(commands, *args, timeout=600):
+    script = "\n".join(commands + ["quit"]) + "\n"
+    r = subprocess.run([ENGINE, "-g", "--noponder", "--nobook", "--weights", WEIGHTS, *args], input=script,
+                       capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r.stdout, r.stderr
+
+
+@pytest.mark.gpu
+@needs_engine
+def test_gtp_heatmap_and_winrate_match_reference_api_golden(ref_golden):
+    # position 0 of the golden set is the empty board; policy_avg / value_avg are the reference's
+    # Network::get_scored_moves / get_value with AVERAGE_ALL on it
+    out, err = gtp(["boardsize 19", "clear_board", "komi 7.5", "heatmap", "vn_winrate"], "-t", "4")
+    rows = [list(map(int, l.split())) for l in err.splitlines() if re.fullmatch(r"(\s*-?\d+\s+){19}", l + " ")]
+    assert len(rows) >= 19, err[-1500:]
+    heat = np.array(rows[:19][::-1], dtype=np.float64).reshape(361) / 1000.0   # printed top row first
+    want = ref_golden["policy_avg"][0].astype(np.float64)
+    assert np.abs(heat - want).max() < 6e-3 + 1e-3   # stated model tolerance + the print's 1/1000 truncation
+    assert want[int(heat.argmax())] >= want.max() - 1e-3   # the empty board is 8-fold symmetric: ties
+    vals = [float(x) for x in re.findall(r"=\s*(0\.\d+|1\.0+)", out)]
+    assert vals, out
+    assert abs(vals[0] - float(ref_golden["value_avg"][0])) < 6e-3
+
+
+@pytest.mark.gpu
+@needs_engine
+def test_gtp_search_uses_batched_leaf_queue():
+    out, err = gtp(["boardsize 19", "clear_board", "komi 7.5", "genmove b", "genmove w", "showboard"],
+                   "-t", "32", "-p", "3000", "--max-outstanding", "2")
+    moves = re.findall(r"^= ([A-T]\d+)\s*$", out, flags=re.M)
+    assert len(moves) == 2 and moves[0] != moves[1], out
+    stats = re.findall(r"(\d+) visits, (\d+) nodes, (\d+) playouts, (\d+) p/s", err)
+    assert len(stats) == 2 and all(int(s[2]) >= 3000 for s in stats), err[-1500:]
+    m = re.search(r"B200 evaluator: (\d+) positions in (\d+) device batches \(mean batch ([\d.]+)\)", err)
+    assert m, err[-1500:]
+    assert int(m.group(1)) > 100            # the nets were consulted
+    assert float(m.group(3)) > 1.5          # requests of different search threads shared device batches

@@ -1,0 +1,103 @@
+"""Engine-level benchmark (BASELINE.json configs[4]): GTP genmove at a fixed think time, playouts/s.
+
+  ours       engine/_build/leela_b200_engine — the reference's search (its own sources) with the B200
+             evaluator behind Network; search threads' single-position requests are coalesced into
+             device batches by the library's queue
+  reference  oracle/_ref/ref_engine — the reference's own CPU engine (OpenBLAS path), same GTP script
+
+Usage (GPU box): python tools/engine_bench.py [--seconds 5] [--moves 4] [--threads 64] [--gpus 1]
+                 [--impl ours|reference|both] [--max-outstanding 2]
+Prints one JSON object per engine.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OURS = os.path.join(ROOT, "engine", "_build", "leela_b200_engine")
+WEIGHTS = os.path.join(ROOT, "engine", "_build", "weights_synth.lb2w")
+REF = os.path.join(ROOT, "oracle", "_ref", "ref_engine")
+STATS = re.compile(r"(\d+) visits, (\d+) nodes, (\d+) playouts, (\d+) p/s")
+BATCH = re.compile(r"B200 evaluator: (\d+) positions in (\d+) device batches \(mean batch ([\d.]+)\), (\d+) requests")
+
+
+def gtp_script(seconds: int, moves: int) -> str:
+    lines = ["boardsize 19", "clear_board", "komi 7.5", f"time_settings 0 {seconds} 1"]
+    for m in range(moves):
+        lines.append("genmove " + ("b" if m % 2 == 0 else "w"))
+    lines.append("quit")
+    return "\n".join(lines) + "\n"
+
+
+def run(cmd, script, env=None, timeout=1200):
+    t0 = time.time()
+    r = subprocess.run(cmd, input=script, capture_output=True, text=True, env=env, timeout=timeout)
+    text = r.stdout + r.stderr
+    per_move = [dict(visits=int(a), nodes=int(b), playouts=int(c), playouts_per_s=int(d)) for a, b, c, d in STATS.findall(text)]
+    moves = re.findall(r"^= ([A-T]\d+|pass|resign)\s*$", r.stdout, flags=re.M | re.I)
+    return r.returncode, text, per_move, moves, time.time() - t0
+
+
+def summarize(name, rc, text, per_move, moves, wall, extra):
+    out = {"engine": name, "rc": rc, "moves": moves, "per_move": per_move, "wall_s": round(wall, 1)}
+    if per_move:
+        out["playouts_per_s_mean"] = sum(m["playouts_per_s"] for m in per_move) / len(per_move)
+        out["playouts_total"] = sum(m["playouts"] for m in per_move)
+    m = BATCH.search(text)
+    if m:
+        out["nn_positions"] = int(m.group(1)); out["device_batches"] = int(m.group(2))
+        out["mean_device_batch"] = float(m.group(3)); out["nn_requests"] = int(m.group(4))
+    out.update(extra)
+    if rc != 0 or not per_move:
+        out["tail"] = text[-1500:]
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=int, default=5)
+    ap.add_argument("--moves", type=int, default=4)
+    ap.add_argument("--threads", type=int, default=64)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--impl", default="both", choices=["ours", "reference", "both"])
+    ap.add_argument("--max-outstanding", type=int, default=2)
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--extra", default="", help="extra engine options for ours, e.g. '--mature_threshold 2 --eval_thresh 0'")
+    args = ap.parse_args()
+    script = gtp_script(args.seconds, args.moves)
+    results = []
+    if args.impl in ("ours", "both"):
+        if not os.path.exists(WEIGHTS):
+            sys.path.insert(0, ROOT)
+            from engine import build as eb
+            eb.write_synth_weights()
+        cmd = [OURS, "-g", "-t", str(args.threads), "--noponder", "--nobook", "--lagbuffer", "0", "--weights", WEIGHTS,
+               "--max-outstanding", str(args.max_outstanding)]
+        if args.batch:
+            cmd += ["--batch", str(args.batch)]
+        for g in range(args.gpus):
+            cmd += ["--gpu", str(g)]
+        cmd += args.extra.split()
+        results.append(summarize("leela_b200_engine", *run(cmd, script),
+                                 {"threads": args.threads, "gpus": args.gpus, "think_s": args.seconds,
+                                  "max_outstanding": args.max_outstanding, "extra": args.extra}))
+    if args.impl in ("reference", "both"):
+        sys.path.insert(0, ROOT)
+        from oracle import reference
+        env = reference._env()
+        threads = min(args.threads, os.cpu_count() or 1, 64)
+        cmd = [REF, "-g", "-t", str(threads), "--noponder", "--nobook", "--lagbuffer", "0"]
+        results.append(summarize("reference_cpu_engine", *run(cmd, script, env=env),
+                                 {"threads": threads, "think_s": args.seconds, "blas_core": env.get("OPENBLAS_CORETYPE")}))
+    for r in results:
+        print(json.dumps(r), flush=True)
+
+
+if __name__ == "__main__":
+    main()
