@@ -10,7 +10,7 @@
 //                         uint32 per board point, bit c = plane c) using the reference's FastBoard
 //                         queries (count_rliberties, after_liberties, ladder readers ...)
 //   * ensembles           DIRECT / RANDOM_ROTATION / AVERAGE_ALL (Network.cpp:590-674); AVERAGE_ALL is
-//                         ONE 8-position device batch, averaged on the host in the reference's order
+//                         lb2_eval_ensemble: expanded x8, evaluated and averaged on the device
 //   * result mapping      EMPTY filter, vertex mapping, losing-ladder prune (Network.cpp:820-829, 656-667)
 //   * async expansion     async_scored_moves + completion callback -> UCTNode::scoring_cb
 //                         (Network.cpp:471-588), on lb2_submit_policy
@@ -209,18 +209,6 @@ struct Waiter {
     }
 };
 
-// the symmetries one call evaluates: n = 1 (DIRECT: `rotation`, RANDOM_ROTATION: a random one) or
-// n = 8 (AVERAGE_ALL: 0..7 over copies of the same planes)
-int fill_symmetries(Network::Ensemble ensemble, int rotation, const uint32_t* one, std::vector<uint32_t>& planes, uint8_t* rot) {
-    const int n = ensemble == Network::AVERAGE_ALL ? 8 : 1;
-    planes.resize((size_t)n * 361);
-    for (int r = 0; r < n; r++) {
-        std::copy(one, one + 361, planes.begin() + (size_t)r * 361);
-        rot[r] = (uint8_t)(n == 8 ? r : rotation);
-    }
-    return n;
-}
-
 // completion of an asynchronous policy expansion (the reference's CallbackData + forward_cb,
 // Network.cpp:471-534)
 struct AsyncExpansion {
@@ -376,21 +364,17 @@ Network::Netresult Network::get_scored_moves(FastState* state, Ensemble ensemble
     } else {
         assert(ensemble == AVERAGE_ALL);
     }
-    std::vector<uint32_t> planes;
-    uint8_t rot[8];
-    const int n = fill_symmetries(ensemble, rotation, one, planes, rot);
-    std::vector<float> probs((size_t)n * 361);
-    Waiter w;
-    if (lb2_submit_policy(g_ctx, planes.data(), rot, n, cfg_softmax_temp, probs.data(), Waiter::signal, &w)) die("lb2_submit_policy");
-    w.wait("policy evaluation");
-    if (n == 8) {   // sum r = 0..7 in that order, then divide (Network.cpp:643-654)
-        for (int idx = 0; idx < 361; idx++) {
-            float s = probs[idx];
-            for (int r = 1; r < 8; r++) s += probs[(size_t)r * 361 + idx];
-            probs[idx] = s / 8.0f;
-        }
+    float probs[361];
+    if (ensemble == AVERAGE_ALL) {
+        // the 8 symmetries are expanded, evaluated and averaged (r = 0..7, then / 8) on the device
+        if (lb2_eval_ensemble(g_ctx, one, nullptr, 1, cfg_softmax_temp, probs, nullptr)) die("lb2_eval_ensemble");
+    } else {
+        const uint8_t rot = (uint8_t)rotation;
+        Waiter w;
+        if (lb2_submit_policy(g_ctx, one, &rot, 1, cfg_softmax_temp, probs, Waiter::signal, &w)) die("lb2_submit_policy");
+        w.wait("policy evaluation");
     }
-    return to_netresult(*state, probs.data(), ladder);
+    return to_netresult(*state, probs, ladder);
 }
 
 float Network::get_value(FastState* state, Ensemble ensemble) {
@@ -404,19 +388,16 @@ float Network::get_value(FastState* state, Ensemble ensemble) {
     int rotation = 0;
     if (ensemble == RANDOM_ROTATION) rotation = Random::get_Rng()->randfix<8>();
     else assert(ensemble == DIRECT || ensemble == AVERAGE_ALL);
-    std::vector<uint32_t> planes;
-    uint8_t rot[8];
-    const int n = fill_symmetries(ensemble, rotation, one, planes, rot);
-    float win[8];
-    Waiter w;
-    if (lb2_submit_value(g_ctx, planes.data(), rot, n, win, Waiter::signal, &w)) die("lb2_submit_value");
-    w.wait("value evaluation");
-    float result = win[0];
-    if (n == 8) {
-        for (int r = 1; r < 8; r++) result += win[r];
-        result /= 8.0f;
+    float win = 0.5f;
+    if (ensemble == AVERAGE_ALL) {
+        if (lb2_eval_ensemble(g_ctx, nullptr, one, 1, 1.0f, nullptr, &win)) die("lb2_eval_ensemble");
+    } else {
+        const uint8_t rot = (uint8_t)rotation;
+        Waiter w;
+        if (lb2_submit_value(g_ctx, one, &rot, 1, &win, Waiter::signal, &w)) die("lb2_submit_value");
+        w.wait("value evaluation");
     }
-    return result;
+    return win;
 }
 
 void Network::async_scored_moves(std::atomic<int>* nodecount, FastState* state, UCTNode* node, Ensemble ensemble, int rotation) {

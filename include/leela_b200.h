@@ -88,6 +88,14 @@ int lb2_eval_both(lb2_ctx* ctx, const uint32_t* policy_planes, const uint32_t* v
                   const uint8_t* rotation, int n, float softmax_temp,
                   float* probs_out, float* winrate_out);
 
+/* Ensemble AVERAGE_ALL (Network.cpp:605-615 value, 643-654 policy) for n positions: each position
+ * is expanded on the device under all 8 symmetries from ONE copy of its planes, the 8 un-rotated
+ * results are summed in the reference's order (r = 0..7) and divided by 8 on the device — the
+ * caller uploads 1/8 and downloads 1/8 of what an explicit 8-entry batch would. Either output (with
+ * its input) may be NULL. Blocking. probs_out: [n][361]; winrate_out: [n]. */
+int lb2_eval_ensemble(lb2_ctx* ctx, const uint32_t* policy_planes, const uint32_t* value_planes, int n,
+                      float softmax_temp, float* probs_out, float* winrate_out);
+
 /* Same as lb2_eval_both but every pointer is DEVICE memory on context device `dev_index`,
  * work is enqueued on `cuda_stream` (a cudaStream_t, NULL = the context's own stream) and the
  * call returns without synchronising. Used to time the kernels with inputs resident in HBM.

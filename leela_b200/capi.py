@@ -20,7 +20,7 @@ P = 361
 # every symbol include/leela_b200.h declares
 EXPORTS = [
     "lb2_init", "lb2_destroy", "lb2_net_create", "lb2_net_push_conv", "lb2_net_push_ip", "lb2_net_finalize",
-    "lb2_eval_policy", "lb2_eval_value", "lb2_eval_both", "lb2_eval_both_device", "lb2_submit_policy",
+    "lb2_eval_policy", "lb2_eval_value", "lb2_eval_both", "lb2_eval_ensemble", "lb2_eval_both_device", "lb2_submit_policy",
     "lb2_submit_value", "lb2_drain", "lb2_backend_name", "lb2_last_error", "lb2_device_count", "lb2_set_option",
     "lb2_get_option", "lb2_launch_count", "lb2_debug_trunk", "lb2_debug_read_trace",
 ]
@@ -54,6 +54,7 @@ def load():
     L.lb2_eval_policy.argtypes = [vp, vp, vp, ip, fp, vp]
     L.lb2_eval_value.argtypes = [vp, vp, vp, ip, vp]
     L.lb2_eval_both.argtypes = [vp, vp, vp, vp, ip, fp, vp, vp]
+    L.lb2_eval_ensemble.argtypes = [vp, vp, vp, ip, fp, vp, vp]
     L.lb2_eval_both_device.argtypes = [vp, ip, vp, vp, vp, ip, fp, vp, vp, vp]
     L.lb2_submit_policy.argtypes = [vp, vp, vp, ip, fp, vp, CALLBACK, vp]
     L.lb2_submit_value.argtypes = [vp, vp, vp, ip, vp, CALLBACK, vp]
@@ -151,6 +152,17 @@ class Evaluator:
         probs = probs_out if probs_out is not None else np.empty((n, P), dtype=np.float32)
         win = win_out if win_out is not None else np.empty(n, dtype=np.float32)
         check(self._L.lb2_eval_both(self.ctx, _p(pp), _p(vp), _p(rotation), n, temp, _p(probs), _p(win)))
+        return probs, win
+
+    def eval_ensemble(self, policy_planes=None, value_planes=None, temp=0.75):
+        """AVERAGE_ALL on the device: mean over the 8 symmetries of every position."""
+        pp = np.ascontiguousarray(policy_planes, dtype=np.uint32) if policy_planes is not None else None
+        vp = np.ascontiguousarray(value_planes, dtype=np.uint32) if value_planes is not None else None
+        n = (pp if pp is not None else vp).shape[0]
+        probs = np.empty((n, P), dtype=np.float32) if pp is not None else None
+        win = np.empty(n, dtype=np.float32) if vp is not None else None
+        check(self._L.lb2_eval_ensemble(self.ctx, _p(pp) if pp is not None else None, _p(vp) if vp is not None else None, n, temp,
+                                        _p(probs) if probs is not None else None, _p(win) if win is not None else None))
         return probs, win
 
     def eval_both_raw(self, pp_ptr, vp_ptr, rot_ptr, n, temp, probs_ptr, win_ptr):

@@ -97,6 +97,23 @@ struct NetDev {
     CUtensorMap tm_x0, tm_act[2];
 };
 
+// Input/output buffers of one host-buffer call in flight on a device. Two slots per device let the
+// copies of one call overlap the kernels of another (the activation workspace is shared, so the
+// kernels themselves run one call after the other on the device's compute stream).
+struct IoSlot {
+    cudaStream_t stream = nullptr;          // copies of this slot
+    cudaEvent_t ev_in = nullptr, ev_done = nullptr;
+    int cap = 0;
+    bool busy = false;
+    uint32_t* d_planes[2] = {nullptr, nullptr};
+    uint8_t* d_rot = nullptr;
+    float *d_probs = nullptr, *d_win = nullptr;
+    uint32_t* h_planes[2] = {nullptr, nullptr};  // pinned staging for pageable caller buffers
+    uint8_t* h_rot = nullptr;
+    float *h_probs = nullptr, *h_win = nullptr;
+};
+constexpr int kIoSlots = 2;
+
 struct DeviceState {
     int id = 0;
     int sm_count = 0;
@@ -117,6 +134,10 @@ struct DeviceState {
     std::vector<cudaEvent_t> prof_events;  // (start, stop) pairs around trunk launches
     std::vector<cudaEvent_t> seg_events;   // profile_trunk == 2: one event around every launch, 4 per eval
     long plan_key[8] = {-1, -1, -1, -1, -1, -1, -1, -1};  // n, run0, run1, limit0, limit1, workspace pointers
+    IoSlot slots[kIoSlots];
+    cudaEvent_t ev_user = nullptr;   // last work enqueued on a caller-provided stream (lb2_eval_both_device)
+    cudaEvent_t ev_comp = nullptr;   // marks the compute stream for such a call to wait on
+    bool user_pending = false;
 };
 
 struct Request {
@@ -151,13 +172,16 @@ struct lb2_ctx {
     long dynamic_items = 1;
     std::atomic<long> launches{0};
     std::atomic<long> stat_positions{0}, stat_batches{0}, stat_requests{0};  // async queue: positions, device batches, requests
-    std::mutex eval_mu;
+    std::mutex eval_mu;                 // guards enqueueing on the devices and the shared workspaces
+    std::mutex slot_mu;                 // guards IoSlot::busy
+    std::condition_variable slot_cv;
     // async submission
     std::mutex q_mu;
     std::condition_variable q_cv, q_idle;
     std::deque<Request> queue;
-    bool worker_run = false, worker_busy = false;
-    std::thread worker;
+    bool worker_run = false;
+    int workers_busy = 0;
+    std::vector<std::thread> workers;   // two: one batch's copies overlap the other's kernels
 };
 
 namespace {
@@ -487,8 +511,9 @@ int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers
     return LB2_OK;
 }
 
+// `ensemble`: n device positions = n/8 input positions x 8 symmetries (AVERAGE_ALL), d_rot unused
 int eval_on_device(lb2_ctx* ctx, DeviceState* d, const uint32_t* d_pol, const uint32_t* d_val, const uint8_t* d_rot,
-                   int n, float temp, float* d_probs, float* d_win, cudaStream_t st) {
+                   int n, float temp, float* d_probs, float* d_win, cudaStream_t st, bool ensemble = false) {
     bool run[2] = {d_probs != nullptr, d_win != nullptr};
     // profile_trunk == 2: an event after every launch -> per-segment device times (debug)
     auto mark = [&]() {
@@ -502,6 +527,7 @@ int eval_on_device(lb2_ctx* ctx, DeviceState* d, const uint32_t* d_pol, const ui
     lb2::ExpandArgs ea;
     memset(&ea, 0, sizeof ea);
     ea.rotation = d_rot;
+    ea.ensemble = ensemble ? 1 : 0;
     ea.n = n;
     ea.zero_word = d->item_counter;
     for (int k = 0; k < 2; k++) {
@@ -527,6 +553,7 @@ int eval_on_device(lb2_ctx* ctx, DeviceState* d, const uint32_t* d_pol, const ui
     lb2::HeadArgs ha;
     memset(&ha, 0, sizeof ha);
     ha.rotation = d_rot;
+    ha.ensemble = ensemble ? 1 : 0;
     ha.temp = temp;
     if (run[0]) {
         NetDev& nd = d->net[0];
@@ -565,28 +592,145 @@ int check_rotations(const uint8_t* rot, int n) {
     return LB2_OK;
 }
 
-// Host-buffer evaluation: shard positions over devices in contiguous slices, chunk each slice
-// by max_batch, stage through pinned memory.
+int ensure_slot(IoSlot* sl, int cap) {
+    if (!sl->stream) {
+        CU_TRY(cudaStreamCreateWithFlags(&sl->stream, cudaStreamNonBlocking));
+        CU_TRY(cudaEventCreateWithFlags(&sl->ev_in, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&sl->ev_done, cudaEventDisableTiming));
+    }
+    if (sl->cap >= cap) return LB2_OK;
+    CU_TRY(cudaStreamSynchronize(sl->stream));
+    for (int k = 0; k < 2; k++) { cudaFree(sl->d_planes[k]); cudaFreeHost(sl->h_planes[k]); }
+    cudaFree(sl->d_rot); cudaFree(sl->d_probs); cudaFree(sl->d_win);
+    cudaFreeHost(sl->h_rot); cudaFreeHost(sl->h_probs); cudaFreeHost(sl->h_win);
+    sl->cap = 0;
+    const size_t pbytes = (size_t)cap * lb2::kPoints * sizeof(uint32_t);
+    for (int k = 0; k < 2; k++) {
+        CU_TRY(cudaMalloc(&sl->d_planes[k], pbytes));
+        CU_TRY(cudaMallocHost(&sl->h_planes[k], pbytes));
+    }
+    CU_TRY(cudaMalloc(&sl->d_rot, cap));
+    CU_TRY(cudaMalloc(&sl->d_probs, (size_t)cap * lb2::kPoints * sizeof(float)));
+    CU_TRY(cudaMalloc(&sl->d_win, (size_t)cap * sizeof(float)));
+    CU_TRY(cudaMallocHost(&sl->h_rot, cap));
+    CU_TRY(cudaMallocHost(&sl->h_probs, (size_t)cap * lb2::kPoints * sizeof(float)));
+    CU_TRY(cudaMallocHost(&sl->h_win, (size_t)cap * sizeof(float)));
+    sl->cap = cap;
+    return LB2_OK;
+}
+
+void free_slot(IoSlot* sl) {
+    for (int k = 0; k < 2; k++) { cudaFree(sl->d_planes[k]); cudaFreeHost(sl->h_planes[k]); }
+    cudaFree(sl->d_rot); cudaFree(sl->d_probs); cudaFree(sl->d_win);
+    cudaFreeHost(sl->h_rot); cudaFreeHost(sl->h_probs); cudaFreeHost(sl->h_win);
+    if (sl->ev_in) cudaEventDestroy(sl->ev_in);
+    if (sl->ev_done) cudaEventDestroy(sl->ev_done);
+    if (sl->stream) cudaStreamDestroy(sl->stream);
+    *sl = IoSlot();
+}
+
+// One slot index on EVERY device for the duration of a host-buffer call (so concurrent callers never
+// hold slots in opposite orders).
+int acquire_slots(lb2_ctx* ctx) {
+    std::unique_lock<std::mutex> lk(ctx->slot_mu);
+    int si = -1;
+    ctx->slot_cv.wait(lk, [&] {
+        for (int i = 0; i < kIoSlots; i++)
+            if (!ctx->dev[0].slots[i].busy) { si = i; return true; }
+        return false;
+    });
+    for (auto& d : ctx->dev) d.slots[si].busy = true;
+    return si;
+}
+void release_slots(lb2_ctx* ctx, int si) {
+    {
+        std::lock_guard<std::mutex> lk(ctx->slot_mu);
+        for (auto& d : ctx->dev) d.slots[si].busy = false;
+    }
+    ctx->slot_cv.notify_one();
+}
+
+// Host-buffer evaluation: shard positions over devices in contiguous slices, chunk each slice by
+// max_batch. Per device the call owns one IoSlot: inputs go up on the slot's stream, the kernels run
+// on the device's compute stream (after the previous call's kernels: the activation workspace is
+// shared), the results come down on the slot's stream — so with two callers in flight the copies
+// of one overlap the kernels of the other. Only the enqueueing is done under the context lock.
+int eval_host_locked_enqueue(lb2_ctx* ctx, DeviceState* d, IoSlot* sl, const uint32_t* const src[2], const bool pin_in[2],
+                             const uint8_t* rot, bool pin_rot, int lo, int cnt, int cap, float temp, const bool need[2],
+                             float* probs, bool pin_probs, float* win, bool pin_win, bool ensemble) {
+    int rc;
+    CU_TRY(cudaSetDevice(d->id));
+    for (int k = 0; k < 2; k++)
+        if (need[k] && d->net[k].cap < cap) {
+            // growing the shared workspace: nothing may still be computing in it
+            CU_TRY(cudaStreamSynchronize(d->stream));
+            if ((rc = ensure_workspace(&d->net[k], k, cap))) return rc;
+        }
+    const size_t pbytes = (size_t)cnt * lb2::kPoints * sizeof(uint32_t);
+    if (!ensemble) CU_TRY(cudaMemcpyAsync(sl->d_rot, pin_rot ? rot + lo : sl->h_rot, cnt, cudaMemcpyHostToDevice, sl->stream));
+    for (int k = 0; k < 2; k++) {
+        if (!need[k]) continue;
+        const uint32_t* from = pin_in[k] ? src[k] + (size_t)lo * lb2::kPoints : sl->h_planes[k];
+        CU_TRY(cudaMemcpyAsync(sl->d_planes[k], from, pbytes, cudaMemcpyHostToDevice, sl->stream));
+    }
+    CU_TRY(cudaEventRecord(sl->ev_in, sl->stream));
+    CU_TRY(cudaStreamWaitEvent(d->stream, sl->ev_in, 0));
+    if (d->user_pending) {   // kernels enqueued on a caller's stream (lb2_eval_both_device) use the same workspace
+        CU_TRY(cudaStreamWaitEvent(d->stream, d->ev_user, 0));
+        d->user_pending = false;
+    }
+    // ensemble: the 8*cnt per-symmetry results land in the first 8*cnt entries of the slot's output
+    // buffers, their means behind them
+    const int n_dev = ensemble ? 8 * cnt : cnt;
+    rc = eval_on_device(ctx, d, sl->d_planes[0], sl->d_planes[1], sl->d_rot, n_dev, temp, need[0] ? sl->d_probs : nullptr,
+                        need[1] ? sl->d_win : nullptr, d->stream, ensemble);
+    if (rc) return rc;
+    const float* res_probs = sl->d_probs;
+    const float* res_win = sl->d_win;
+    if (ensemble) {
+        lb2::MeanArgs ma;
+        memset(&ma, 0, sizeof ma);
+        if (need[0]) { ma.probs8 = sl->d_probs; ma.probs = sl->d_probs + (size_t)n_dev * lb2::kPoints; ma.n_policy = cnt; res_probs = ma.probs; }
+        if (need[1]) { ma.win8 = sl->d_win; ma.win = sl->d_win + n_dev; ma.n_value = cnt; res_win = ma.win; }
+        CU_TRY(lb2::launch_ensemble_mean(ma, d->stream));
+        ctx->launches++;
+    }
+    CU_TRY(cudaEventRecord(sl->ev_done, d->stream));
+    CU_TRY(cudaStreamWaitEvent(sl->stream, sl->ev_done, 0));
+    if (need[0])
+        CU_TRY(cudaMemcpyAsync(pin_probs ? probs + (size_t)lo * lb2::kPoints : sl->h_probs, res_probs,
+                               (size_t)cnt * lb2::kPoints * sizeof(float), cudaMemcpyDeviceToHost, sl->stream));
+    if (need[1])
+        CU_TRY(cudaMemcpyAsync(pin_win ? win + lo : sl->h_win, res_win, (size_t)cnt * sizeof(float), cudaMemcpyDeviceToHost,
+                               sl->stream));
+    return LB2_OK;
+}
+
 int eval_host(lb2_ctx* ctx, const uint32_t* pol, const uint32_t* val, const uint8_t* rot, int n, float temp,
-              float* probs, float* win) {
+              float* probs, float* win, bool ensemble = false) {
     bool need[2] = {probs != nullptr, win != nullptr};
     int rc = check_ready(ctx, need);
     if (rc) return rc;
     if (n < 0) return fail(LB2_ERR_INVALID, "n < 0");
     if (n == 0) return LB2_OK;
-    if (!rot || (need[0] && !pol) || (need[1] && !val)) return fail(LB2_ERR_INVALID, "null input pointer");
+    if ((!ensemble && !rot) || (need[0] && !pol) || (need[1] && !val)) return fail(LB2_ERR_INVALID, "null input pointer");
     if (need[0] && !(temp > 0.0f)) return fail(LB2_ERR_INVALID, "softmax temperature must be > 0");
-    if ((rc = check_rotations(rot, n))) return rc;
-    std::lock_guard<std::mutex> lk(ctx->eval_mu);
+    if (!ensemble && (rc = check_rotations(rot, n))) return rc;
     // caller buffers that are already page-locked are used directly; pageable ones go through the
-    // context's pinned staging buffers
+    // slot's pinned staging buffers
     const bool pin_in[2] = {is_pinned(pol), is_pinned(val)};
-    const bool pin_rot = is_pinned(rot), pin_probs = is_pinned(probs), pin_win = is_pinned(win);
+    const bool pin_rot = ensemble || is_pinned(rot), pin_probs = is_pinned(probs), pin_win = is_pinned(win);
+    const uint32_t* const src[2] = {pol, val};
     const int ndev = (int)ctx->dev.size();
     const int per = (n + ndev - 1) / ndev;
-    const int chunk = (int)std::min<long>(ctx->max_batch, per);
+    long max_batch;
+    { std::lock_guard<std::mutex> lk(ctx->eval_mu); max_batch = ctx->max_batch; }
+    // an ensemble position occupies 8 device positions (+1 for its mean in the output buffers)
+    const int chunk = (int)std::min<long>(ensemble ? std::max<long>(1, max_batch / 8) : max_batch, per);
+    const int dev_per_pos = ensemble ? 8 : 1, slot_per_pos = ensemble ? 9 : 1;
+    const int si = acquire_slots(ctx);
+    struct Release { lb2_ctx* c; int s; ~Release() { release_slots(c, s); } } release{ctx, si};
     for (int base = 0; base < per; base += chunk) {
-        // enqueue one chunk on every device, then collect
         std::vector<int> cnt(ndev, 0), off(ndev, 0);
         for (int di = 0; di < ndev; di++) {
             const int lo = std::min(n, di * per + base), hi = std::min(n, std::min((di + 1) * per, di * per + base + chunk));
@@ -594,41 +738,27 @@ int eval_host(lb2_ctx* ctx, const uint32_t* pol, const uint32_t* val, const uint
             off[di] = lo;
             if (!cnt[di]) continue;
             DeviceState* d = &ctx->dev[di];
+            IoSlot* sl = &d->slots[si];
             CU_TRY(cudaSetDevice(d->id));
-            if ((rc = ensure_device_staging(d, std::max(chunk, cnt[di])))) return rc;
+            if ((rc = ensure_slot(sl, slot_per_pos * std::max(chunk, cnt[di])))) return rc;
+            // staging copies happen outside the context lock
+            if (!pin_rot) memcpy(sl->h_rot, rot + lo, cnt[di]);
             for (int k = 0; k < 2; k++)
-                if (need[k] && (rc = ensure_workspace(&d->net[k], k, std::max(chunk, cnt[di])))) return rc;
-            const size_t pbytes = (size_t)cnt[di] * lb2::kPoints * sizeof(uint32_t);
-            if (pin_rot) {
-                CU_TRY(cudaMemcpyAsync(d->rot, rot + lo, cnt[di], cudaMemcpyHostToDevice, d->stream));
-            } else {
-                memcpy(d->h_rot, rot + lo, cnt[di]);
-                CU_TRY(cudaMemcpyAsync(d->rot, d->h_rot, cnt[di], cudaMemcpyHostToDevice, d->stream));
-            }
-            const uint32_t* src[2] = {pol, val};
-            for (int k = 0; k < 2; k++) {
-                if (!need[k]) continue;
-                const uint32_t* from = src[k] + (size_t)lo * lb2::kPoints;
-                if (!pin_in[k]) { memcpy(d->h_planes[k], from, pbytes); from = d->h_planes[k]; }
-                CU_TRY(cudaMemcpyAsync(d->net[k].planes, from, pbytes, cudaMemcpyHostToDevice, d->stream));
-            }
-            rc = eval_on_device(ctx, d, d->net[0].planes, d->net[1].planes, d->rot, cnt[di], temp,
-                                need[0] ? d->net[0].out : nullptr, need[1] ? d->net[1].out : nullptr, d->stream);
+                if (need[k] && !pin_in[k])
+                    memcpy(sl->h_planes[k], src[k] + (size_t)lo * lb2::kPoints, (size_t)cnt[di] * lb2::kPoints * sizeof(uint32_t));
+            std::lock_guard<std::mutex> lk(ctx->eval_mu);
+            rc = eval_host_locked_enqueue(ctx, d, sl, src, pin_in, rot, pin_rot, lo, cnt[di], dev_per_pos * std::max(chunk, cnt[di]), temp,
+                                          need, probs, pin_probs, win, pin_win, ensemble);
             if (rc) return rc;
-            if (need[0])
-                CU_TRY(cudaMemcpyAsync(pin_probs ? probs + (size_t)lo * lb2::kPoints : d->h_probs, d->net[0].out,
-                                       (size_t)cnt[di] * lb2::kPoints * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
-            if (need[1])
-                CU_TRY(cudaMemcpyAsync(pin_win ? win + lo : d->h_win, d->net[1].out, (size_t)cnt[di] * sizeof(float),
-                                       cudaMemcpyDeviceToHost, d->stream));
         }
         for (int di = 0; di < ndev; di++) {
             if (!cnt[di]) continue;
             DeviceState* d = &ctx->dev[di];
+            IoSlot* sl = &d->slots[si];
             CU_TRY(cudaSetDevice(d->id));
-            CU_TRY(cudaStreamSynchronize(d->stream));
-            if (need[0] && !pin_probs) memcpy(probs + (size_t)off[di] * lb2::kPoints, d->h_probs, (size_t)cnt[di] * lb2::kPoints * sizeof(float));
-            if (need[1] && !pin_win) memcpy(win + off[di], d->h_win, (size_t)cnt[di] * sizeof(float));
+            CU_TRY(cudaStreamSynchronize(sl->stream));
+            if (need[0] && !pin_probs) memcpy(probs + (size_t)off[di] * lb2::kPoints, sl->h_probs, (size_t)cnt[di] * lb2::kPoints * sizeof(float));
+            if (need[1] && !pin_win) memcpy(win + off[di], sl->h_win, (size_t)cnt[di] * sizeof(float));
         }
     }
     return LB2_OK;
@@ -654,7 +784,7 @@ void worker_loop(lb2_ctx* ctx) {
                     ++it;
                 }
             }
-            ctx->worker_busy = true;
+            ctx->workers_busy++;
         }
         int total = 0;
         for (auto& r : batch) total += r.n;
@@ -683,8 +813,8 @@ void worker_loop(lb2_ctx* ctx) {
         }
         {
             std::lock_guard<std::mutex> lk(ctx->q_mu);
-            ctx->worker_busy = false;
-            if (ctx->queue.empty()) ctx->q_idle.notify_all();
+            ctx->workers_busy--;
+            if (ctx->queue.empty() && ctx->workers_busy == 0) ctx->q_idle.notify_all();
         }
     }
 }
@@ -704,7 +834,7 @@ int submit(lb2_ctx* ctx, int kind, const uint32_t* planes, const uint8_t* rot, i
         std::lock_guard<std::mutex> lk(ctx->q_mu);
         if (!ctx->worker_run) {
             ctx->worker_run = true;
-            ctx->worker = std::thread(worker_loop, ctx);
+            for (int i = 0; i < kIoSlots; i++) ctx->workers.emplace_back(worker_loop, ctx);
         }
         ctx->queue.push_back(std::move(r));
     }
@@ -747,6 +877,8 @@ int lb2_init(const int* device_ids, int n_devices, lb2_ctx** ctx_out) {
         CU_TRY(cudaMalloc(&d.item_counter, sizeof(uint32_t)));
         CU_TRY(cudaMemset(d.item_counter, 0, sizeof(uint32_t)));
         CU_TRY(cudaMallocHost(&d.h_jobs, lb2::kMaxJobs * sizeof(lb2::LayerJob)));
+        CU_TRY(cudaEventCreateWithFlags(&d.ev_user, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&d.ev_comp, cudaEventDisableTiming));
         CU_TRY(lb2::trunk_kernel_setup());
         if (ctx->backend.empty()) ctx->backend = std::string("B200 tcgen05: ") + prop.name;
         ctx->dev.push_back(d);
@@ -766,7 +898,7 @@ void lb2_destroy(lb2_ctx* ctx) {
         ctx->worker_run = false;
     }
     ctx->q_cv.notify_all();
-    if (ctx->worker.joinable()) ctx->worker.join();
+    for (auto& w : ctx->workers) if (w.joinable()) w.join();
     for (auto& d : ctx->dev) {
         cudaSetDevice(d.id);
         cudaStreamSynchronize(d.stream);
@@ -777,6 +909,9 @@ void lb2_destroy(lb2_ctx* ctx) {
             cudaFree(nd.ip2_w); cudaFree(nd.ip2_b);
             free_workspace(&nd);
         }
+        for (auto& sl : d.slots) free_slot(&sl);
+        if (d.ev_user) cudaEventDestroy(d.ev_user);
+        if (d.ev_comp) cudaEventDestroy(d.ev_comp);
         cudaFree(d.rot); cudaFree(d.jobs_dev); cudaFree(d.item_counter);
         cudaFreeHost(d.h_planes[0]); cudaFreeHost(d.h_planes[1]); cudaFreeHost(d.h_rot);
         cudaFreeHost(d.h_probs); cudaFreeHost(d.h_win); cudaFreeHost(d.h_jobs);
@@ -868,6 +1003,11 @@ int lb2_eval_both(lb2_ctx* ctx, const uint32_t* pol, const uint32_t* val, const 
     return eval_host(ctx, pol, val, rotation, n, temp, probs, winrate);
 }
 
+int lb2_eval_ensemble(lb2_ctx* ctx, const uint32_t* pol, const uint32_t* val, int n, float temp, float* probs, float* winrate) {
+    if (!probs && !winrate && n > 0) return fail(LB2_ERR_INVALID, "null output pointers");
+    return eval_host(ctx, probs ? pol : nullptr, winrate ? val : nullptr, nullptr, n, probs ? temp : 1.0f, probs, winrate, true);
+}
+
 int lb2_eval_both_device(lb2_ctx* ctx, int dev_index, const uint32_t* d_pol, const uint32_t* d_val,
                          const uint8_t* d_rot, int n, float temp, float* d_probs, float* d_win, void* stream) {
     bool need[2] = {d_probs != nullptr, d_win != nullptr};
@@ -883,13 +1023,25 @@ int lb2_eval_both_device(lb2_ctx* ctx, int dev_index, const uint32_t* d_pol, con
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : d->stream;
     const int chunk = (int)ctx->max_batch;
     for (int k = 0; k < 2; k++)
-        if (need[k] && (rc = ensure_workspace(&d->net[k], k, std::min(n, chunk)))) return rc;
+        if (need[k] && d->net[k].cap < std::min(n, chunk)) {
+            CU_TRY(cudaStreamSynchronize(d->stream));   // nothing may be computing in the workspace while it grows
+            CU_TRY(cudaStreamSynchronize(st));
+            if ((rc = ensure_workspace(&d->net[k], k, std::min(n, chunk)))) return rc;
+        }
+    if (st != d->stream) {   // the workspace is shared with host-buffer calls running on the compute stream
+        CU_TRY(cudaEventRecord(d->ev_comp, d->stream));
+        CU_TRY(cudaStreamWaitEvent(st, d->ev_comp, 0));
+    }
     for (int lo = 0; lo < n; lo += chunk) {
         const int c = std::min(chunk, n - lo);
         rc = eval_on_device(ctx, d, d_pol ? d_pol + (size_t)lo * lb2::kPoints : nullptr,
                             d_val ? d_val + (size_t)lo * lb2::kPoints : nullptr, d_rot + lo, c, temp,
                             d_probs ? d_probs + (size_t)lo * lb2::kPoints : nullptr, d_win ? d_win + lo : nullptr, st);
         if (rc) return rc;
+    }
+    if (st != d->stream) {
+        CU_TRY(cudaEventRecord(d->ev_user, st));
+        d->user_pending = true;
     }
     return LB2_OK;
 }
@@ -908,7 +1060,7 @@ int lb2_submit_value(lb2_ctx* ctx, const uint32_t* planes, const uint8_t* rotati
 int lb2_drain(lb2_ctx* ctx) {
     if (!ctx) return fail(LB2_ERR_INVALID, "null context");
     std::unique_lock<std::mutex> lk(ctx->q_mu);
-    ctx->q_idle.wait(lk, [&] { return ctx->queue.empty() && !ctx->worker_busy; });
+    ctx->q_idle.wait(lk, [&] { return ctx->queue.empty() && ctx->workers_busy == 0; });
     return LB2_OK;
 }
 

@@ -52,8 +52,9 @@ __global__ void __launch_bounds__(256) expand_planes_kernel(const ExpandArgs A) 
     const int y = rem / 21, x = rem - y * 21;
     uint32_t bits = 0;
     if (x < kBoard && y < kBoard) {
-        const int src = rotate_idx(y * kBoard + x, A.rotation[pos] & 7);
-        bits = A.planes[k][(size_t)pos * kPoints + src];
+        const int sym = A.ensemble ? (pos & 7) : (A.rotation[pos] & 7);
+        const int src = rotate_idx(y * kBoard + x, sym);
+        bits = A.planes[k][(size_t)(A.ensemble ? pos >> 3 : pos) * kPoints + src];
     }
     const uint32_t one = 0x3C00u;  // fp16 1.0
     __half* x0 = A.x0[k];
@@ -660,7 +661,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // policy head: one CTA per position. logit = ELU(b + conv), softmax with temperature over the
 // 361 points (Network.cpp:450-469), un-rotate (Network.cpp:820-823).
 __device__ __forceinline__ void policy_head_body(const float* __restrict__ zbuf, int chunk_rows,
-                                                 const float* __restrict__ bias, const uint8_t* __restrict__ rotation,
+                                                 const float* __restrict__ bias, const uint8_t* __restrict__ rotation, int ensemble,
                                                  float temp, float* __restrict__ probs, int pos, float* smem_f) {
     float* sm = smem_f;            // [361]
     float* red = smem_f + 368;     // [12]
@@ -685,7 +686,7 @@ __device__ __forceinline__ void policy_head_body(const float* __restrict__ zbuf,
     for (int i = 0; i < 12; i++) s += red[i];
     if (tid < kPoints) sm[tid] = e / s;
     named_bar_sync(3, 384);
-    if (tid < kPoints) probs[(size_t)pos * kPoints + tid] = sm[rev_rotate_idx(tid, rotation[pos] & 7)];
+    if (tid < kPoints) probs[(size_t)pos * kPoints + tid] = sm[rev_rotate_idx(tid, ensemble ? (pos & 7) : (rotation[pos] & 7))];
 }
 
 // value head: kValueGroup positions per CTA. v = ELU(b + conv) [361]; h = ELU(W1 v + b1);
@@ -787,13 +788,40 @@ __global__ void __launch_bounds__(kValueThreads) heads_kernel(const HeadArgs A) 
         value_head_body(A.v_zbuf, A.v_chunk_rows, A.v_bias, A.ip1_wt, A.ip1_b, A.hidden, A.ip2_w, A.ip2_b, A.n_value,
                         A.winrate, blockIdx.x, hsm);
     else
-        policy_head_body(A.p_zbuf, A.p_chunk_rows, A.p_bias, A.rotation, A.temp, A.probs, blockIdx.x - value_blocks,
+        policy_head_body(A.p_zbuf, A.p_chunk_rows, A.p_bias, A.rotation, A.ensemble, A.temp, A.probs, blockIdx.x - value_blocks,
                          reinterpret_cast<float*>(hsm));
+}
+
+// AVERAGE_ALL: one thread per output element; the 8 addends are summed in the reference's order.
+__global__ void __launch_bounds__(256) ensemble_mean_kernel(const MeanArgs A) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int np = A.n_policy * kPoints;
+    if (t < np) {
+        const int i = t / kPoints, idx = t - i * kPoints;
+        const float* src = A.probs8 + (size_t)i * 8 * kPoints + idx;
+        float s = src[0];
+#pragma unroll
+        for (int r = 1; r < 8; r++) s += src[(size_t)r * kPoints];
+        A.probs[t] = s / 8.0f;
+    } else if (t - np < A.n_value) {
+        const int i = t - np;
+        float s = A.win8[8 * i];
+#pragma unroll
+        for (int r = 1; r < 8; r++) s += A.win8[8 * i + r];
+        A.win[i] = s / 8.0f;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+cudaError_t launch_ensemble_mean(const MeanArgs& a, cudaStream_t st) {
+    const int total = a.n_policy * kPoints + a.n_value;
+    if (total == 0) return cudaSuccess;
+    ensemble_mean_kernel<<<(total + 255) / 256, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_expand(const ExpandArgs& a, cudaStream_t st) {
     const size_t threads = (size_t)a.n * 441 * a.n_nets + (a.pf_bytes + 127) / 128;
     expand_planes_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a);

@@ -99,7 +99,8 @@ struct ExpandArgs {
     const uint32_t* planes[2];   // packed bit-planes of up to two nets
     __half* x0[2];               // their first-conv input buffers (S=21 row space)
     int32_t chunk_rows[2];
-    const uint8_t* rotation;
+    const uint8_t* rotation;     // [n] symmetry per position; ignored when `ensemble`
+    int32_t ensemble;            // 1: device position p is input position p / 8 under symmetry p % 8 (AVERAGE_ALL)
     int32_t n, n_nets;
     const uint8_t* pf;           // optional buffer to pull into L2
     size_t pf_bytes;
@@ -113,12 +114,21 @@ struct HeadArgs {
     // value head (n_value positions, 0 = skip)
     const float* v_zbuf; int32_t v_chunk_rows; const float* v_bias; const float* ip1_wt; const float* ip1_b; int32_t hidden;
     const float* ip2_w; const float* ip2_b; float* winrate; int32_t n_value;
+    int32_t ensemble;            // 1: position p was evaluated under symmetry p % 8 (rotation is unused)
+};
+
+// AVERAGE_ALL on the device: mean over the 8 symmetries of each position, summed in the reference's
+// order r = 0..7 then divided by 8 (Network.cpp:605-615, 643-654)
+struct MeanArgs {
+    const float* probs8; float* probs; int32_t n_policy;   // [8n][361] -> [n][361]
+    const float* win8; float* win; int32_t n_value;        // [8n] -> [n]
 };
 
 // launchers (lb2_kernels.cu)
 cudaError_t launch_expand(const ExpandArgs& a, cudaStream_t st);
 cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool pair, cudaStream_t st);
 cudaError_t launch_heads(const HeadArgs& a, cudaStream_t st);
+cudaError_t launch_ensemble_mean(const MeanArgs& a, cudaStream_t st);
 cudaError_t trunk_kernel_setup();
 
 }  // namespace lb2

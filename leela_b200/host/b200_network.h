@@ -5,7 +5,8 @@
 // the part of the path that lives above the backend seam:
 //   Ensemble {DIRECT, RANDOM_ROTATION, AVERAGE_ALL}, scored_node = pair<float prob, int vertex>,
 //   Netresult in raster order over EMPTY points only (no renormalisation, Network.cpp:820-829),
-//   AVERAGE_ALL = mean over the 8 symmetries (Network.cpp:643-654, 605-615), losing-ladder points
+//   AVERAGE_ALL = mean over the 8 symmetries (Network.cpp:643-654, 605-615; on the device:
+//   lb2_eval_ensemble), losing-ladder points
 //   zeroed (Network.cpp:656-667), board != 19 -> empty result / 0.5 (Network.cpp:591-594, 627-629),
 //   DIRECT needs rotation 0..7, RANDOM_ROTATION needs -1 (asserts at Network.cpp:636-640).
 //
@@ -92,33 +93,27 @@ public:
                                int rotation, float softmax_temp, Rng8&& rng8) {
         Netresult result;
         if (state->board.get_boardsize() != 19) return result;
-        uint32_t packed[8 * 361];
-        uint8_t rot[8];
-        float probs[8 * 361];
-        int n = 1;
+        uint32_t packed[361];
+        float probs[361];
         pack_planes(planes, packed);
-        if (ensemble == DIRECT) {
-            if (rotation < 0 || rotation > 7) throw std::invalid_argument("DIRECT needs rotation 0..7");
-            rot[0] = (uint8_t)rotation;
-        } else if (ensemble == RANDOM_ROTATION) {
-            if (rotation != -1) throw std::invalid_argument("RANDOM_ROTATION needs rotation -1");
-            rot[0] = (uint8_t)(rng8() & 7);
-        } else {  // AVERAGE_ALL: the 8 symmetries as ONE device batch
-            n = 8;
-            for (int r = 1; r < 8; r++) std::copy(packed, packed + 361, packed + r * 361);
-            for (int r = 0; r < 8; r++) rot[r] = (uint8_t)r;
+        if (ensemble == AVERAGE_ALL) {  // the 8 symmetries are expanded, evaluated and averaged on the device
+            check(lb2_eval_ensemble(m_ctx, packed, nullptr, 1, softmax_temp, probs, nullptr));
+        } else {
+            uint8_t rot;
+            if (ensemble == DIRECT) {
+                if (rotation < 0 || rotation > 7) throw std::invalid_argument("DIRECT needs rotation 0..7");
+                rot = (uint8_t)rotation;
+            } else {
+                if (rotation != -1) throw std::invalid_argument("RANDOM_ROTATION needs rotation -1");
+                rot = (uint8_t)(rng8() & 7);
+            }
+            check(lb2_eval_policy(m_ctx, packed, &rot, 1, softmax_temp, probs));
         }
-        check(lb2_eval_policy(m_ctx, packed, rot, n, softmax_temp, probs));
         for (int idx = 0; idx < 361; idx++) {
             const int vtx = state->board.get_vertex(idx % 19, idx / 19);
             using Board = typename std::remove_reference<decltype(state->board)>::type;
             if (state->board.get_square(vtx) != Board::EMPTY) continue;
-            float p = probs[idx];                     // outputs are already un-rotated
-            if (n == 8) {
-                for (int r = 1; r < 8; r++) p += probs[r * 361 + idx];   // same order as Network.cpp:645-651
-                p /= 8.0f;
-            }
-            result.emplace_back(p, vtx);
+            result.emplace_back(probs[idx], vtx);   // outputs are already un-rotated
         }
         if (ladder) {  // prune losing ladders completely (Network.cpp:656-667)
             for (auto& sm : result) {
@@ -133,21 +128,16 @@ public:
     template <class State, class Rng8>
     float get_value(State* state, const NNPlanes& planes, Ensemble ensemble, Rng8&& rng8) {
         if (state->board.get_boardsize() != 19) return 0.5f;
-        uint32_t packed[8 * 361];
-        uint8_t rot[8] = {0, 1, 2, 3, 4, 5, 6, 7};
-        float win[8];
-        int n = 1;
+        uint32_t packed[361];
+        float win = 0.5f;
         pack_planes(planes, packed);
-        if (ensemble == RANDOM_ROTATION) rot[0] = (uint8_t)(rng8() & 7);
-        else if (ensemble == AVERAGE_ALL) {
-            n = 8;
-            for (int r = 1; r < 8; r++) std::copy(packed, packed + 361, packed + r * 361);
+        if (ensemble == AVERAGE_ALL) {
+            check(lb2_eval_ensemble(m_ctx, nullptr, packed, 1, 1.0f, nullptr, &win));
+        } else {
+            const uint8_t rot = ensemble == RANDOM_ROTATION ? (uint8_t)(rng8() & 7) : (uint8_t)0;
+            check(lb2_eval_value(m_ctx, packed, &rot, 1, &win));
         }
-        check(lb2_eval_value(m_ctx, packed, rot, n, win));
-        if (n == 1) return win[0];
-        float s = win[0];
-        for (int r = 1; r < 8; r++) s += win[r];
-        return s / 8.0f;
+        return win;
     }
 
 private:

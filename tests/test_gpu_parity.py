@@ -195,6 +195,42 @@ def test_average_all_as_microbatch(ev, ref_golden):
         assert abs(v.mean() - g["value_avg"][i]) < TOL_V
 
 
+def test_device_ensemble_equals_microbatch_and_reference(ev, ref_golden, bench_positions):
+    """lb2_eval_ensemble (8 symmetries expanded + averaged on the device) is bit-identical to the
+    explicit 8-entry batch averaged on the host in the reference's order (r = 0..7, then / 8,
+    Network.cpp:605-615, 643-654), matches the reference's API-level AVERAGE_ALL output, and handles
+    batches larger than one device pass (ragged chunking) and single-net calls."""
+    g = ref_golden
+    temp = float(g["softmax_temp"])
+    n = g["policy_avg"].shape[0]
+    pe, ve = ev.eval_ensemble(g["policy_planes"][:n], g["value_planes"][:n], temp)
+    rot = np.tile(np.arange(8, dtype=np.uint8), n)
+    p8, v8 = ev.eval_both(np.repeat(g["policy_planes"][:n], 8, 0), np.repeat(g["value_planes"][:n], 8, 0), rot, temp)
+    p8, v8 = p8.reshape(n, 8, 361), v8.reshape(n, 8)
+    want_p, want_v = p8[:, 0].copy(), v8[:, 0].copy()
+    for r in range(1, 8):
+        want_p += p8[:, r]
+        want_v += v8[:, r]
+    want_p /= np.float32(8); want_v /= np.float32(8)
+    np.testing.assert_array_equal(pe, want_p)
+    np.testing.assert_array_equal(ve, want_v)
+    for i in range(n):
+        empty = (g["policy_planes"][i] & 1).astype(bool)
+        ladder = ((g["policy_planes"][i] >> 25) & 1).astype(bool)
+        acc = pe[i].copy(); acc[ladder] = 0
+        assert np.abs(acc[empty] - g["policy_avg"][i][empty]).max() < TOL_P
+        assert abs(ve[i] - g["value_avg"][i]) < TOL_V
+    # 77 positions = 616 device positions: several passes of max_batch / 8 positions plus a ragged tail
+    m = 77
+    pb, vb = bench_positions["policy_planes"][:m], bench_positions["value_planes"][:m]
+    big_p, big_v = ev.eval_ensemble(pb, vb, temp)
+    one_p, _ = ev.eval_ensemble(pb[40:41], None, temp)
+    _, one_v = ev.eval_ensemble(None, vb[76:77], temp)
+    np.testing.assert_array_equal(big_p[40], one_p[0])
+    np.testing.assert_array_equal(big_v[76], one_v[0])
+    assert np.allclose(big_p.sum(1), 1.0, atol=1e-4) and (big_v > 0).all() and (big_v < 1).all()
+
+
 def test_softmax_temperature_is_runtime(ev, ref_golden, oracle_nets):
     from oracle import oracle
     g = ref_golden
