@@ -16,6 +16,24 @@
 
 namespace lb2 {
 
+// tuning knobs (tools/ab_variants.py builds variants side by side)
+#ifndef LB2_PROBE_TAP
+#define LB2_PROBE_TAP 4   // tap after which the MMA issuer probes the next stage; < 0: before the stage's MMAs
+#endif
+#ifndef LB2_RING_SLEEP
+#define LB2_RING_SLEEP 64 // ns between polls of the work-item ring by the scout / publisher / stage forwarder
+#endif
+#ifndef LB2_EPI_GROUP
+#define LB2_EPI_GROUP 2   // 8-column TMEM loads the epilogue issues back to back
+#endif
+constexpr int kEpiGroup = LB2_EPI_GROUP;
+#ifndef LB2_PDL
+#define LB2_PDL 0         // trunk and heads start under programmatic dependent launch (prologue overlaps the predecessor's tail)
+#endif
+#ifndef LB2_EPI_PIPE
+#define LB2_EPI_PIPE 1    // epilogue keeps the TMEM loads of the next two units in flight
+#endif
+
 // Network::rotate_nn_idx (Network.cpp:1348-1379): bit2 swaps x/y first, bit0 flips y, bit1 flips x.
 __device__ __forceinline__ int rotate_idx(int v, int s) {
     int x = v % kBoard, y = v / kBoard;
@@ -37,6 +55,7 @@ __device__ __forceinline__ float elu1(float v) { return v > 0.0f ? v : (__expf(v
 // 8 fp16. Spare threads prefetch a read-late buffer into L2.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) expand_planes_kernel(const ExpandArgs A) {
+    if (LB2_PDL) grid_dep_launch();   // the trunk may set itself up while we run; it waits for us before reading
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t == 0 && A.zero_word) *A.zero_word = 0;
     const size_t per_net = (size_t)A.n * 441;
@@ -136,20 +155,6 @@ __device__ __forceinline__ void locate_item(const TrunkParams& P, const LayerJob
     else { job = na > nb ? a : b; idx = local - m; }
 }
 
-// tuning knobs (tools/ab_variants.py builds variants side by side)
-#ifndef LB2_PROBE_TAP
-#define LB2_PROBE_TAP 4   // tap after which the MMA issuer probes the next stage; < 0: before the stage's MMAs
-#endif
-#ifndef LB2_RING_SLEEP
-#define LB2_RING_SLEEP 64 // ns between polls of the work-item ring by the scout / publisher / stage forwarder
-#endif
-#ifndef LB2_EPI_GROUP
-#define LB2_EPI_GROUP 2   // 8-column TMEM loads the epilogue issues back to back
-#endif
-constexpr int kEpiGroup = LB2_EPI_GROUP;
-#ifndef LB2_EPI_PIPE
-#define LB2_EPI_PIPE 1    // epilogue keeps the TMEM loads of the next two units in flight
-#endif
 constexpr int kClaimRing = 16;  // work-item ring entries per CTA (claimed-but-unpublished items)
 constexpr int kClaimAhead = 4;  // how far ahead of the last published item the scout may hand out items
 constexpr uint32_t kEndJob = 31;  // job field of the ring entry that ends a CTA's walk
@@ -252,6 +257,12 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
     __syncthreads();
     if (kPair) cluster_sync_all();  // the peer's barriers and ring are initialised before anyone signals them
     tc_fence_after_sync();
+    if (LB2_PDL) {
+        // everything above touched only launch-invariant data (weights, job table); the activations,
+        // flags and the item counter belong to the predecessor in the stream until it has completed
+        grid_dep_wait();
+        grid_dep_launch();
+    }
     const uint32_t tmem_base = *tmem_slot;
     jobs = jobs_s;  // from here on every role reads the shared-memory copy
     if (P.trace && threadIdx.x == 0) {  // effective SM clock: cycle and wall timestamps at both ends
@@ -666,6 +677,7 @@ __device__ __forceinline__ void policy_head_body(const float* __restrict__ zbuf,
     float* sm = smem_f;            // [361]
     float* red = smem_f + 368;     // [12]
     const int tid = threadIdx.x;
+    if (LB2_PDL) grid_dep_wait();
     if (tid >= 384) return;        // 12 warps do the work (no block-wide barrier below this point involves the rest)
     float logit = -INFINITY;
     if (tid < kPoints) {
@@ -695,7 +707,12 @@ __device__ __forceinline__ void policy_head_body(const float* __restrict__ zbuf,
 // copy bandwidth instead of one L2/HBM round trip per unrolled load batch.
 constexpr int kValueGroup = 4;
 constexpr int kValueThreads = 1024;  // thread (o, part): output o, input rows part, part+4, ... of each tile
-constexpr int kVTileRows = 19, kVTiles = 19, kVSlots = 4;
+#ifndef LB2_VTILE_ROWS
+#define LB2_VTILE_ROWS 64
+#endif
+constexpr int kVTileRows = LB2_VTILE_ROWS;                      // rows of the 361 x H matrix per ring slot
+constexpr int kVTiles = (kPoints + kVTileRows - 1) / kVTileRows;
+constexpr int kVSlots = kVTileRows >= 48 ? 3 : 4;
 
 __device__ __forceinline__ void value_head_body(const float* __restrict__ zbuf, int chunk_rows,
                                                 const float* __restrict__ bias,
@@ -710,16 +727,18 @@ __device__ __forceinline__ void value_head_body(const float* __restrict__ zbuf, 
     uint64_t* full = reinterpret_cast<uint64_t*>(part_s + 3 * kValueGroup * hidden);  // [kVSlots]
     const int tid = threadIdx.x;
     const int pos0 = block * kValueGroup;
-    const uint32_t tile_bytes = kVTileRows * hidden * sizeof(float);
+    auto tile_rows = [](int t) { return min(kVTileRows, kPoints - t * kVTileRows); };
+    auto tile_bytes = [&](int t) { return (uint32_t)(tile_rows(t) * hidden * sizeof(float)); };
     if (tid == 0) {
         for (int i = 0; i < kVSlots; i++) mbar_init(full + i, 1);
         fence_mbar_init();
         fence_proxy_async_smem();
-        for (int t = 0; t < kVSlots - 1; t++) {  // prefetch distance 3
-            mbar_arrive_expect_tx(full + t, tile_bytes);
-            bulk_load_1d(w_s + t * kVTileRows * hidden, ip1_wt + (size_t)t * kVTileRows * hidden, tile_bytes, full + t);
+        for (int t = 0; t < kVSlots - 1 && t < kVTiles; t++) {  // prefetch distance kVSlots - 1
+            mbar_arrive_expect_tx(full + t, tile_bytes(t));
+            bulk_load_1d(w_s + t * kVTileRows * hidden, ip1_wt + (size_t)t * kVTileRows * hidden, tile_bytes(t), full + t);
         }
     }
+    if (LB2_PDL) grid_dep_wait();   // the weight tiles above do not depend on the trunk; zbuf does
     for (int i = tid; i < kValueGroup * kPoints; i += blockDim.x) {
         const int g = i / kPoints, p = i - g * kPoints;
         float v = 0.0f;
@@ -739,21 +758,19 @@ __device__ __forceinline__ void value_head_body(const float* __restrict__ zbuf, 
         mbar_wait(full + slot, (t / kVSlots) & 1);
         if (part < n_parts) {
             const float* wt = w_s + slot * kVTileRows * hidden + o;
-#pragma unroll
-            for (int r = 0; r < 5; r++) {
-                const int row = part + r * n_parts;   // n_parts == 4 for hidden == 256
-                if (row < kVTileRows) {
-                    const float wv = wt[row * hidden];
-                    const float4 v0 = *reinterpret_cast<const float4*>(v_s + (t * kVTileRows + row) * kValueGroup);
-                    a[0] = fmaf(wv, v0.x, a[0]); a[1] = fmaf(wv, v0.y, a[1]); a[2] = fmaf(wv, v0.z, a[2]); a[3] = fmaf(wv, v0.w, a[3]);
-                }
+            const int rows = tile_rows(t);
+#pragma unroll 4
+            for (int row = part; row < rows; row += n_parts) {   // n_parts == 4 for hidden == 256
+                const float wv = wt[row * hidden];
+                const float4 v0 = *reinterpret_cast<const float4*>(v_s + (t * kVTileRows + row) * kValueGroup);
+                a[0] = fmaf(wv, v0.x, a[0]); a[1] = fmaf(wv, v0.y, a[1]); a[2] = fmaf(wv, v0.z, a[2]); a[3] = fmaf(wv, v0.w, a[3]);
             }
         }
         __syncthreads();  // everyone is done with this slot's predecessor: refill it
         if (tid == 0 && t + kVSlots - 1 < kVTiles) {
             const int tn = t + kVSlots - 1, sn = tn % kVSlots;
-            mbar_arrive_expect_tx(full + sn, tile_bytes);
-            bulk_load_1d(w_s + sn * kVTileRows * hidden, ip1_wt + (size_t)tn * kVTileRows * hidden, tile_bytes, full + sn);
+            mbar_arrive_expect_tx(full + sn, tile_bytes(tn));
+            bulk_load_1d(w_s + sn * kVTileRows * hidden, ip1_wt + (size_t)tn * kVTileRows * hidden, tile_bytes(tn), full + sn);
         }
     }
     if (part > 0 && part < n_parts) {
@@ -833,7 +850,7 @@ cudaError_t trunk_kernel_setup() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(trunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytes);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    return cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
 }
 
 cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool pair, cudaStream_t st) {
@@ -842,8 +859,13 @@ cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool 
     cfg.blockDim = dim3(kTrunkThreads);
     cfg.dynamicSmemBytes = kTrunkSmemBytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[3];
     int na = 0;
+    if (LB2_PDL && pair) {   // (the single-CTA form is a cooperative launch, which excludes it)
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        na++;
+    }
     if (pair) {
         // CTA pairs: clusters of 2 are always co-scheduled; with one CTA per SM and grid <= #SMs
         // every cluster is resident, which is all the dataflow needs
@@ -867,8 +889,17 @@ cudaError_t launch_heads(const HeadArgs& a, cudaStream_t st) {
     size_t smem = 2048;  // policy head scratch
     if (a.n_value)
         smem = ((size_t)kVSlots * kVTileRows * a.hidden + kValueGroup * kPoints + 4 * kValueGroup * a.hidden) * sizeof(float) + 64;
-    heads_kernel<<<blocks, kValueThreads, smem, st>>>(a);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(kValueThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = LB2_PDL ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, heads_kernel, a);
 }
 
 }  // namespace lb2

@@ -84,6 +84,14 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
         : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (and run its
+// prologue) while its predecessor in the stream is still finishing; grid_dep_wait() blocks until the
+// predecessor has completed and its writes are visible. grid_dep_launch() in the predecessor lets
+// the successor's CTAs be scheduled as soon as resources free up.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- proxies / fences
 // generic-proxy writes (st.shared / st.global) -> visible to the async proxy (TMA, tcgen05)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
