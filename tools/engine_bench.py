@@ -46,6 +46,9 @@ def run(cmd, script, env=None, timeout=1200):
 
 def summarize(name, rc, text, per_move, moves, wall, extra):
     out = {"engine": name, "rc": rc, "moves": moves, "per_move": per_move, "wall_s": round(wall, 1)}
+    nb = re.findall(r"(\d+) (predictions|evaluations) in\s+([\d.]+) seconds -> (\d+) p/s", text)
+    if nb:
+        out["netbench"] = {what: {"n": int(n), "seconds": float(sec), "per_s": int(ps)} for n, what, sec, ps in nb}
     if per_move:
         out["playouts_per_s_mean"] = sum(m["playouts_per_s"] for m in per_move) / len(per_move)
         out["playouts_total"] = sum(m["playouts"] for m in per_move)
@@ -54,7 +57,7 @@ def summarize(name, rc, text, per_move, moves, wall, extra):
         out["nn_positions"] = int(m.group(1)); out["device_batches"] = int(m.group(2))
         out["mean_device_batch"] = float(m.group(3)); out["nn_requests"] = int(m.group(4))
     out.update(extra)
-    if rc != 0 or not per_move:
+    if rc != 0 or (not per_move and not nb):
         out["tail"] = text[-1500:]
     return out
 
@@ -68,9 +71,10 @@ def main():
     ap.add_argument("--impl", default="both", choices=["ours", "reference", "both"])
     ap.add_argument("--max-outstanding", type=int, default=2)
     ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--netbench", action="store_true", help="run the GTP `netbench` command (Network::benchmark) instead of genmove")
     ap.add_argument("--extra", default="", help="extra engine options for ours, e.g. '--mature_threshold 2 --eval_thresh 0'")
     args = ap.parse_args()
-    script = gtp_script(args.seconds, args.moves)
+    script = gtp_script(args.seconds, args.moves) if not args.netbench else "boardsize 19\nclear_board\nnetbench\nquit\n"
     results = []
     if args.impl in ("ours", "both"):
         if not os.path.exists(WEIGHTS):
