@@ -71,9 +71,10 @@ int lb2_net_push_conv(lb2_net* net, int k, int c_in, int c_out, const float* w_o
 int lb2_net_push_ip(lb2_net* net, int n_in, int n_out, const float* w, const float* bias);
 
 /* Repacks the weights for the tensor-core kernels and replicates them to every device.
- * Supported stacks: a 5x5 conv from 32 planes, then 3x3 convs of constant width
- * (c_out a multiple of 16, <= 128), then a 3x3 conv to 1 channel; the value net adds
- * innerproduct 361 -> H (H <= 256) and H -> 1. That covers NN128 and NNValue. */
+ * Supported stacks: a 5x5 conv from 32 planes, then 3x3 convs (c_out a multiple of 32 up to 128,
+ * or a multiple of 64 up to 256 — run as two column splits), then a 3x3 conv to 1 channel; the value
+ * net adds innerproduct 361 -> H (H <= 256) and H -> 1. That covers NN128 (Network.cpp:82-107),
+ * the 192-wide OpenCL-build policy net (Network.cpp:55-80) and NNValue (Network.cpp:110-137). */
 int lb2_net_finalize(lb2_net* net);
 
 /* Replace OpenCL_Network::forward (OpenCL.cpp:490-569) for a BATCH of n positions (the

@@ -67,21 +67,23 @@ struct HostIp {
     std::vector<float> w, b;
 };
 
+// One trunk layer on a device. A layer wider than 128 output channels is stored (and later run) as
+// n_split column splits of c_out / n_split channels each, every split packed like a layer of its own.
 struct TrunkLayerDev {
     int k, c_in, c_out;
-    __half* wpk = nullptr;
-    __half* wpk2 = nullptr;  // CTA-pair packing
-    float* bias = nullptr;
+    int n_split = 1;
+    __half* wpk[lb2::kMaxSplit] = {nullptr, nullptr};
+    __half* wpk2[lb2::kMaxSplit] = {nullptr, nullptr};  // CTA-pair packing
+    float* bias[lb2::kMaxSplit] = {nullptr, nullptr};
 };
 
 // One net replicated on one device, with its workspace.
 struct NetDev {
     std::vector<TrunkLayerDev> trunk;
     int head_c_in = 0;
-    float *head_wt = nullptr, *head_b = nullptr;  // final conv weights transposed to [9 taps][c_in]
+    float *head_wt[lb2::kMaxSplit] = {nullptr, nullptr};  // final conv weights per column split of the last trunk layer, [9 taps][c_in / n_split]
+    float* head_b = nullptr;
     float* zbuf = nullptr;                        // fused-head partial sums [2][9][rows3]
-    std::vector<std::vector<float>> h_bias;       // host copies for the constant-memory tables
-    std::vector<float> h_head_wt;
     int hidden = 0;
     float *ip1_wt = nullptr, *ip1_b = nullptr, *ip2_w = nullptr, *ip2_b = nullptr;
     // workspace
@@ -241,36 +243,49 @@ int upload(T** dst, const void* src, size_t bytes) {
     return LB2_OK;
 }
 
+int n_splits(int c_out) { return c_out > 128 ? 2 : 1; }
+
 int upload_net(const lb2_net* net, NetDev* nd) {
     const size_t nconv = net->convs.size();
     nd->trunk.clear();
-    nd->h_bias.clear();
     nd->width = 0;
     for (size_t l = 0; l + 1 < nconv; l++) {
         const HostConv& c = net->convs[l];
         TrunkLayerDev t;
         t.k = c.k; t.c_in = c.c_in; t.c_out = c.c_out;
-        std::vector<__half> pk = pack_trunk_weights(c);
-        int rc = upload(&t.wpk, pk.data(), pk.size() * sizeof(__half));
-        if (rc) return rc;
-        std::vector<__half> pk2 = pack_trunk_weights_pair(c);
-        rc = upload(&t.wpk2, pk2.data(), pk2.size() * sizeof(__half));
-        if (rc) return rc;
-        rc = upload(&t.bias, c.b.data(), c.b.size() * sizeof(float));
-        if (rc) return rc;
-        nd->h_bias.push_back(c.b);
+        t.n_split = n_splits(c.c_out);
+        const int w = c.c_out / t.n_split;
+        for (int sp = 0; sp < t.n_split; sp++) {
+            HostConv part;   // output channels [sp*w, (sp+1)*w): a contiguous block of the OIHW array
+            part.k = c.k; part.c_in = c.c_in; part.c_out = w;
+            const size_t per_out = (size_t)c.c_in * c.k * c.k;
+            part.w.assign(c.w.begin() + (size_t)sp * w * per_out, c.w.begin() + (size_t)(sp + 1) * w * per_out);
+            part.b.assign(c.b.begin() + sp * w, c.b.begin() + (sp + 1) * w);
+            std::vector<__half> pk = pack_trunk_weights(part);
+            int rc = upload(&t.wpk[sp], pk.data(), pk.size() * sizeof(__half));
+            if (rc) return rc;
+            std::vector<__half> pk2 = pack_trunk_weights_pair(part);
+            rc = upload(&t.wpk2[sp], pk2.data(), pk2.size() * sizeof(__half));
+            if (rc) return rc;
+            rc = upload(&t.bias[sp], part.b.data(), part.b.size() * sizeof(float));
+            if (rc) return rc;
+        }
         nd->trunk.push_back(t);
         nd->width = std::max(nd->width, c.c_out);
     }
     const HostConv& h = net->convs.back();
     nd->head_c_in = h.c_in;
-    std::vector<float> hwt((size_t)9 * h.c_in);
-    for (int c = 0; c < h.c_in; c++)
-        for (int t = 0; t < 9; t++) hwt[(size_t)t * h.c_in + c] = h.w[(size_t)c * 9 + t];
-    int rc = upload(&nd->head_wt, hwt.data(), hwt.size() * sizeof(float));
-    if (rc) return rc;
-    nd->h_head_wt = hwt;
-    rc = upload(&nd->head_b, h.b.data(), sizeof(float));
+    {
+        const int ns = n_splits(h.c_in), w = h.c_in / ns;
+        for (int sp = 0; sp < ns; sp++) {
+            std::vector<float> hwt((size_t)9 * w);
+            for (int c = 0; c < w; c++)
+                for (int t = 0; t < 9; t++) hwt[(size_t)t * w + c] = h.w[(size_t)(sp * w + c) * 9 + t];
+            int rc = upload(&nd->head_wt[sp], hwt.data(), hwt.size() * sizeof(float));
+            if (rc) return rc;
+        }
+    }
+    int rc = upload(&nd->head_b, h.b.data(), sizeof(float));
     if (rc) return rc;
     if (net->kind == LB2_VALUE) {
         const HostIp& a = net->ips[0];
@@ -330,10 +345,11 @@ int ensure_workspace(NetDev* nd, int kind, int cap) {
     CU_TRY(cudaMemset(nd->act[1], 0, act_bytes));
     const size_t out_elems = kind == LB2_POLICY ? (size_t)cap * lb2::kPoints : (size_t)cap;
     CU_TRY(cudaMalloc(&nd->out, out_elems * sizeof(float)));
-    CU_TRY(cudaMalloc(&nd->zbuf, (size_t)9 * lb2::kColParts * nd->rows3 * sizeof(float)));
+    CU_TRY(cudaMalloc(&nd->zbuf, (size_t)9 * lb2::kColParts * lb2::kMaxSplit * nd->rows3 * sizeof(float)));
     nd->flags_stride = nd->rows5 / lb2::kTileRows + 2;
-    CU_TRY(cudaMalloc(&nd->flags, (size_t)lb2::kMaxJobs * nd->flags_stride * sizeof(uint32_t)));
-    CU_TRY(cudaMemset(nd->flags, 0, (size_t)lb2::kMaxJobs * nd->flags_stride * sizeof(uint32_t)));
+    const size_t n_flags = (size_t)lb2::kMaxLayers * lb2::kMaxSplit * nd->flags_stride;
+    CU_TRY(cudaMalloc(&nd->flags, n_flags * sizeof(uint32_t)));
+    CU_TRY(cudaMemset(nd->flags, 0, n_flags * sizeof(uint32_t)));
     int rc;
     if ((rc = make_act_tmap(&nd->tm_x0, nd->x0, nd->rows5, 4, 48))) return rc;
     if ((rc = make_act_tmap(&nd->tm_act[0], nd->act[0], nd->rows3, nd->width / 8, 24))) return rc;
@@ -369,59 +385,68 @@ struct JobPlan {
     int tmap_base[2] = {0, 3};
 };
 
-// Interleave the two nets layer by layer: P1 V1 P2 V2 ... so that one launch round holds
-// independent jobs of equal depth.
+// Interleave the two nets layer by layer: P1 V1 P2a P2b V2 ... so that one launch round holds the
+// independent jobs of equal depth (a layer wider than 128 channels contributes one job per column
+// split; they are consecutive in the table).
 JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2], bool pair) {
     JobPlan pl;
     size_t depth = 0;
     for (int k = 0; k < 2; k++)
         if (run[k]) depth = std::max(depth, (size_t)std::min<int>(limit_layers[k], d->net[k].trunk.size()));
-    int prev_job[2] = {-1, -1};
+    int prev_job[2] = {-1, -1}, prev_split[2] = {1, 1};
     for (size_t l = 0; l < depth; l++) {
         for (int k = 0; k < 2; k++) {
             NetDev& nd = d->net[k];
             if (!run[k] || l >= nd.trunk.size() || (int)l >= limit_layers[k]) continue;
             const TrunkLayerDev& t = nd.trunk[l];
-            lb2::LayerJob J;
-            memset(&J, 0, sizeof J);
-            const bool first = (l == 0);
-            J.S = first ? 21 : 20;
-            J.ksize = t.k;
-            J.halo = first ? 48 : 24;
-            J.n_slabs = t.c_in / 16;
-            J.n_out = t.c_out;
-            const int n_tiles = (n * J.S * J.S + lb2::kTileRows - 1) / lb2::kTileRows;
-            J.n_items = pair ? (n_tiles + 1) / 2 : n_tiles;
-            J.item_base = pl.total_items;
-            J.remap = first ? 1 : 0;
-            // buffers: x0 -> act0 -> act1 -> act0 ...
-            J.tmap = pl.tmap_base[k] + (first ? 0 : 1 + (int)((l - 1) & 1));
-            J.out = nd.act[l & 1];
-            J.out_chunk_rows = nd.rows3;
-            J.dep_job = prev_job[k];
-            if (J.dep_job >= 0) {
-                J.dep_remap = pl.jobs[J.dep_job].remap;
-                J.dep_n_items = pl.tiles[J.dep_job];
+            const int first_job = (int)pl.jobs.size();
+            const int w = t.c_out / t.n_split;
+            for (int sp = 0; sp < t.n_split; sp++) {
+                lb2::LayerJob J;
+                memset(&J, 0, sizeof J);
+                const bool first = (l == 0);
+                J.S = first ? 21 : 20;
+                J.ksize = t.k;
+                J.halo = first ? 48 : 24;
+                J.n_slabs = t.c_in / 16;
+                J.n_out = w;
+                const int n_tiles = (n * J.S * J.S + lb2::kTileRows - 1) / lb2::kTileRows;
+                J.n_items = pair ? (n_tiles + 1) / 2 : n_tiles;
+                J.item_base = pl.total_items;
+                J.remap = first ? 1 : 0;
+                // buffers: x0 -> act0 -> act1 -> act0 ...; a split writes its own chunk planes
+                J.tmap = pl.tmap_base[k] + (first ? 0 : 1 + (int)((l - 1) & 1));
+                J.out = nd.act[l & 1] + (size_t)(sp * w / 8) * nd.rows3 * 8;
+                J.out_chunk_rows = nd.rows3;
+                J.dep_job = prev_job[k];
+                if (J.dep_job >= 0) {
+                    J.dep_n_split = prev_split[k];
+                    J.dep_remap = pl.jobs[J.dep_job].remap;
+                    J.dep_n_items = pl.tiles[J.dep_job];
+                }
+                J.n_pos = n;
+                J.net = k;
+                J.layer = (int)l;
+                J.wpk = t.wpk[sp];
+                J.wpk2 = t.wpk2[sp];
+                J.bias = t.bias[sp];
+                J.flags = nd.flags + ((size_t)l * lb2::kMaxSplit + sp) * nd.flags_stride;
+                J.head_slot = k * lb2::kMaxSplit + sp;
+                if (l + 1 == nd.trunk.size() && limit_layers[k] > (int)nd.trunk.size()) {
+                    // whole net: fold the final 3x3 conv to one channel into this layer's epilogue
+                    J.head_taps = 9;
+                    J.head_w = nd.head_wt[sp];
+                    J.zbuf = nd.zbuf;
+                    J.zparts = sp * lb2::kColParts;
+                }
+                pl.jobs.push_back(J);
+                pl.round_of.push_back((int)l);
+                pl.tiles.push_back(n_tiles);
+                pl.total_items += J.n_items;
+                pl.last_act[k] = nd.act[l & 1];
             }
-            J.n_pos = n;
-            J.net = k;
-            J.layer = (int)l;
-            J.wpk = t.wpk;
-            J.wpk2 = t.wpk2;
-            J.bias = t.bias;
-            J.flags = nd.flags + (size_t)l * nd.flags_stride;
-            if (l + 1 == nd.trunk.size() && limit_layers[k] > (int)nd.trunk.size()) {
-                // whole net: fold the final 3x3 conv to one channel into this layer's epilogue
-                J.head_taps = 9;
-                J.head_w = nd.head_wt;
-                J.zbuf = nd.zbuf;
-            }
-            prev_job[k] = (int)pl.jobs.size();
-            pl.jobs.push_back(J);
-            pl.round_of.push_back((int)l);
-            pl.tiles.push_back(n_tiles);
-            pl.total_items += J.n_items;
-            pl.last_act[k] = J.out;
+            prev_job[k] = first_job;
+            prev_split[k] = t.n_split;
         }
     }
     return pl;
@@ -464,9 +489,9 @@ int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers
     for (size_t i = 0; i < pl.jobs.size();) {
         size_t e = i;
         while (e < pl.jobs.size() && pl.round_of[e] == pl.round_of[i]) e++;
-        if (P.n_rounds >= lb2::kMaxRounds || e - i > 2) return fail(LB2_ERR_UNSUPPORTED, "too many layers");
-        P.round_a[P.n_rounds] = (int16_t)i;
-        P.round_b[P.n_rounds] = e - i == 2 ? (int16_t)(i + 1) : (int16_t)-1;
+        if (P.n_rounds >= lb2::kMaxRounds || e - i > (size_t)lb2::kMaxRoundJobs) return fail(LB2_ERR_UNSUPPORTED, "too many layers");
+        P.round_first[P.n_rounds] = (int16_t)i;
+        P.round_jobs[P.n_rounds] = (int16_t)(e - i);
         int items = 0;
         for (size_t k = i; k < e; k++) items += pl.jobs[k].n_items;
         P.round_base[P.n_rounds + 1] = P.round_base[P.n_rounds] + items;
@@ -558,11 +583,13 @@ int eval_on_device(lb2_ctx* ctx, DeviceState* d, const uint32_t* d_pol, const ui
     if (run[0]) {
         NetDev& nd = d->net[0];
         ha.p_zbuf = nd.zbuf; ha.p_chunk_rows = nd.rows3; ha.p_bias = nd.head_b; ha.probs = d_probs; ha.n_policy = n;
+        ha.p_parts = nd.trunk.back().n_split * lb2::kColParts;
     }
     if (run[1]) {
         NetDev& nd = d->net[1];
         ha.v_zbuf = nd.zbuf; ha.v_chunk_rows = nd.rows3; ha.v_bias = nd.head_b; ha.ip1_wt = nd.ip1_wt; ha.ip1_b = nd.ip1_b;
         ha.hidden = nd.hidden; ha.ip2_w = nd.ip2_w; ha.ip2_b = nd.ip2_b; ha.winrate = d_win; ha.n_value = n;
+        ha.v_parts = nd.trunk.back().n_split * lb2::kColParts;
     }
     CU_TRY(lb2::launch_heads(ha, st));
     ctx->launches++;
@@ -904,8 +931,10 @@ void lb2_destroy(lb2_ctx* ctx) {
         cudaStreamSynchronize(d.stream);
         for (int k = 0; k < 2; k++) {
             NetDev& nd = d.net[k];
-            for (auto& t : nd.trunk) { cudaFree(t.wpk); cudaFree(t.wpk2); cudaFree(t.bias); }
-            cudaFree(nd.head_wt); cudaFree(nd.head_b); cudaFree(nd.ip1_wt); cudaFree(nd.ip1_b);
+            for (auto& t : nd.trunk)
+                for (int sp = 0; sp < lb2::kMaxSplit; sp++) { cudaFree(t.wpk[sp]); cudaFree(t.wpk2[sp]); cudaFree(t.bias[sp]); }
+            for (int sp = 0; sp < lb2::kMaxSplit; sp++) cudaFree(nd.head_wt[sp]);
+            cudaFree(nd.head_b); cudaFree(nd.ip1_wt); cudaFree(nd.ip1_b);
             cudaFree(nd.ip2_w); cudaFree(nd.ip2_b);
             free_workspace(&nd);
         }
@@ -967,7 +996,9 @@ int lb2_net_finalize(lb2_net* net) {
     for (size_t l = 0; l + 1 < cv.size(); l++) {
         if (l >= (size_t)lb2::kMaxLayers) return fail(LB2_ERR_UNSUPPORTED, "too many layers");
         if (l > 0 && cv[l].k != 3) return fail(LB2_ERR_UNSUPPORTED, "layer %zu: only 3x3 after the first layer", l + 1);
-        if (cv[l].c_out % 32 || cv[l].c_out > 128 || cv[l].c_in % 16)
+        // widths up to 128 run as one job (MMA N = c_out), up to 256 as two column splits of c_out / 2
+        const bool ok_out = cv[l].c_out <= 128 ? cv[l].c_out % 32 == 0 : (cv[l].c_out <= 256 && cv[l].c_out % 64 == 0);
+        if (!ok_out || cv[l].c_in % 16 || cv[l].c_in > 256)
             return fail(LB2_ERR_UNSUPPORTED, "layer %zu: channels %d->%d not supported", l + 1, cv[l].c_in, cv[l].c_out);
     }
     if (cv.back().k != 3 || cv.back().c_out != 1) return fail(LB2_ERR_UNSUPPORTED, "last conv must be 3x3 to 1 channel");

@@ -142,36 +142,52 @@ __device__ __forceinline__ float elu_fast(float v) {
 }
 
 // Item index -> (job, item within the job). Rounds are consecutive in the launch-wide order; inside
-// a round the items of its two jobs (policy layer l, value layer l) alternate, so that at any time
-// every cluster works on a mix of wide/long and narrow/short items instead of the whole GPU
-// switching between the two regimes. `r` is the caller's monotonically advancing round cursor.
+// a round the items of its jobs (policy layer l — possibly as two column-split jobs — and value
+// layer l) are dealt round robin, so that at any time every cluster works on a mix of wide/long and
+// narrow/short items instead of the whole GPU switching between regimes. Cycle c of the deal gives
+// one item to every job that still has more than c. `r` is the caller's monotonically advancing
+// round cursor. Only the scout warp runs this, once per item.
 __device__ __forceinline__ void locate_item(const TrunkParams& P, const LayerJob* jobs, int q, int& r, int& job, int& idx) {
     while (q >= P.round_base[r + 1]) r++;
-    const int local = q - P.round_base[r];
-    const int a = P.round_a[r], b = P.round_b[r];
-    const int na = jobs[a].n_items, nb = b >= 0 ? jobs[b].n_items : 0;
-    const int m = na < nb ? na : nb;
-    if (local < 2 * m) { job = (local & 1) ? b : a; idx = local >> 1; }
-    else { job = na > nb ? a : b; idx = local - m; }
+    int local = q - P.round_base[r];
+    const int first = P.round_first[r], m = P.round_jobs[r];
+    int done = 0;   // cycles dealt so far
+    for (;;) {
+        int active = 0, shortest = 0x7fffffff;
+        for (int k = 0; k < m; k++) {
+            const int n = jobs[first + k].n_items;
+            if (n > done) { active++; shortest = n < shortest ? n : shortest; }
+        }
+        const int phase = active * (shortest - done);   // items dealt until the shortest active job runs out
+        if (local < phase) {
+            idx = done + local / active;
+            int nth = local % active;
+            for (int k = 0; k < m; k++)
+                if (jobs[first + k].n_items > done && nth-- == 0) { job = first + k; return; }
+        }
+        local -= phase;
+        done = shortest;
+    }
 }
 
 constexpr int kClaimRing = 16;  // work-item ring entries per CTA (claimed-but-unpublished items)
 constexpr int kClaimAhead = 4;  // how far ahead of the last published item the scout may hand out items
-constexpr uint32_t kEndJob = 31;  // job field of the ring entry that ends a CTA's walk
+constexpr uint32_t kEndJob = 63;  // job field of the ring entry that ends a CTA's walk
 
 // Work-item ring. The scout warp of the cluster leader decides which item the cluster processes
 // k-th (static: round robin over the launch's item list; dynamic: the next one of a global in-order
 // counter — greedy list scheduling, still strictly increasing per cluster), resolves it to
-// (job, index within the job) ONCE and writes a 32-bit entry [tag:6 | job:5 | index:21] into the
+// (job, index within the job) ONCE and writes a 32-bit entry [tag:5 | job:6 | index:21] into the
 // ring of every CTA of the cluster. All other roles just read entry k: one shared-memory load,
 // no search through the round table, no acquire fence (tag and payload share the word).
-__device__ __forceinline__ uint32_t item_tag(uint32_t k) { return ((k / kClaimRing) & 31u) + 1u; }
+__device__ __forceinline__ uint32_t item_tag(uint32_t k) { return ((k / kClaimRing) & 15u) + 1u; }   // 1..16, never 0
+static_assert(kMaxLaunchJobs < (int)kEndJob, "job field of the item ring");
 __device__ __forceinline__ uint32_t item_pack(uint32_t k, uint32_t job, uint32_t idx) {
-    return (item_tag(k) << 26) | (job << 21) | idx;
+    return (item_tag(k) << 27) | (job << 21) | idx;
 }
 __device__ __forceinline__ bool item_peek(const uint32_t* ring, uint32_t k, uint32_t& v) {
     v = ld_volatile_shared(ring + k % kClaimRing);
-    return (v >> 26) == item_tag(k);
+    return (v >> 27) == item_tag(k);
 }
 // blocking read of entry k; false at the end marker. `relaxed`: roles off the critical path back off
 // between polls so their spinning stays off the shared-memory port the tensor core reads through.
@@ -179,17 +195,17 @@ template <bool relaxed = false>
 __device__ __forceinline__ bool item_get(const uint32_t* ring, uint32_t k, int& job, int& idx) {
     uint32_t v;
     while (!item_peek(ring, k, v)) { if (relaxed && LB2_RING_SLEEP) __nanosleep(LB2_RING_SLEEP); }
-    job = (int)((v >> 21) & 31u);
+    job = (int)((v >> 21) & 63u);
     idx = (int)(v & 0x1fffffu);
     return job != (int)kEndJob;
 }
 
 // The MMA issuer's own ring: everything it needs to know about item k in one word
-// [tag:6 | end:1 | 5x5:1 | halo/8:4 | c_in/16:6 | c_out/8:6 | S:8], so that a single shared-memory
+// [tag:5 | end:1 | 5x5:1 | halo/8:4 | c_in/16:6 | c_out/8:6 | S:8], so that a single shared-memory
 // load separates the last MMA of one item from the first of the next.
 __device__ __forceinline__ uint32_t geom_pack(uint32_t k, const LayerJob* J) {
-    if (!J) return (item_tag(k) << 26) | (1u << 25);
-    return (item_tag(k) << 26) | ((J->ksize == 5 ? 1u : 0u) << 24) | ((uint32_t)(J->halo >> 3) << 20) |
+    if (!J) return (item_tag(k) << 27) | (1u << 25);
+    return (item_tag(k) << 27) | ((J->ksize == 5 ? 1u : 0u) << 24) | ((uint32_t)(J->halo >> 3) << 20) |
            ((uint32_t)J->n_slabs << 14) | ((uint32_t)(J->n_out >> 3) << 8) | (uint32_t)J->S;
 }
 
@@ -211,8 +227,8 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
     uint32_t* geom_ring = item_ring + kClaimRing;  // [kClaimRing] the MMA issuer's view of them (see geom_pack)
     // broadcast reads (one wavefront per warp-wide LDS.128), resident for the whole launch
     float* bias_all = reinterpret_cast<float*>(smem + kTrunkRingBytes + kCtrlBytes);   // [kMaxLaunchJobs][128]
-    float* headw_all = bias_all + kMaxLaunchJobs * 128;                         // [2 nets][9][128]
-    LayerJob* jobs_s = reinterpret_cast<LayerJob*>(headw_all + 2 * 9 * 128);    // [kMaxLaunchJobs] job table copy
+    float* headw_all = bias_all + kMaxLaunchJobs * 128;                         // [kHeadSlots][9][128]
+    LayerJob* jobs_s = reinterpret_cast<LayerJob*>(headw_all + kHeadSlots * 9 * 128);    // [kMaxLaunchJobs] job table copy
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -250,7 +266,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
     }
     for (int jj = 0; jj < P.n_jobs; jj++) {
         if (!jobs[jj].head_taps) continue;
-        float* dst = headw_all + jobs[jj].net * (9 * 128);
+        float* dst = headw_all + jobs[jj].head_slot * (9 * 128);
         for (int i = threadIdx.x; i < 9 * jobs[jj].n_out; i += blockDim.x) dst[(i / jobs[jj].n_out) * 128 + i % jobs[jj].n_out] = jobs[jj].head_w[i];
     }
     tc_fence_before_sync();
@@ -436,7 +452,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             float* __restrict__ zbuf = J.zbuf;
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             const float* bs = bias_all + jj * 128;
-            const float* headw_s = headw_all + J.net * (9 * 128);
+            const float* headw_s = headw_all + J.head_slot * (9 * 128);
             const int cols = n_out / kColParts;   // columns handled by this warp
             const int col0 = part * cols;
             const int upc = cols >> 3;            // 8-column units per 128-row half tile
@@ -519,7 +535,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                             z[t] = fmaf(v[6], w1.z, z[t]); z[t] = fmaf(v[7], w1.w, z[t]);
                         }
                     }
-                    float* zb = zbuf + (size_t)part * 9 * chunk_rows + out_row2[h];
+                    float* zb = zbuf + (size_t)(J.zparts + part) * 9 * chunk_rows + out_row2[h];
 #pragma unroll
                     for (int t = 0; t < 9; t++) zb[(size_t)t * chunk_rows] = valid2[h] ? z[t] : 0.0f;
                 }
@@ -624,9 +640,11 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             if (P.use_flags && J.dep_job >= 0) {
                 int lo, hi;
                 dependency_range(J, tile_of(idx), lo, hi);
-                const uint32_t* flags = jobs[J.dep_job].flags;
-                if (lo + lane <= hi)
-                    while (ld_acquire_gpu(flags + lo + lane) != P.epoch) __nanosleep(20);
+                for (int sp = 0; sp < J.dep_n_split; sp++) {   // every column split of the producing layer
+                    const uint32_t* flags = jobs[J.dep_job + sp].flags;
+                    if (lo + lane <= hi)
+                        while (ld_acquire_gpu(flags + lo + lane) != P.epoch) __nanosleep(20);
+                }
             }
             __syncwarp();
             if (lane == 0) st_release_cta_shared(deps_ready, it + 1);
@@ -647,14 +665,13 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
 // heads. The 3x3 conv to one channel was folded into the last trunk layer's epilogue as per-tap
 // partial sums z[half][t][row]; what is left is a 9-point gather per board point.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float head_gather(const float* __restrict__ zbuf, int chunk_rows, int base_row, int y, int x) {
+__device__ __forceinline__ float head_gather(const float* __restrict__ zbuf, int chunk_rows, int n_parts, int base_row, int y, int x) {
     float acc = 0.0f;
 #pragma unroll
     for (int t = 0; t < 9; t++) {
         const int row = base_row + (y + t / 3 - 1) * 20 + (x + t % 3 - 1);
         if (row >= 0) {  // rows above the first position are implicit zero padding
-#pragma unroll
-            for (int p = 0; p < kColParts; p++) acc += zbuf[(size_t)(p * 9 + t) * chunk_rows + row];
+            for (int p = 0; p < n_parts; p++) acc += zbuf[(size_t)(p * 9 + t) * chunk_rows + row];
         }
     }
     return acc;
@@ -671,7 +688,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // policy head: one CTA per position. logit = ELU(b + conv), softmax with temperature over the
 // 361 points (Network.cpp:450-469), un-rotate (Network.cpp:820-823).
-__device__ __forceinline__ void policy_head_body(const float* __restrict__ zbuf, int chunk_rows,
+__device__ __forceinline__ void policy_head_body(const float* __restrict__ zbuf, int chunk_rows, int n_parts,
                                                  const float* __restrict__ bias, const uint8_t* __restrict__ rotation, int ensemble,
                                                  float temp, float* __restrict__ probs, int pos, float* smem_f) {
     float* sm = smem_f;            // [361]
@@ -682,7 +699,7 @@ __device__ __forceinline__ void policy_head_body(const float* __restrict__ zbuf,
     float logit = -INFINITY;
     if (tid < kPoints) {
         const int y = tid / kBoard, x = tid - y * kBoard;
-        logit = elu1(bias[0] + head_gather(zbuf, chunk_rows, pos * 400, y, x));
+        logit = elu1(bias[0] + head_gather(zbuf, chunk_rows, n_parts, pos * 400, y, x));
     }
     float m = warp_max(logit);
     if ((tid & 31) == 0) red[tid >> 5] = m;
@@ -714,7 +731,7 @@ constexpr int kVTileRows = LB2_VTILE_ROWS;                      // rows of the 3
 constexpr int kVTiles = (kPoints + kVTileRows - 1) / kVTileRows;
 constexpr int kVSlots = kVTileRows >= 48 ? 3 : 4;
 
-__device__ __forceinline__ void value_head_body(const float* __restrict__ zbuf, int chunk_rows,
+__device__ __forceinline__ void value_head_body(const float* __restrict__ zbuf, int chunk_rows, int n_zparts,
                                                 const float* __restrict__ bias,
                                                 const float* __restrict__ ip1_wt /*[361][hidden]*/,
                                                 const float* __restrict__ ip1_b, int hidden,
@@ -744,7 +761,7 @@ __device__ __forceinline__ void value_head_body(const float* __restrict__ zbuf, 
         float v = 0.0f;
         if (pos0 + g < n) {
             const int y = p / kBoard, x = p - y * kBoard;
-            v = elu1(bias[0] + head_gather(zbuf, chunk_rows, (pos0 + g) * 400, y, x));
+            v = elu1(bias[0] + head_gather(zbuf, chunk_rows, n_zparts, (pos0 + g) * 400, y, x));
         }
         v_s[p * kValueGroup + g] = v;
     }
@@ -802,10 +819,10 @@ __global__ void __launch_bounds__(kValueThreads) heads_kernel(const HeadArgs A) 
     extern __shared__ __align__(128) uint8_t hsm[];
     const int value_blocks = (A.n_value + kValueGroup - 1) / kValueGroup;
     if ((int)blockIdx.x < value_blocks)
-        value_head_body(A.v_zbuf, A.v_chunk_rows, A.v_bias, A.ip1_wt, A.ip1_b, A.hidden, A.ip2_w, A.ip2_b, A.n_value,
+        value_head_body(A.v_zbuf, A.v_chunk_rows, A.v_parts, A.v_bias, A.ip1_wt, A.ip1_b, A.hidden, A.ip2_w, A.ip2_b, A.n_value,
                         A.winrate, blockIdx.x, hsm);
     else
-        policy_head_body(A.p_zbuf, A.p_chunk_rows, A.p_bias, A.rotation, A.ensemble, A.temp, A.probs, blockIdx.x - value_blocks,
+        policy_head_body(A.p_zbuf, A.p_chunk_rows, A.p_parts, A.p_bias, A.rotation, A.ensemble, A.temp, A.probs, blockIdx.x - value_blocks,
                          reinterpret_cast<float*>(hsm));
 }
 

@@ -20,7 +20,7 @@ namespace lb2 {
 constexpr int kPoints = 361;
 constexpr int kBoard = 19;
 constexpr int kTileRows = 256;  // output rows per work item (two M=128 MMA halves)
-constexpr int kStagesSingle = 4;  // smem ring depth (A slab + B block per stage), one CTA per item
+constexpr int kStagesSingle = 3;  // smem ring depth (A slab + B block per stage), one CTA per item
 constexpr int kStagesPair = 6;    // CTA pairs stage only half of B, so the ring is deeper
 constexpr int kMaxHalo = 48;    // 5x5 conv in S=21 space needs 2*21+2 = 44 -> 48 (multiple of 8)
 constexpr int kASlabBytes = (kTileRows + 2 * kMaxHalo) * 32;  // rows x 16 ch x fp16
@@ -35,19 +35,23 @@ constexpr int kEpilogueWarps = LB2_EPI_WARPS;  // 8 or 16: TMEM lane quadrant (w
 constexpr int kColParts = kEpilogueWarps / 4;     // parts the output channels of a tile are split into
 // warp0 TMA producer, warp1 MMA issuer, warps2-9 epilogue, warp10 tile publisher, warp11 dependency scout
 constexpr int kTrunkThreads = 64 + 32 * kEpilogueWarps + 64;
-constexpr int kMaxLaunchJobs = 24;  // jobs whose biases are kept resident in smem
+constexpr int kMaxLaunchJobs = 40;  // jobs whose biases are kept resident in smem
+constexpr int kMaxSplit = 2;        // a layer wider than 128 channels runs as this many column-split jobs
+constexpr int kHeadSlots = 2 * kMaxSplit;  // fused-head weight sets resident in smem: [net][split]
 constexpr int kPubDepth = 4;        // tiles that may be waiting for publication
 // stages | mbarriers, TMEM slot, progress counters (256 B)
-constexpr int kRingBytesSingle = kStagesSingle * kStageBytesSingle;   // 192,512
+constexpr int kRingBytesSingle = kStagesSingle * kStageBytesSingle;   // 144,384
 constexpr int kRingBytesPair = kStagesPair * kStageBytesPair;         // 178,176
 constexpr int kTrunkRingBytes = kRingBytesSingle > kRingBytesPair ? kRingBytesSingle : kRingBytesPair;
-// ring | mbarriers etc. (256 B) | bias [jobs][128] f32 | fused-head weights [2 nets][9][128] f32 | job table
+// ring | mbarriers etc. | bias [jobs][128] f32 | fused-head weights [kHeadSlots][9][128] f32 | job table
 constexpr int kCtrlBytes = 384;  // mbarriers, TMEM slot, progress counters, claim ring
-constexpr int kTrunkSmemBytes = kTrunkRingBytes + kCtrlBytes + kMaxLaunchJobs * 128 * 4 + 2 * 9 * 128 * 4 + kMaxLaunchJobs * 160;
+constexpr int kTrunkSmemBytes = kTrunkRingBytes + kCtrlBytes + kMaxLaunchJobs * 128 * 4 + kHeadSlots * 9 * 128 * 4 + kMaxLaunchJobs * 160;
+static_assert(kTrunkSmemBytes <= 227 * 1024, "trunk kernel shared memory");
 constexpr int kMaxLayers = 16;
 constexpr int kMaxTensorMaps = 6;
-constexpr int kMaxJobs = 32;
-constexpr int kMaxRounds = 16;  // a round = the jobs of equal depth (one per net); their items are interleaved
+constexpr int kMaxJobs = 40;
+constexpr int kMaxRounds = 16;  // a round = the jobs of equal depth (all nets, all column splits); their items are interleaved
+constexpr int kMaxRoundJobs = 2 * kMaxSplit;
 constexpr int kTraceItems = 96;
 constexpr int kTraceEvents = 16;
 
@@ -59,16 +63,19 @@ struct LayerJob {
     int32_t ksize;           // 3 or 5
     int32_t halo;            // halo rows loaded each side of a tile (multiple of 8)
     int32_t n_slabs;         // c_in / 16
-    int32_t n_out;           // c_out = MMA N (multiple of 16, <= 128)
+    int32_t n_out;           // output channels of this job = MMA N (multiple of 32, <= 128); a wider layer is split
     int32_t tmap;            // index of the input buffer's tensor map
     int32_t remap;           // 1: outputs are re-addressed from S=21 space into S=20 space
-    int32_t dep_job;         // job producing this job's input in the same launch, or -1
-    int32_t dep_remap;       // that job's remap flag
+    int32_t dep_job;         // first job producing this job's input in the same launch, or -1
+    int32_t dep_n_split;     // ... and how many consecutive (column-split) jobs produce it
+    int32_t dep_remap;       // their remap flag
     int32_t dep_n_items;     // that job's tile count
     int32_t n_pos;           // positions in the batch
     int32_t out_chunk_rows;  // rows per chunk plane of the output buffer
     int32_t head_taps;       // 9: the net's final 3x3 conv to 1 channel is fused into this job's epilogue
-    int32_t net;             // 0 = policy, 1 = value: selects the constant-memory bias / head-weight tables
+    int32_t net;             // 0 = policy, 1 = value
+    int32_t head_slot;       // which resident fused-head weight set (net * kMaxSplit + split)
+    int32_t zparts;          // fused head: zbuf parts written before this job's (split * kColParts)
     int32_t layer;           // layer index within the net
     const __half* wpk;       // packed weights: per (slab, tap group): [tap][2 chunks][n_out][8]
     const __half* wpk2;      // CTA-pair packing: per (slab, tap group): [rank][tap][2 chunks][n_out/2][8]
@@ -76,7 +83,7 @@ struct LayerJob {
     __half* out;             // output activation buffer
     uint32_t* flags;         // [n_items] completion flags (value = launch epoch)
     const float* head_w;     // fused head weights [9 taps][n_out] fp32
-    float* zbuf;             // fused head output [kColParts channel parts][9 taps][out_chunk_rows] fp32
+    float* zbuf;             // fused head output [splits * kColParts channel parts][9 taps][out_chunk_rows] fp32
 };
 
 struct TrunkParams {
@@ -86,7 +93,7 @@ struct TrunkParams {
     int32_t item_begin, item_end;  // launch-wide item index range handled by this launch
     int32_t n_rounds;
     int32_t round_base[kMaxRounds + 1];             // first item index of each round
-    int16_t round_a[kMaxRounds], round_b[kMaxRounds];  // its jobs (round_b = -1 if only one)
+    int16_t round_first[kMaxRounds], round_jobs[kMaxRounds];  // its jobs: round_jobs consecutive entries of the job table
     uint32_t epoch;
     int32_t use_flags;  // 1: cross-CTA dataflow through flags (single persistent launch)
     uint32_t* next_item;        // dynamic scheduling: global in-order item counter (zero at launch), or null
@@ -110,10 +117,10 @@ struct ExpandArgs {
 struct HeadArgs {
     // policy head (n_policy positions, 0 = skip)
     const float* p_zbuf; int32_t p_chunk_rows; const float* p_bias; const uint8_t* rotation; float temp; float* probs;
-    int32_t n_policy;
+    int32_t n_policy; int32_t p_parts;   // p_parts: zbuf parts to sum (column splits x kColParts)
     // value head (n_value positions, 0 = skip)
     const float* v_zbuf; int32_t v_chunk_rows; const float* v_bias; const float* ip1_wt; const float* ip1_b; int32_t hidden;
-    const float* ip2_w; const float* ip2_b; float* winrate; int32_t n_value;
+    const float* ip2_w; const float* ip2_b; float* winrate; int32_t n_value; int32_t v_parts;
     int32_t ensemble;            // 1: position p was evaluated under symmetry p % 8 (rotation is unused)
 };
 

@@ -36,6 +36,8 @@ class InnerProduct:
 
 
 POLICY_CONVS = (Conv(5, 32, 96), Conv(3, 96, 128)) + (Conv(3, 128, 128),) * 10 + (Conv(3, 128, 1),)
+# the OpenCL build's policy net (Network.cpp:55-80): 5x5 32->128, 3x3 128->192, 10x 192->192, 192->1
+POLICY192_CONVS = (Conv(5, 32, 128), Conv(3, 128, 192)) + (Conv(3, 192, 192),) * 10 + (Conv(3, 192, 1),)
 VALUE_CONVS = (Conv(5, 32, 64),) + (Conv(3, 64, 64),) * 10 + (Conv(3, 64, 1),)
 VALUE_IPS = (InnerProduct(361, 256), InnerProduct(256, 1))
 
@@ -44,4 +46,5 @@ VALUE_IPS = (InnerProduct(361, 256), InnerProduct(256, 1))
 POLICY_FLOPS = 2 * P * sum(c.k * c.k * c.c_in * c.c_out for c in POLICY_CONVS)
 VALUE_FLOPS = 2 * P * sum(c.k * c.k * c.c_in * c.c_out for c in VALUE_CONVS) \
     + 2 * sum(i.n_in * i.n_out for i in VALUE_IPS)
-assert POLICY_FLOPS == 1_200_761_088 and VALUE_FLOPS == 303_725_696
+POLICY192_FLOPS = 2 * P * sum(c.k * c.k * c.c_in * c.c_out for c in POLICY192_CONVS)
+assert POLICY_FLOPS == 1_200_761_088 and VALUE_FLOPS == 303_725_696 and POLICY192_FLOPS == 2_630_297_984

@@ -10,7 +10,7 @@ from __future__ import annotations
 import dataclasses
 import numpy as np
 
-from .netdefs import POLICY_CONVS, VALUE_CONVS, VALUE_IPS
+from .netdefs import POLICY_CONVS, POLICY192_CONVS, VALUE_CONVS, VALUE_IPS
 
 DEFAULT_SEED = 20260001
 DEFAULT_POLICY_GAIN = 2.0
@@ -60,6 +60,16 @@ def policy_weights(seed: int = DEFAULT_SEED, gain: float = DEFAULT_POLICY_GAIN) 
         w.append(synth_weights(c.n_weights, seed, 2 * i, c.fan_in, g).reshape(c.c_out, c.c_in, c.k, c.k))
         b.append(synth_biases(c.c_out, seed, 2 * i + 1))
     return NetWeights(POLICY_CONVS, w, b)
+
+
+def policy192_weights(seed: int = DEFAULT_SEED, gain: float = DEFAULT_POLICY_GAIN) -> NetWeights:
+    """The 192-wide policy stack of the reference's OpenCL build (Network.cpp:55-80); array ids 64.."""
+    w, b = [], []
+    for i, c in enumerate(POLICY192_CONVS):
+        g = gain if i == len(POLICY192_CONVS) - 1 else 1.0
+        w.append(synth_weights(c.n_weights, seed, 64 + 2 * i, c.fan_in, g).reshape(c.c_out, c.c_in, c.k, c.k))
+        b.append(synth_biases(c.c_out, seed, 65 + 2 * i))
+    return NetWeights(POLICY192_CONVS, w, b)
 
 
 def value_weights(seed: int = DEFAULT_SEED) -> NetWeights:

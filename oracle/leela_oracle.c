@@ -28,6 +28,7 @@
 #include <string.h>
 
 #define LB2O_P 361
+#define LB2O_MAXC 256   /* widest layer any caller uses (the OpenCL-build policy net is 192 wide, Network.cpp:55-80) */
 #define LB2O_ROUND_W 1
 #define LB2O_ROUND_ACT 2
 #define LB2O_ROUND_LAST 4
@@ -194,8 +195,8 @@ static void run_trunk(const lb2o_net* net, const uint32_t* packed, int rotation,
  * logits_out (optional) gets the 361 pre-softmax outputs in network orientation. */
 void lb2o_policy_forward(const lb2o_net* net, const uint32_t* packed, int rotation,
                          float temperature, int emulate, float* probs, float* logits_out) {
-    float* a = (float*)malloc(sizeof(float) * 128 * LB2O_P);
-    float* b = (float*)malloc(sizeof(float) * 128 * LB2O_P);
+    float* a = (float*)malloc(sizeof(float) * LB2O_MAXC * LB2O_P);
+    float* b = (float*)malloc(sizeof(float) * LB2O_MAXC * LB2O_P);
     float sm[LB2O_P];
     float* last;
     run_trunk(net, packed, rotation, emulate, a, b, &last);
@@ -208,8 +209,8 @@ void lb2o_policy_forward(const lb2o_net* net, const uint32_t* packed, int rotati
 /* Network::get_value_internal, Network.cpp:676-740: 12 convs, innerproduct<361,256> (ELU),
  * innerproduct<256,1> (linear), winrate = (1 + tanh(x)) / 2 for the side to move. */
 float lb2o_value_forward(const lb2o_net* net, const uint32_t* packed, int rotation, int emulate) {
-    float* a = (float*)malloc(sizeof(float) * 128 * LB2O_P);
-    float* b = (float*)malloc(sizeof(float) * 128 * LB2O_P);
+    float* a = (float*)malloc(sizeof(float) * LB2O_MAXC * LB2O_P);
+    float* b = (float*)malloc(sizeof(float) * LB2O_MAXC * LB2O_P);
     float h[256], o[1];
     float* last;
     run_trunk(net, packed, rotation, emulate, a, b, &last);
@@ -238,7 +239,7 @@ void lb2o_value_forward_batch(const lb2o_net* net, const uint32_t* packed, const
  * ([c_out][361], network orientation, after bias+ELU and any emulated rounding). */
 void lb2o_trunk_activations(const lb2o_net* net, const uint32_t* packed, int rotation,
                             int emulate, float* const* acts) {
-    float* in = (float*)malloc(sizeof(float) * 128 * LB2O_P);
+    float* in = (float*)malloc(sizeof(float) * LB2O_MAXC * LB2O_P);
     lb2o_expand_planes(packed, rotation, in);
     const float* cur = in;
     for (int l = 0; l < net->n_conv; l++) {

@@ -97,6 +97,49 @@ def test_trunk_layers_vs_oracle(ev, ref_golden, oracle_nets, kind, n_layers):
             assert np.abs(got[i] - want).mean() < 2e-3
 
 
+def test_wide_policy_net_192_vs_oracle(ref_golden, bench_positions):
+    """The 192-wide policy stack of the reference's OpenCL build (Network.cpp:55-80: 5x5 32->128,
+    3x3 128->192, 10x 192->192, 192->1) runs as two column-split jobs per layer (N = 96). Checked
+    layer by layer and end to end against the C oracle (no reference golden exists for this net: its
+    weights are missing from the snapshot and the reference's BLAS build cannot run it), in every
+    launch mode, bit-identically across modes."""
+    from leela_b200 import capi, synth
+    from oracle import oracle
+    w = synth.policy192_weights()
+    onet = oracle.OracleNet(w)
+    g = ref_golden
+    n = 12
+    planes, rot = g["policy_planes"][:n], g["rotation"][:n]
+    e = capi.Evaluator(policy=w)
+    try:
+        for n_layers in (1, 2, 3, 12):
+            got = e.debug_trunk(capi.POLICY, planes[:3], rot[:3], n_layers, w.convs[n_layers - 1].c_out)
+            for i in range(3):
+                want = oracle.trunk_activations(onet, planes[i], int(rot[i]), emulate=7)[n_layers - 1]
+                assert np.abs(got[i] - want).max() < (2e-3 if n_layers == 1 else 3e-2), n_layers
+                assert np.abs(got[i] - want).mean() < 3e-3, n_layers
+        temp = float(g["softmax_temp"])
+        want = oracle.policy_forward(onet, planes, rot, temp)
+        results = {}
+        for mode, pair in ((1, 1), (0, 1), (1, 0)):
+            e.set_option("trunk_mode", mode); e.set_option("cta_pair", pair)
+            results[(mode, pair)] = e.eval_policy(planes, rot, temp)
+        e.set_option("trunk_mode", 1); e.set_option("cta_pair", 1)
+        got = results[(1, 1)]
+        assert np.abs(got - want).max() < TOL_P
+        assert (got.argmax(1) == want.argmax(1)).mean() >= 0.9
+        for k in results:
+            np.testing.assert_array_equal(results[k], got)
+        # a full-size batch through the persistent launch: 34 jobs, 3 jobs per round
+        m = 256
+        big = e.eval_policy(bench_positions["policy_planes"][:m], bench_positions["rotation"][:m], temp)
+        small = e.eval_policy(bench_positions["policy_planes"][100:104], bench_positions["rotation"][100:104], temp)
+        np.testing.assert_array_equal(big[100:104], small)
+        assert np.allclose(big.sum(1), 1.0, atol=1e-4)
+    finally:
+        e.close()
+
+
 def test_launch_modes_bit_identical(ev, ref_golden):
     """One launch per layer vs the single persistent dataflow launch: same arithmetic, same bits."""
     g = ref_golden
@@ -262,6 +305,12 @@ def test_abi_misuse_returns_error_codes(ref_golden):
     with pytest.raises(capi.Lb2Error) as ei:
         e.eval_value(g["value_planes"][:1], g["rotation"][:1])
     assert ei.value.code == -3
+    with pytest.raises(capi.Lb2Error) as ei:   # ensemble over a net that was never pushed
+        e.eval_ensemble(None, g["value_planes"][:1])
+    assert ei.value.code == -3
+    with pytest.raises(capi.Lb2Error) as ei:
+        e.eval_ensemble(g["policy_planes"][:1], None, temp=-1.0)
+    assert ei.value.code == -1
     bad = synth.value_weights()
     bad.convs = (Conv(3, 32, 64),) + tuple(bad.convs[1:])
     bad.conv_w[0] = bad.conv_w[0][:, :, :3, :3]
@@ -269,6 +318,52 @@ def test_abi_misuse_returns_error_codes(ref_golden):
         e.push_net(capi.VALUE, bad)
     assert ei.value.code == -5  # LB2_ERR_UNSUPPORTED
     e.close()
+
+
+def test_concurrent_blocking_callers(ev, bench_positions):
+    """Several host threads inside lb2_eval_* at once (the search's threads do that): calls share
+    the device through the two I/O slots and must return exactly what they return alone — pageable
+    and page-locked buffers, different sizes, both nets / one net, ensembles in between."""
+    import threading
+    import torch
+    b = bench_positions
+    jobs = []
+    for t, (lo, n) in enumerate([(0, 256), (100, 37), (300, 512), (7, 1), (600, 129), (40, 300)]):
+        jobs.append((b["policy_planes"][lo:lo + n], b["value_planes"][lo:lo + n], b["rotation"][lo:lo + n]))
+    alone = [ev.eval_both(*j, 0.75) for j in jobs]
+    ens_alone = ev.eval_ensemble(b["policy_planes"][:9], b["value_planes"][:9], 0.75)
+    got = [None] * len(jobs)
+    ens_got = [None]
+    errors = []
+
+    def run(i):
+        try:
+            pp, vp, rot = jobs[i]
+            for rep in range(6):
+                if i % 2:   # page-locked caller buffers are used for the DMA directly
+                    hp = torch.from_numpy(pp.astype(np.int32)).pin_memory(); hv = torch.from_numpy(vp.astype(np.int32)).pin_memory()
+                    hr = torch.from_numpy(rot.copy()).pin_memory()
+                    op = torch.empty((pp.shape[0], 361)).pin_memory(); ow = torch.empty((pp.shape[0],)).pin_memory()
+                    ev.eval_both_raw(hp.data_ptr(), hv.data_ptr(), hr.data_ptr(), pp.shape[0], 0.75, op.data_ptr(), ow.data_ptr())
+                    got[i] = (op.numpy().copy(), ow.numpy().copy())
+                else:
+                    got[i] = ev.eval_both(pp, vp, rot, 0.75)
+                if i == 0:
+                    ens_got[0] = ev.eval_ensemble(b["policy_planes"][:9], b["value_planes"][:9], 0.75)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=run, args=(i,)) for i in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for a, g_ in zip(alone, got):
+        np.testing.assert_array_equal(a[0], g_[0])
+        np.testing.assert_array_equal(a[1], g_[1])
+    np.testing.assert_array_equal(ens_alone[0], ens_got[0][0])
+    np.testing.assert_array_equal(ens_alone[1], ens_got[0][1])
 
 
 def test_async_submit_coalesces(ev, ref_golden):
