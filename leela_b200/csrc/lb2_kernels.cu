@@ -665,16 +665,24 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
 // heads. The 3x3 conv to one channel was folded into the last trunk layer's epilogue as per-tap
 // partial sums z[half][t][row]; what is left is a 9-point gather per board point.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float head_gather(const float* __restrict__ zbuf, int chunk_rows, int n_parts, int base_row, int y, int x) {
+template <int kParts>
+__device__ __forceinline__ float head_gather_parts(const float* __restrict__ zbuf, int chunk_rows, int base_row, int y, int x) {
     float acc = 0.0f;
 #pragma unroll
     for (int t = 0; t < 9; t++) {
         const int row = base_row + (y + t / 3 - 1) * 20 + (x + t % 3 - 1);
         if (row >= 0) {  // rows above the first position are implicit zero padding
-            for (int p = 0; p < n_parts; p++) acc += zbuf[(size_t)(p * 9 + t) * chunk_rows + row];
+#pragma unroll
+            for (int p = 0; p < kParts; p++) acc += zbuf[(size_t)(p * 9 + t) * chunk_rows + row];
         }
     }
     return acc;
+}
+// n_parts = column splits of the last trunk layer x kColParts; the loads of one point are independent
+// and must be issued together, hence the compile-time part counts
+__device__ __forceinline__ float head_gather(const float* __restrict__ zbuf, int chunk_rows, int n_parts, int base_row, int y, int x) {
+    return n_parts == kColParts ? head_gather_parts<kColParts>(zbuf, chunk_rows, base_row, y, x)
+                                : head_gather_parts<kColParts * kMaxSplit>(zbuf, chunk_rows, base_row, y, x);
 }
 
 __device__ __forceinline__ float warp_max(float v) {

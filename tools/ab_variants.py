@@ -1,5 +1,5 @@
 """A/B timing of tuning builds of libleela_b200.so on ONE box, interleaved (boxes differ by a few %).
-Here:   python tools/ab_variants.py build name[:DEF=VAL,DEF2=VAL2] ...   (name 'head' = last commit's sources)
+Here:   python tools/ab_variants.py build name[@rev][:DEF=VAL,DEF2=VAL2] ...   (name 'head' = last commit's sources, name@rev = that commit's)
 On GPU: python tools/ab_variants.py run [reps]       -> trunk/step us per variant, interleaved rounds"""
 import os, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -15,12 +15,16 @@ def do_build(specs):
         name, _, defs = spec.partition(":")
         defines = [d for d in defs.split(",") if d]
         out = os.path.join(VDIR, f"{name}.so")
-        if name == "head":
+        rev = "HEAD"
+        if "@" in name:
+            name, rev = name.split("@")
+            out = os.path.join(VDIR, f"{name}.so")
+        if name == "head" or rev != "HEAD":
             with tempfile.TemporaryDirectory() as td:
                 os.makedirs(os.path.join(td, "leela_b200", "csrc")); os.makedirs(os.path.join(td, "include"))
                 for rel in ["leela_b200/csrc/lb2_api.cu", "leela_b200/csrc/lb2_kernels.cu", "leela_b200/csrc/lb2_kernels.cuh",
                             "leela_b200/csrc/lb2_ptx.cuh", "include/leela_b200.h"]:
-                    open(os.path.join(td, rel), "wb").write(subprocess.check_output(["git", "show", f"HEAD:{rel}"], cwd=ROOT))
+                    open(os.path.join(td, rel), "wb").write(subprocess.check_output(["git", "show", f"{rev}:{rel}"], cwd=ROOT))
                 build.build(defines=defines, out=out, csrc=os.path.join(td, "leela_b200", "csrc"))
         else:
             build.build(defines=defines, out=out)
