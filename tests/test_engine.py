@@ -44,6 +44,20 @@ def test_feature_planes_bit_identical_to_reference(tmp_path, n, seed):
     assert a.movenum.max() > 150
 
 
+@needs_engine
+def test_engine_starts_without_a_gpu_only_for_help_and_planes():
+    """The binary loads (its shared library is found through the relative rpath) and answers --help;
+    asking it to evaluate without a B200 must fail loudly — there is no CPU fallback."""
+    r = subprocess.run([ENGINE, "--help"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "--weights" in r.stdout and "--gpu" in r.stdout
+    r = subprocess.run([ENGINE, "--bogus"], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "Unrecognized argument" in r.stdout
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([ENGINE, "-g", "--noponder", "--weights", WEIGHTS], input="quit\n", capture_output=True, text=True, timeout=60)
+        assert r.returncode != 0 and "leela_b200" in (r.stderr + r.stdout)
+
+
 def test_weights_file_round_trip(tmp_path):
     from leela_b200 import synth
     path = str(tmp_path / "w.lb2w")
