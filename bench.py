@@ -186,6 +186,8 @@ def run_ours(args):
 
     ev = capi.Evaluator(policy=synth.policy_weights(), value=synth.value_weights(), devices=[local])
     ev.set_option("max_batch", max(B, 256))
+    if args.overlap_io:
+        ev.set_option("overlap_io", 1)
     pp, vp, rot = load_positions()
     n_pos = pp.shape[0]
     # input pool: every batch is a different window (stride 3, wrapping) over the distinct positions,
@@ -336,6 +338,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--flush-l2", action="store_true", help="evict L2 before every step instead of cycling an input pool larger than L2")
+    ap.add_argument("--overlap-io", action="store_true", help="A/B: expand/heads kernels of host-buffer calls on the I/O slot's stream")
     ap.add_argument("--e2e-threads", type=int, default=2, help="host threads calling the C ABI concurrently in the e2e leg")
     args = ap.parse_args()
     if args.impl == "reference":

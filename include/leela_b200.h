@@ -126,6 +126,8 @@ int lb2_device_count(lb2_ctx* ctx);
  *   "trunk_mode": 0 = one launch per layer, 1 = single persistent dataflow launch (default)
  *   "cta_pair":   1 = tensor-core work issued for CTA pairs (tcgen05 cta_group::2, default), 0 = per CTA
  *   "dynamic_items": 1 = clusters claim work items from a global in-order counter (default), 0 = round robin
+ *   "overlap_io": 1 = host-buffer calls run their expand / heads kernels on the I/O slot's stream, beside the
+ *                 trunk kernel of another call in flight; 0 = on the compute stream (default: measured faster)
  *   "max_batch":  positions per device pass (larger calls are chunked), default 256
  *   "profile_trunk": 1 = bracket every trunk launch with CUDA events; lb2_get_option("trunk_ns")
  *                 then returns the device nanoseconds accumulated since the last query

@@ -77,13 +77,19 @@ struct TrunkLayerDev {
     float* bias[lb2::kMaxSplit] = {nullptr, nullptr};
 };
 
+// Workspace sets: 0 = calls on device pointers (lb2_eval_both_device, lb2_debug_trunk), 1 + i = I/O slot i.
+constexpr int kIoSlots = 2;
+constexpr int kSets = 1 + kIoSlots;
+
 // One net replicated on one device, with its workspace.
 struct NetDev {
     std::vector<TrunkLayerDev> trunk;
     int head_c_in = 0;
     float *head_wt[lb2::kMaxSplit] = {nullptr, nullptr};  // final conv weights per column split of the last trunk layer, [9 taps][c_in / n_split]
     float* head_b = nullptr;
-    float* zbuf = nullptr;                        // fused-head partial sums [2][9][rows3]
+    // Buffers written OUTSIDE the trunk launch exist once per workspace set (kSets below), so that
+    // the expand and heads kernels of one call can overlap the trunk of another:
+    float* zbuf[1 + kIoSlots] = {};               // fused-head partial sums [splits * parts][9][rows3]
     int hidden = 0;
     float *ip1_wt = nullptr, *ip1_b = nullptr, *ip2_w = nullptr, *ip2_b = nullptr;
     // workspace
@@ -91,12 +97,12 @@ struct NetDev {
     int width = 0;           // widest trunk c_out
     int rows5 = 0, rows3 = 0;  // chunk-plane rows of the S=21 / S=20 buffers
     uint32_t* planes = nullptr;
-    __half* x0 = nullptr;
+    __half* x0[1 + kIoSlots] = {};                // first-conv input (S=21 row space)
     __half* act[2] = {nullptr, nullptr};
     float* out = nullptr;    // probs [cap][361] or winrate [cap]
     uint32_t* flags = nullptr;
     int flags_stride = 0;
-    CUtensorMap tm_x0, tm_act[2];
+    CUtensorMap tm_x0[1 + kIoSlots], tm_act[2];
 };
 
 // Input/output buffers of one host-buffer call in flight on a device. Two slots per device let the
@@ -114,28 +120,27 @@ struct IoSlot {
     uint8_t* h_rot = nullptr;
     float *h_probs = nullptr, *h_win = nullptr;
 };
-constexpr int kIoSlots = 2;
-
 struct DeviceState {
     int id = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     NetDev net[2];
     uint8_t* rot = nullptr;
-    lb2::LayerJob* jobs_dev = nullptr;
-    uint32_t* item_counter = nullptr;  // dynamic scheduling counter, cleared by the expand kernel of each step
+    lb2::LayerJob* jobs_dev[kSets] = {};   // one job table per workspace set (they differ in x0 / zbuf)
+    uint32_t* item_counter = nullptr;     // dynamic scheduling: claim counter, never reset
+    uint32_t claim_base = 0;              // its value at the start of the next trunk launch
     // pinned staging
     uint32_t* h_planes[2] = {nullptr, nullptr};
     uint8_t* h_rot = nullptr;
     float* h_probs = nullptr;
     float* h_win = nullptr;
-    lb2::LayerJob* h_jobs = nullptr;
+    lb2::LayerJob* h_jobs[kSets] = {};
     int cap = 0;
     uint32_t epoch = 0;
     unsigned long long* trace = nullptr;   // debug timeline buffer (option "trace")
     std::vector<cudaEvent_t> prof_events;  // (start, stop) pairs around trunk launches
     std::vector<cudaEvent_t> seg_events;   // profile_trunk == 2: one event around every launch, 4 per eval
-    long plan_key[8] = {-1, -1, -1, -1, -1, -1, -1, -1};  // n, run0, run1, limit0, limit1, workspace pointers
+    long plan_key[kSets][8];  // n, run0, run1, limit0, limit1, workspace pointers, pair (-1 = none yet)
     IoSlot slots[kIoSlots];
     cudaEvent_t ev_user = nullptr;   // last work enqueued on a caller-provided stream (lb2_eval_both_device)
     cudaEvent_t ev_comp = nullptr;   // marks the compute stream for such a call to wait on
@@ -171,6 +176,8 @@ struct lb2_ctx {
     long max_batch = 256;  // batch-256 chunks keep both nets' ping-pong activations L2-resident (measured best)
     long profile_trunk = 0;
     long cta_pair = 1;
+    long overlap_io = 0;   // 1: host-buffer calls run expand / heads on the I/O slot's stream, beside the trunk of another
+                           // call. Measured 2-3 % slower end to end (the value head's blocks hold up the next trunk's CTAs): off.
     long dynamic_items = 1;
     std::atomic<long> launches{0};
     std::atomic<long> stat_positions{0}, stat_batches{0}, stat_requests{0};  // async queue: positions, device batches, requests
@@ -322,10 +329,10 @@ int make_act_tmap(CUtensorMap* tm, __half* base, int rows, int chunks, int halo)
 }
 
 void free_workspace(NetDev* nd) {
-    cudaFree(nd->planes); cudaFree(nd->x0); cudaFree(nd->act[0]); cudaFree(nd->act[1]);
-    cudaFree(nd->out); cudaFree(nd->flags); cudaFree(nd->zbuf);
-    nd->zbuf = nullptr;
-    nd->planes = nullptr; nd->x0 = nullptr; nd->act[0] = nd->act[1] = nullptr; nd->out = nullptr; nd->flags = nullptr;
+    cudaFree(nd->planes); cudaFree(nd->act[0]); cudaFree(nd->act[1]);
+    cudaFree(nd->out); cudaFree(nd->flags);
+    for (int w = 0; w < kSets; w++) { cudaFree(nd->x0[w]); cudaFree(nd->zbuf[w]); nd->x0[w] = nullptr; nd->zbuf[w] = nullptr; }
+    nd->planes = nullptr; nd->act[0] = nd->act[1] = nullptr; nd->out = nullptr; nd->flags = nullptr;
     nd->cap = 0;
 }
 
@@ -337,21 +344,24 @@ int ensure_workspace(NetDev* nd, int kind, int cap) {
     const size_t x0_bytes = (size_t)4 * nd->rows5 * 16;
     const size_t act_bytes = (size_t)(nd->width / 8) * nd->rows3 * 16;
     CU_TRY(cudaMalloc(&nd->planes, (size_t)cap * lb2::kPoints * sizeof(uint32_t)));
-    CU_TRY(cudaMalloc(&nd->x0, x0_bytes));
+    for (int w = 0; w < kSets; w++) {
+        CU_TRY(cudaMalloc(&nd->x0[w], x0_bytes));
+        CU_TRY(cudaMemset(nd->x0[w], 0, x0_bytes));
+        CU_TRY(cudaMalloc(&nd->zbuf[w], (size_t)9 * lb2::kColParts * lb2::kMaxSplit * nd->rows3 * sizeof(float)));
+    }
     CU_TRY(cudaMalloc(&nd->act[0], act_bytes));
     CU_TRY(cudaMalloc(&nd->act[1], act_bytes));
-    CU_TRY(cudaMemset(nd->x0, 0, x0_bytes));
     CU_TRY(cudaMemset(nd->act[0], 0, act_bytes));  // padding rows/columns must start (and stay) zero
     CU_TRY(cudaMemset(nd->act[1], 0, act_bytes));
     const size_t out_elems = kind == LB2_POLICY ? (size_t)cap * lb2::kPoints : (size_t)cap;
     CU_TRY(cudaMalloc(&nd->out, out_elems * sizeof(float)));
-    CU_TRY(cudaMalloc(&nd->zbuf, (size_t)9 * lb2::kColParts * lb2::kMaxSplit * nd->rows3 * sizeof(float)));
     nd->flags_stride = nd->rows5 / lb2::kTileRows + 2;
     const size_t n_flags = (size_t)lb2::kMaxLayers * lb2::kMaxSplit * nd->flags_stride;
     CU_TRY(cudaMalloc(&nd->flags, n_flags * sizeof(uint32_t)));
     CU_TRY(cudaMemset(nd->flags, 0, n_flags * sizeof(uint32_t)));
     int rc;
-    if ((rc = make_act_tmap(&nd->tm_x0, nd->x0, nd->rows5, 4, 48))) return rc;
+    for (int w = 0; w < kSets; w++)
+        if ((rc = make_act_tmap(&nd->tm_x0[w], nd->x0[w], nd->rows5, 4, 48))) return rc;
     if ((rc = make_act_tmap(&nd->tm_act[0], nd->act[0], nd->rows3, nd->width / 8, 24))) return rc;
     if ((rc = make_act_tmap(&nd->tm_act[1], nd->act[1], nd->rows3, nd->width / 8, 24))) return rc;
     nd->cap = cap;
@@ -388,7 +398,7 @@ struct JobPlan {
 // Interleave the two nets layer by layer: P1 V1 P2a P2b V2 ... so that one launch round holds the
 // independent jobs of equal depth (a layer wider than 128 channels contributes one job per column
 // split; they are consecutive in the table).
-JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2], bool pair) {
+JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2], bool pair, int ws) {
     JobPlan pl;
     size_t depth = 0;
     for (int k = 0; k < 2; k++)
@@ -436,7 +446,7 @@ JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2], bool 
                     // whole net: fold the final 3x3 conv to one channel into this layer's epilogue
                     J.head_taps = 9;
                     J.head_w = nd.head_wt[sp];
-                    J.zbuf = nd.zbuf;
+                    J.zbuf = nd.zbuf[ws];
                     J.zparts = sp * lb2::kColParts;
                 }
                 pl.jobs.push_back(J);
@@ -452,36 +462,37 @@ JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2], bool 
     return pl;
 }
 
+// `ws`: workspace set (x0 / zbuf / job table) this launch works in
 int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers[2], cudaStream_t st,
-              JobPlan* plan_out) {
+              JobPlan* plan_out, int ws) {
     const bool pair = ctx->cta_pair != 0 && d->sm_count >= 2;
-    JobPlan pl = plan_jobs(d, run, n, limit_layers, pair);
+    JobPlan pl = plan_jobs(d, run, n, limit_layers, pair, ws);
     if (pl.jobs.empty()) return fail(LB2_ERR_STATE, "no trunk layers to run");
     if ((int)pl.jobs.size() > lb2::kMaxLaunchJobs) return fail(LB2_ERR_UNSUPPORTED, "too many layers");
     const long key[8] = {n, run[0], run[1], limit_layers[0], limit_layers[1],
                          (long)reinterpret_cast<uintptr_t>(d->net[0].act[0]), (long)reinterpret_cast<uintptr_t>(d->net[1].act[0]), pair};
-    if (memcmp(key, d->plan_key, sizeof key)) {
-        // the job table on the device is reused by back-to-back launches of the same shape;
+    if (memcmp(key, d->plan_key[ws], sizeof key)) {
+        // the set's job table on the device is reused by back-to-back launches of the same shape;
         // rewrite it only when the shape changes, after earlier work has drained
         CU_TRY(cudaStreamSynchronize(st));
         CU_TRY(cudaStreamSynchronize(d->stream));
-        memcpy(d->h_jobs, pl.jobs.data(), pl.jobs.size() * sizeof(lb2::LayerJob));
-        CU_TRY(cudaMemcpyAsync(d->jobs_dev, d->h_jobs, pl.jobs.size() * sizeof(lb2::LayerJob), cudaMemcpyHostToDevice, st));
+        memcpy(d->h_jobs[ws], pl.jobs.data(), pl.jobs.size() * sizeof(lb2::LayerJob));
+        CU_TRY(cudaMemcpyAsync(d->jobs_dev[ws], d->h_jobs[ws], pl.jobs.size() * sizeof(lb2::LayerJob), cudaMemcpyHostToDevice, st));
         CU_TRY(cudaStreamSynchronize(st));
-        memcpy(d->plan_key, key, sizeof key);
+        memcpy(d->plan_key[ws], key, sizeof key);
     }
     lb2::TrunkParams P;
     memset(&P, 0, sizeof P);
     for (int k = 0; k < 2; k++) {
         if (!d->net[k].cap) continue;
-        P.tmaps[pl.tmap_base[k] + 0] = d->net[k].tm_x0;
+        P.tmaps[pl.tmap_base[k] + 0] = d->net[k].tm_x0[ws];
         P.tmaps[pl.tmap_base[k] + 1] = d->net[k].tm_act[0];
         P.tmaps[pl.tmap_base[k] + 2] = d->net[k].tm_act[1];
     }
     for (int k = 0; k < 2; k++)  // unused slots still get prefetched: point them at a valid map
         if (!d->net[k].cap)
-            for (int i = 0; i < 3; i++) P.tmaps[pl.tmap_base[k] + i] = d->net[1 - k].tm_x0;
-    P.jobs = d->jobs_dev;
+            for (int i = 0; i < 3; i++) P.tmaps[pl.tmap_base[k] + i] = d->net[1 - k].tm_x0[ws];
+    P.jobs = d->jobs_dev[ws];
     P.n_jobs = (int)pl.jobs.size();
     // rounds: jobs of equal depth, their items interleaved in the launch-wide order
     P.n_rounds = 0;
@@ -514,6 +525,11 @@ int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers
         P.use_flags = 1;
         P.next_item = ctx->dynamic_items ? d->item_counter : nullptr;
         const int grid = pair ? std::min(d->sm_count & ~1, 2 * pl.total_items) : std::min(d->sm_count, pl.total_items);
+        if (P.next_item) {
+            // every cluster claims until it draws an index past the end: items + clusters claims per launch
+            P.claim_base = d->claim_base;
+            d->claim_base += (uint32_t)pl.total_items + (uint32_t)(pair ? grid / 2 : grid);
+        }
         CU_TRY(lb2::launch_trunk(P, grid, true, pair, st));
         ctx->launches++;
     } else {
@@ -536,17 +552,30 @@ int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers
     return LB2_OK;
 }
 
-// `ensemble`: n device positions = n/8 input positions x 8 symmetries (AVERAGE_ALL), d_rot unused
+// One evaluation on one device; all pointers are device pointers. The expand and heads kernels go on
+// `st_io`, the trunk on `st`; when the two differ (host-buffer calls: the I/O slot's stream and the
+// device's compute stream) `ev_in` / `ev_done` order them, and the expand / heads of one call run
+// beside the trunk of another. `ws` is the workspace set (x0, zbuf, job table) the call works in.
+// `ensemble`: n device positions = n/8 input positions x 8 symmetries (AVERAGE_ALL), d_rot unused.
 int eval_on_device(lb2_ctx* ctx, DeviceState* d, const uint32_t* d_pol, const uint32_t* d_val, const uint8_t* d_rot,
-                   int n, float temp, float* d_probs, float* d_win, cudaStream_t st, bool ensemble = false) {
+                   int n, float temp, float* d_probs, float* d_win, cudaStream_t st, int ws = 0, bool ensemble = false,
+                   cudaStream_t st_io = nullptr, cudaEvent_t ev_in = nullptr, cudaEvent_t ev_done = nullptr, bool overlap = true) {
     bool run[2] = {d_probs != nullptr, d_win != nullptr};
+    const bool split = st_io != nullptr && st_io != st;
+    if (!split) st_io = st;
+    // overlap off: the expand and heads kernels go on the compute stream too (the two streams are still ordered)
+    cudaStream_t st_k = overlap ? st_io : st;
     // profile_trunk == 2: an event after every launch -> per-segment device times (debug)
-    auto mark = [&]() {
+    auto mark = [&](cudaStream_t s) {
         if (ctx->profile_trunk != 2) return;
         cudaEvent_t e;
-        if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); d->seg_events.push_back(e); }
+        if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, s); d->seg_events.push_back(e); }
     };
-    mark();
+    if (split && !overlap) {   // inputs arrive on st_io
+        CU_TRY(cudaEventRecord(ev_in, st_io));
+        CU_TRY(cudaStreamWaitEvent(st, ev_in, 0));
+    }
+    mark(st_k);
     const uint32_t* planes[2] = {d_pol, d_val};
     int limit[2] = {1 << 20, 1 << 20};
     lb2::ExpandArgs ea;
@@ -554,13 +583,12 @@ int eval_on_device(lb2_ctx* ctx, DeviceState* d, const uint32_t* d_pol, const ui
     ea.rotation = d_rot;
     ea.ensemble = ensemble ? 1 : 0;
     ea.n = n;
-    ea.zero_word = d->item_counter;
     for (int k = 0; k < 2; k++) {
         if (!run[k]) continue;
         NetDev& nd = d->net[k];
         if (nd.cap < n) return fail(LB2_ERR_STATE, "workspace too small");
         ea.planes[ea.n_nets] = planes[k];
-        ea.x0[ea.n_nets] = nd.x0;
+        ea.x0[ea.n_nets] = nd.x0[ws];
         ea.chunk_rows[ea.n_nets] = nd.rows5;
         ea.n_nets++;
         if (k == 1 && nd.ip1_wt) {  // pull the value head's matrix into L2 while the trunk runs
@@ -568,13 +596,21 @@ int eval_on_device(lb2_ctx* ctx, DeviceState* d, const uint32_t* d_pol, const ui
             ea.pf_bytes = (size_t)lb2::kPoints * nd.hidden * sizeof(float);
         }
     }
-    CU_TRY(lb2::launch_expand(ea, st));
+    CU_TRY(lb2::launch_expand(ea, st_k));
     ctx->launches++;
-    mark();
+    mark(st_k);
+    if (split && overlap) {
+        CU_TRY(cudaEventRecord(ev_in, st_io));
+        CU_TRY(cudaStreamWaitEvent(st, ev_in, 0));
+    }
     JobPlan pl;
-    int rc = run_trunk(ctx, d, run, n, limit, st, &pl);
+    int rc = run_trunk(ctx, d, run, n, limit, st, &pl, ws);
     if (rc) return rc;
-    mark();
+    mark(st);
+    if (split && overlap) {
+        CU_TRY(cudaEventRecord(ev_done, st));
+        CU_TRY(cudaStreamWaitEvent(st_io, ev_done, 0));
+    }
     lb2::HeadArgs ha;
     memset(&ha, 0, sizeof ha);
     ha.rotation = d_rot;
@@ -582,18 +618,22 @@ int eval_on_device(lb2_ctx* ctx, DeviceState* d, const uint32_t* d_pol, const ui
     ha.temp = temp;
     if (run[0]) {
         NetDev& nd = d->net[0];
-        ha.p_zbuf = nd.zbuf; ha.p_chunk_rows = nd.rows3; ha.p_bias = nd.head_b; ha.probs = d_probs; ha.n_policy = n;
+        ha.p_zbuf = nd.zbuf[ws]; ha.p_chunk_rows = nd.rows3; ha.p_bias = nd.head_b; ha.probs = d_probs; ha.n_policy = n;
         ha.p_parts = nd.trunk.back().n_split * lb2::kColParts;
     }
     if (run[1]) {
         NetDev& nd = d->net[1];
-        ha.v_zbuf = nd.zbuf; ha.v_chunk_rows = nd.rows3; ha.v_bias = nd.head_b; ha.ip1_wt = nd.ip1_wt; ha.ip1_b = nd.ip1_b;
+        ha.v_zbuf = nd.zbuf[ws]; ha.v_chunk_rows = nd.rows3; ha.v_bias = nd.head_b; ha.ip1_wt = nd.ip1_wt; ha.ip1_b = nd.ip1_b;
         ha.hidden = nd.hidden; ha.ip2_w = nd.ip2_w; ha.ip2_b = nd.ip2_b; ha.winrate = d_win; ha.n_value = n;
         ha.v_parts = nd.trunk.back().n_split * lb2::kColParts;
     }
-    CU_TRY(lb2::launch_heads(ha, st));
+    CU_TRY(lb2::launch_heads(ha, st_k));
     ctx->launches++;
-    mark();
+    mark(st_k);
+    if (split && !overlap) {   // results are fetched on st_io
+        CU_TRY(cudaEventRecord(ev_done, st));
+        CU_TRY(cudaStreamWaitEvent(st_io, ev_done, 0));
+    }
     return LB2_OK;
 }
 
@@ -689,8 +729,8 @@ int eval_host_locked_enqueue(lb2_ctx* ctx, DeviceState* d, IoSlot* sl, const uin
     CU_TRY(cudaSetDevice(d->id));
     for (int k = 0; k < 2; k++)
         if (need[k] && d->net[k].cap < cap) {
-            // growing the shared workspace: nothing may still be computing in it
-            CU_TRY(cudaStreamSynchronize(d->stream));
+            // growing the shared workspace: nothing (trunk, or another slot's expand / heads) may still be using it
+            CU_TRY(cudaDeviceSynchronize());
             if ((rc = ensure_workspace(&d->net[k], k, cap))) return rc;
         }
     const size_t pbytes = (size_t)cnt * lb2::kPoints * sizeof(uint32_t);
@@ -700,9 +740,7 @@ int eval_host_locked_enqueue(lb2_ctx* ctx, DeviceState* d, IoSlot* sl, const uin
         const uint32_t* from = pin_in[k] ? src[k] + (size_t)lo * lb2::kPoints : sl->h_planes[k];
         CU_TRY(cudaMemcpyAsync(sl->d_planes[k], from, pbytes, cudaMemcpyHostToDevice, sl->stream));
     }
-    CU_TRY(cudaEventRecord(sl->ev_in, sl->stream));
-    CU_TRY(cudaStreamWaitEvent(d->stream, sl->ev_in, 0));
-    if (d->user_pending) {   // kernels enqueued on a caller's stream (lb2_eval_both_device) use the same workspace
+    if (d->user_pending) {   // kernels enqueued on a caller's stream (lb2_eval_both_device) use the same activation buffers
         CU_TRY(cudaStreamWaitEvent(d->stream, d->ev_user, 0));
         d->user_pending = false;
     }
@@ -710,7 +748,8 @@ int eval_host_locked_enqueue(lb2_ctx* ctx, DeviceState* d, IoSlot* sl, const uin
     // buffers, their means behind them
     const int n_dev = ensemble ? 8 * cnt : cnt;
     rc = eval_on_device(ctx, d, sl->d_planes[0], sl->d_planes[1], sl->d_rot, n_dev, temp, need[0] ? sl->d_probs : nullptr,
-                        need[1] ? sl->d_win : nullptr, d->stream, ensemble);
+                        need[1] ? sl->d_win : nullptr, d->stream, 1 + (int)(sl - d->slots), ensemble, sl->stream, sl->ev_in, sl->ev_done,
+                        ctx->overlap_io != 0);
     if (rc) return rc;
     const float* res_probs = sl->d_probs;
     const float* res_win = sl->d_win;
@@ -719,11 +758,9 @@ int eval_host_locked_enqueue(lb2_ctx* ctx, DeviceState* d, IoSlot* sl, const uin
         memset(&ma, 0, sizeof ma);
         if (need[0]) { ma.probs8 = sl->d_probs; ma.probs = sl->d_probs + (size_t)n_dev * lb2::kPoints; ma.n_policy = cnt; res_probs = ma.probs; }
         if (need[1]) { ma.win8 = sl->d_win; ma.win = sl->d_win + n_dev; ma.n_value = cnt; res_win = ma.win; }
-        CU_TRY(lb2::launch_ensemble_mean(ma, d->stream));
+        CU_TRY(lb2::launch_ensemble_mean(ma, sl->stream));
         ctx->launches++;
     }
-    CU_TRY(cudaEventRecord(sl->ev_done, d->stream));
-    CU_TRY(cudaStreamWaitEvent(sl->stream, sl->ev_done, 0));
     if (need[0])
         CU_TRY(cudaMemcpyAsync(pin_probs ? probs + (size_t)lo * lb2::kPoints : sl->h_probs, res_probs,
                                (size_t)cnt * lb2::kPoints * sizeof(float), cudaMemcpyDeviceToHost, sl->stream));
@@ -900,10 +937,13 @@ int lb2_init(const int* device_ids, int n_devices, lb2_ctx** ctx_out) {
         d.id = id;
         d.sm_count = prop.multiProcessorCount;
         CU_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
-        CU_TRY(cudaMalloc(&d.jobs_dev, lb2::kMaxJobs * sizeof(lb2::LayerJob)));
+        for (int w = 0; w < kSets; w++) {
+            CU_TRY(cudaMalloc(&d.jobs_dev[w], lb2::kMaxJobs * sizeof(lb2::LayerJob)));
+            CU_TRY(cudaMallocHost(&d.h_jobs[w], lb2::kMaxJobs * sizeof(lb2::LayerJob)));
+            for (int i = 0; i < 8; i++) d.plan_key[w][i] = -1;
+        }
         CU_TRY(cudaMalloc(&d.item_counter, sizeof(uint32_t)));
         CU_TRY(cudaMemset(d.item_counter, 0, sizeof(uint32_t)));
-        CU_TRY(cudaMallocHost(&d.h_jobs, lb2::kMaxJobs * sizeof(lb2::LayerJob)));
         CU_TRY(cudaEventCreateWithFlags(&d.ev_user, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&d.ev_comp, cudaEventDisableTiming));
         CU_TRY(lb2::trunk_kernel_setup());
@@ -941,9 +981,10 @@ void lb2_destroy(lb2_ctx* ctx) {
         for (auto& sl : d.slots) free_slot(&sl);
         if (d.ev_user) cudaEventDestroy(d.ev_user);
         if (d.ev_comp) cudaEventDestroy(d.ev_comp);
-        cudaFree(d.rot); cudaFree(d.jobs_dev); cudaFree(d.item_counter);
+        cudaFree(d.rot); cudaFree(d.item_counter);
+        for (int w = 0; w < kSets; w++) { cudaFree(d.jobs_dev[w]); cudaFreeHost(d.h_jobs[w]); }
         cudaFreeHost(d.h_planes[0]); cudaFreeHost(d.h_planes[1]); cudaFreeHost(d.h_rot);
-        cudaFreeHost(d.h_probs); cudaFreeHost(d.h_win); cudaFreeHost(d.h_jobs);
+        cudaFreeHost(d.h_probs); cudaFreeHost(d.h_win);
         cudaStreamDestroy(d.stream);
     }
     delete ctx;
@@ -1055,8 +1096,7 @@ int lb2_eval_both_device(lb2_ctx* ctx, int dev_index, const uint32_t* d_pol, con
     const int chunk = (int)ctx->max_batch;
     for (int k = 0; k < 2; k++)
         if (need[k] && d->net[k].cap < std::min(n, chunk)) {
-            CU_TRY(cudaStreamSynchronize(d->stream));   // nothing may be computing in the workspace while it grows
-            CU_TRY(cudaStreamSynchronize(st));
+            CU_TRY(cudaDeviceSynchronize());   // nothing may be using the workspace while it grows
             if ((rc = ensure_workspace(&d->net[k], k, std::min(n, chunk)))) return rc;
         }
     if (st != d->stream) {   // the workspace is shared with host-buffer calls running on the compute stream
@@ -1067,7 +1107,7 @@ int lb2_eval_both_device(lb2_ctx* ctx, int dev_index, const uint32_t* d_pol, con
         const int c = std::min(chunk, n - lo);
         rc = eval_on_device(ctx, d, d_pol ? d_pol + (size_t)lo * lb2::kPoints : nullptr,
                             d_val ? d_val + (size_t)lo * lb2::kPoints : nullptr, d_rot + lo, c, temp,
-                            d_probs ? d_probs + (size_t)lo * lb2::kPoints : nullptr, d_win ? d_win + lo : nullptr, st);
+                            d_probs ? d_probs + (size_t)lo * lb2::kPoints : nullptr, d_win ? d_win + lo : nullptr, st, 0);
         if (rc) return rc;
     }
     if (st != d->stream) {
@@ -1121,6 +1161,8 @@ int lb2_set_option(lb2_ctx* ctx, const char* name, long value) {
         ctx->cta_pair = value ? 1 : 0;
     } else if (!strcmp(name, "dynamic_items")) {
         ctx->dynamic_items = value ? 1 : 0;
+    } else if (!strcmp(name, "overlap_io")) {
+        ctx->overlap_io = value ? 1 : 0;
     } else if (!strcmp(name, "profile_trunk")) {
         ctx->profile_trunk = value;
     } else if (!strcmp(name, "max_batch")) {
@@ -1138,6 +1180,7 @@ long lb2_get_option(lb2_ctx* ctx, const char* name) {
     if (!strcmp(name, "max_batch")) return ctx->max_batch;
     if (!strcmp(name, "cta_pair")) return ctx->cta_pair;
     if (!strcmp(name, "dynamic_items")) return ctx->dynamic_items;
+    if (!strcmp(name, "overlap_io")) return ctx->overlap_io;
     if (!strcmp(name, "sm_count")) return ctx->dev.empty() ? 0 : ctx->dev[0].sm_count;
     if (!strcmp(name, "stat_positions")) return ctx->stat_positions.load();
     if (!strcmp(name, "stat_batches")) return ctx->stat_batches.load();
@@ -1213,14 +1256,14 @@ int lb2_debug_trunk(lb2_ctx* ctx, int kind, const uint32_t* planes, const uint8_
     CU_TRY(cudaMemcpyAsync(nd.planes, planes, (size_t)n * lb2::kPoints * sizeof(uint32_t), cudaMemcpyHostToDevice, d->stream));
     lb2::ExpandArgs ea;
     memset(&ea, 0, sizeof ea);
-    ea.rotation = d->rot; ea.n = n; ea.n_nets = 1; ea.zero_word = d->item_counter;
-    ea.planes[0] = nd.planes; ea.x0[0] = nd.x0; ea.chunk_rows[0] = nd.rows5;
+    ea.rotation = d->rot; ea.n = n; ea.n_nets = 1;
+    ea.planes[0] = nd.planes; ea.x0[0] = nd.x0[0]; ea.chunk_rows[0] = nd.rows5;
     CU_TRY(lb2::launch_expand(ea, d->stream));
     ctx->launches++;
     int limit[2] = {0, 0};
     limit[kind] = n_layers;
     JobPlan pl;
-    if ((rc = run_trunk(ctx, d, need, n, limit, d->stream, &pl))) return rc;
+    if ((rc = run_trunk(ctx, d, need, n, limit, d->stream, &pl, 0))) return rc;
     const int c_out = nd.trunk[n_layers - 1].c_out;
     std::vector<__half> host((size_t)(c_out / 8) * nd.rows3 * 8);
     CU_TRY(cudaMemcpyAsync(host.data(), pl.last_act[kind], host.size() * sizeof(__half), cudaMemcpyDeviceToHost, d->stream));

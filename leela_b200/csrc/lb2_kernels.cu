@@ -57,7 +57,6 @@ __device__ __forceinline__ float elu1(float v) { return v > 0.0f ? v : (__expf(v
 __global__ void __launch_bounds__(256) expand_planes_kernel(const ExpandArgs A) {
     if (LB2_PDL) grid_dep_launch();   // the trunk may set itself up while we run; it waits for us before reading
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t == 0 && A.zero_word) *A.zero_word = 0;
     const size_t per_net = (size_t)A.n * 441;
     const size_t total = per_net * A.n_nets;
     if (t >= total) {
@@ -622,7 +621,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                 int q = 0;
                 if (lane == 0) {
                     while (it >= *pub_done + kClaimAhead) __nanosleep(20);
-                    q = dynamic ? P.item_begin + (int)atomicAdd(P.next_item, 1u) : first + (int)it * step;
+                    q = dynamic ? P.item_begin + (int)(atomicAdd(P.next_item, 1u) - P.claim_base) : first + (int)it * step;
                 }
                 q = __shfl_sync(0xffffffffu, q, 0);
                 if (q < P.item_end) locate_item(P, jobs, q, j, jj, idx);

@@ -96,7 +96,8 @@ struct TrunkParams {
     int16_t round_first[kMaxRounds], round_jobs[kMaxRounds];  // its jobs: round_jobs consecutive entries of the job table
     uint32_t epoch;
     int32_t use_flags;  // 1: cross-CTA dataflow through flags (single persistent launch)
-    uint32_t* next_item;        // dynamic scheduling: global in-order item counter (zero at launch), or null
+    uint32_t* next_item;        // dynamic scheduling: global in-order claim counter, or null. It is never reset:
+    uint32_t claim_base;        // its value when this launch starts (every launch advances it by items + clusters)
     unsigned long long* trace;  // optional timeline buffer [cta][kTraceItems][kTraceEvents] of %globaltimer ns
     int32_t debug_flags;  // timing experiments only (results wrong): bit1 = all tap offsets 0, bit2 = no epilogue math,
                           // bit3 = no B loads, bit4 = no A loads, bit5 = only the first M half of 3x3 layers, bit6 = epilogue does nothing
@@ -111,7 +112,6 @@ struct ExpandArgs {
     int32_t n, n_nets;
     const uint8_t* pf;           // optional buffer to pull into L2
     size_t pf_bytes;
-    uint32_t* zero_word;         // optional word to clear (the trunk's dynamic-scheduling counter)
 };
 
 struct HeadArgs {
