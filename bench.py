@@ -25,6 +25,8 @@ positions sharded, no collective on the data path (weak scaling).
             host cores, bounded sample, rank 0 at N=1 only.
 
 --impl reference times that CPU path alone with the same JSON shape.
+--engine runs the engine-level benchmark instead (GTP genmove at a fixed think time and netbench:
+the drop-in engine beside the reference's own CPU engine); it is not part of the driver's contract.
 """
 from __future__ import annotations
 
@@ -163,6 +165,27 @@ def run_reference(args):
             "cpu_baseline": info,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_engine(args):
+    """BASELINE.json configs[4] at engine level: GTP genmove at a fixed think time (and `netbench`),
+    the drop-in engine (reference search + B200 evaluator) beside the reference's own CPU engine
+    (oracle/_ref/ref_engine, built from /root/reference). One JSON object per engine and leg."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import engine_bench as eb
+    from oracle import reference
+    ref_engine = os.path.join(ROOT, "oracle", "_ref", "ref_engine")
+    env = reference._env()
+    cores = os.cpu_count() or 1
+    for netbench in (False, True):
+        a = eb.parser().parse_args(["--threads", str(64 if netbench else min(cores, 64)), "--gpus", str(args.gpus)] +
+                                   (["--netbench"] if netbench else []))
+        print(json.dumps(eb.run_ours(a)), flush=True)
+        threads = min(cores, 64)
+        cmd = [ref_engine, "-g", "-t", str(threads), "--noponder", "--nobook", "--lagbuffer", "0"]
+        print(json.dumps(eb.summarize("reference_cpu_engine", *eb.run(cmd, eb.script_for(a), env=env),
+                                      {"threads": threads, "think_s": a.seconds, "blas_core": env.get("OPENBLAS_CORETYPE")})), flush=True)
     return 0
 
 
@@ -337,10 +360,13 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--engine", action="store_true", help="engine-level benchmark instead: GTP genmove / netbench, ours vs the reference's CPU engine")
     ap.add_argument("--flush-l2", action="store_true", help="evict L2 before every step instead of cycling an input pool larger than L2")
     ap.add_argument("--overlap-io", action="store_true", help="A/B: expand/heads kernels of host-buffer calls on the I/O slot's stream")
     ap.add_argument("--e2e-threads", type=int, default=2, help="host threads calling the C ABI concurrently in the e2e leg")
     args = ap.parse_args()
+    if args.engine:
+        return run_engine(args)
     if args.impl == "reference":
         return run_reference(args)
     if args.gpus > 1 and "RANK" not in os.environ:

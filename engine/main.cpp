@@ -12,7 +12,7 @@
 //   --dump-planes OUT N SEED   write the feature planes of N seeded self-play positions and exit
 //                              (no GPU needed; tests compare them with the reference's own)
 //   -DLB2_REFERENCE_BUILD  the same main for the reference's own CPU engine (oracle/ref/Makefile
-//                          `ref_engine`, the baseline of tools/engine_bench.py): B200 options dropped
+//                          `ref_engine`, the baseline of `bench.py --engine`): B200 options dropped
 //   the OpenCL self-test (GTP.cpp:105-125) is not run: it pins the reference's 192-wide weights,
 //   which are not in the snapshot.
 #include <cstdio>

@@ -1,6 +1,6 @@
 """GPU bring-up checks, one step per subprocess so a hang in one does not hide the others.
-Usage (on the GPU box): python tools/gpu_debug.py            # runs every step with timeouts
-                        python tools/gpu_debug.py step NAME  # one step in-process
+Usage (on the GPU box): python tests/gpu_bringup.py            # runs every step with timeouts
+                        python tests/gpu_bringup.py step NAME  # one step in-process
 """
 import os
 import subprocess

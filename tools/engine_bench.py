@@ -1,13 +1,13 @@
 """Engine-level benchmark (BASELINE.json configs[4]): GTP genmove at a fixed think time, playouts/s.
 
-  ours       engine/_build/leela_b200_engine — the reference's search (its own sources) with the B200
-             evaluator behind Network; search threads' single-position requests are coalesced into
-             device batches by the library's queue
-  reference  oracle/_ref/ref_engine — the reference's own CPU engine (OpenBLAS path), same GTP script
+Runs engine/_build/leela_b200_engine — the reference's search (its own sources) with the B200
+evaluator behind Network; search threads' single-position requests are coalesced into device batches
+by the library's queue — through a GTP script and prints one JSON object.
 
-Usage (GPU box): python tools/engine_bench.py [--seconds 5] [--moves 4] [--threads 64] [--gpus 1]
-                 [--impl ours|reference|both] [--max-outstanding 2]
-Prints one JSON object per engine.
+Usage (GPU box): python tools/engine_bench.py [--seconds 5] [--moves 4] [--threads 16] [--gpus 1]
+                 [--max-outstanding 2] [--netbench] [--extra "..."]
+The same script against the reference's own CPU engine (the baseline) is `python bench.py --engine`:
+only bench.py and tests/ may execute anything under oracle/.
 """
 from __future__ import annotations
 
@@ -22,7 +22,6 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OURS = os.path.join(ROOT, "engine", "_build", "leela_b200_engine")
 WEIGHTS = os.path.join(ROOT, "engine", "_build", "weights_synth.lb2w")
-REF = os.path.join(ROOT, "oracle", "_ref", "ref_engine")
 STATS = re.compile(r"(\d+) visits, (\d+) nodes, (\d+) playouts, (\d+) p/s")
 BATCH = re.compile(r"B200 evaluator: (\d+) positions in (\d+) device batches \(mean batch ([\d.]+)\), (\d+) requests")
 
@@ -62,45 +61,42 @@ def summarize(name, rc, text, per_move, moves, wall, extra):
     return out
 
 
-def main():
+def parser():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=int, default=5)
     ap.add_argument("--moves", type=int, default=4)
-    ap.add_argument("--threads", type=int, default=64)
+    ap.add_argument("--threads", type=int, default=16)
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--impl", default="both", choices=["ours", "reference", "both"])
     ap.add_argument("--max-outstanding", type=int, default=2)
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--netbench", action="store_true", help="run the GTP `netbench` command (Network::benchmark) instead of genmove")
-    ap.add_argument("--extra", default="", help="extra engine options for ours, e.g. '--mature_threshold 2 --eval_thresh 0'")
-    args = ap.parse_args()
-    script = gtp_script(args.seconds, args.moves) if not args.netbench else "boardsize 19\nclear_board\nnetbench\nquit\n"
-    results = []
-    if args.impl in ("ours", "both"):
-        if not os.path.exists(WEIGHTS):
-            sys.path.insert(0, ROOT)
-            from engine import build as eb
-            eb.write_synth_weights()
-        cmd = [OURS, "-g", "-t", str(args.threads), "--noponder", "--nobook", "--lagbuffer", "0", "--weights", WEIGHTS,
-               "--max-outstanding", str(args.max_outstanding)]
-        if args.batch:
-            cmd += ["--batch", str(args.batch)]
-        for g in range(args.gpus):
-            cmd += ["--gpu", str(g)]
-        cmd += args.extra.split()
-        results.append(summarize("leela_b200_engine", *run(cmd, script),
-                                 {"threads": args.threads, "gpus": args.gpus, "think_s": args.seconds,
-                                  "max_outstanding": args.max_outstanding, "extra": args.extra}))
-    if args.impl in ("reference", "both"):
+    ap.add_argument("--extra", default="", help="extra engine options, e.g. '--mature_threshold 2 --eval_thresh 0'")
+    return ap
+
+
+def script_for(args) -> str:
+    return gtp_script(args.seconds, args.moves) if not args.netbench else "boardsize 19\nclear_board\nnetbench\nquit\n"
+
+
+def run_ours(args) -> dict:
+    if not os.path.exists(WEIGHTS):
         sys.path.insert(0, ROOT)
-        from oracle import reference
-        env = reference._env()
-        threads = min(args.threads, os.cpu_count() or 1, 64)
-        cmd = [REF, "-g", "-t", str(threads), "--noponder", "--nobook", "--lagbuffer", "0"]
-        results.append(summarize("reference_cpu_engine", *run(cmd, script, env=env),
-                                 {"threads": threads, "think_s": args.seconds, "blas_core": env.get("OPENBLAS_CORETYPE")}))
-    for r in results:
-        print(json.dumps(r), flush=True)
+        from engine import build as eb
+        eb.write_synth_weights()
+    cmd = [OURS, "-g", "-t", str(args.threads), "--noponder", "--nobook", "--lagbuffer", "0", "--weights", WEIGHTS,
+           "--max-outstanding", str(args.max_outstanding)]
+    if args.batch:
+        cmd += ["--batch", str(args.batch)]
+    for g in range(args.gpus):
+        cmd += ["--gpu", str(g)]
+    cmd += args.extra.split()
+    return summarize("leela_b200_engine", *run(cmd, script_for(args)),
+                     {"threads": args.threads, "gpus": args.gpus, "think_s": args.seconds,
+                      "max_outstanding": args.max_outstanding, "extra": args.extra})
+
+
+def main():
+    print(json.dumps(run_ours(parser().parse_args())), flush=True)
 
 
 if __name__ == "__main__":
