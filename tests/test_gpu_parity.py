@@ -180,12 +180,15 @@ def test_batch_and_slot_invariance(ev, ref_golden):
     perm = np.random.default_rng(3).permutation(96)
     pp2, vv2 = ev.eval_both(pp[perm], vp[perm], rot[perm], TEMP)
     assert np.array_equal(pp2, full_p[perm]) and np.array_equal(vv2, full_v[perm])
-    ev.set_option("max_batch", 7)
+    ens_p, ens_v = ev.eval_ensemble(pp[:5], vp[:5], TEMP)
+    ev.set_option("max_batch", 7)   # smaller than one ensemble position's 8 symmetries
     try:
         p3, v3 = ev.eval_both(pp, vp, rot, TEMP)
+        ens_p3, ens_v3 = ev.eval_ensemble(pp[:5], vp[:5], TEMP)
     finally:
         ev.set_option("max_batch", 256)
     assert np.array_equal(p3, full_p) and np.array_equal(v3, full_v)
+    assert np.array_equal(ens_p3, ens_p) and np.array_equal(ens_v3, ens_v)
 
 
 def test_deterministic(ev, ref_golden):
