@@ -74,6 +74,10 @@ int dump_planes(const char* out, int n, uint32_t seed) {
     std::vector<uint32_t> pol((size_t)n * 361), val((size_t)n * 361);
     std::vector<uint8_t> rot((n + 3) / 4 * 4, 0);
     std::vector<int32_t> to_move(n), movenum(n);
+    // the raw positions beside the planes (OUT.raw, "LB2RAW01"): what lb2_planes_from_position takes
+    std::vector<uint8_t> stones((size_t)n * 361);
+    std::vector<int32_t> ko(n), last(n), prev(n);
+    std::vector<float> komi(n);
     Random::get_Rng()->seedrandom(seed);
     std::mt19937 pick(seed * 2654435761u + 17u);
     int got = 0;
@@ -84,6 +88,19 @@ int dump_planes(const char* out, int n, uint32_t seed) {
         rot[got] = (uint8_t)(got % 8);
         to_move[got] = s.get_to_move();
         movenum[got] = s.get_movenum();
+        auto index_of = [&](int vertex) {
+            if (vertex <= 0) return -1;   // none or pass
+            const std::pair<int, int> xy = s.board.get_xy(vertex);
+            return xy.second * 19 + xy.first;
+        };
+        for (int idx = 0; idx < 361; idx++) {
+            const FastBoard::square_t sq = s.board.get_square(s.board.get_vertex(idx % 19, idx / 19));
+            stones[(size_t)got * 361 + idx] = sq == FastBoard::BLACK ? 1 : (sq == FastBoard::WHITE ? 2 : 0);
+        }
+        ko[got] = index_of(s.get_komove());
+        last[got] = index_of(s.get_last_move());
+        prev[got] = index_of(s.get_prevlast_move());
+        komi[got] = s.get_komi();
         got++;
     };
     GameState game;
@@ -111,6 +128,18 @@ int dump_planes(const char* out, int n, uint32_t seed) {
     fwrite(rot.data(), 1, rot.size(), f);
     fwrite(to_move.data(), 4, n, f);
     fwrite(movenum.data(), 4, n, f);
+    fclose(f);
+    const std::string raw_path = std::string(out) + ".raw";
+    f = fopen(raw_path.c_str(), "wb");
+    if (!f) { perror(raw_path.c_str()); return 2; }
+    fwrite("LB2RAW01", 1, 8, f);
+    fwrite(hdr, 4, 2, f);
+    fwrite(stones.data(), 1, stones.size(), f);
+    fwrite(to_move.data(), 4, n, f);
+    fwrite(ko.data(), 4, n, f);
+    fwrite(last.data(), 4, n, f);
+    fwrite(prev.data(), 4, n, f);
+    fwrite(komi.data(), 4, n, f);
     fclose(f);
     return 0;
 }

@@ -117,6 +117,20 @@ int lb2_submit_value(lb2_ctx* ctx, const uint32_t* planes, const uint8_t* rotati
                      float* winrate_out, lb2_callback cb, void* user);
 int lb2_drain(lb2_ctx* ctx);
 
+/* Feature planes from a RAW position — replaces Network::gather_features_policy / _value
+ * (Network.cpp:883-1201) together with the FastBoard queries they make (liberties, liberties after a
+ * move, the ladder readers: FastBoard.cpp:2482-2564, 2647-2837), bit for bit, with a board of this
+ * library's own. Pure host code (no device needed); thread-safe.
+ *   stones[361]     idx = y*19 + x: 0 empty, 1 black, 2 white
+ *   white_to_move   side to move
+ *   ko_point        idx of the point forbidden by ko (FastState::get_komove), or -1
+ *   last_move       idx of the last move, -1 if none or a pass; prev_move likewise (only used when
+ *                   last_move >= 0, as in Network.cpp:1026-1036)
+ *   komi            white's komi (plane "has_komi" is set for white stones when |komi| > 0.75)
+ * policy_planes / value_planes: [361] packed as lb2_eval_* take them; either may be NULL. */
+int lb2_planes_from_position(const uint8_t* stones, int white_to_move, int ko_point, int last_move, int prev_move,
+                             float komi, uint32_t* policy_planes, uint32_t* value_planes);
+
 /* Replaces OpenCL::get_device_name / Network::get_backend (Network.cpp:1535-1553). */
 const char* lb2_backend_name(lb2_ctx* ctx);
 const char* lb2_last_error(void);

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libleela_b200.so")
-SOURCES = ["lb2_api.cu", "lb2_kernels.cu"]
+SOURCES = ["lb2_api.cu", "lb2_kernels.cu", "lb2_planes.cpp"]
 HEADERS = ["lb2_kernels.cuh", "lb2_ptx.cuh", os.path.join("..", "..", "include", "leela_b200.h")]
 
 

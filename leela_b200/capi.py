@@ -22,7 +22,7 @@ EXPORTS = [
     "lb2_init", "lb2_destroy", "lb2_net_create", "lb2_net_push_conv", "lb2_net_push_ip", "lb2_net_finalize",
     "lb2_eval_policy", "lb2_eval_value", "lb2_eval_both", "lb2_eval_ensemble", "lb2_eval_both_device", "lb2_submit_policy",
     "lb2_submit_value", "lb2_drain", "lb2_backend_name", "lb2_last_error", "lb2_device_count", "lb2_set_option",
-    "lb2_get_option", "lb2_launch_count", "lb2_debug_trunk", "lb2_debug_read_trace",
+    "lb2_get_option", "lb2_launch_count", "lb2_debug_trunk", "lb2_debug_read_trace", "lb2_planes_from_position",
 ]
 
 CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_int)
@@ -55,6 +55,7 @@ def load():
     L.lb2_eval_value.argtypes = [vp, vp, vp, ip, vp]
     L.lb2_eval_both.argtypes = [vp, vp, vp, vp, ip, fp, vp, vp]
     L.lb2_eval_ensemble.argtypes = [vp, vp, vp, ip, fp, vp, vp]
+    L.lb2_planes_from_position.argtypes = [vp, ip, ip, ip, ip, fp, vp, vp]
     L.lb2_eval_both_device.argtypes = [vp, ip, vp, vp, vp, ip, fp, vp, vp, vp]
     L.lb2_submit_policy.argtypes = [vp, vp, vp, ip, fp, vp, CALLBACK, vp]
     L.lb2_submit_value.argtypes = [vp, vp, vp, ip, vp, CALLBACK, vp]
@@ -78,6 +79,16 @@ def check(rc: int):
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def planes_from_position(stones, white_to_move, ko_point=-1, last_move=-1, prev_move=-1, komi=7.5):
+    """Policy and value feature planes (uint32 [361] each) of a raw position; host code, no GPU needed."""
+    L = load()
+    st = np.ascontiguousarray(stones, dtype=np.uint8).reshape(361)
+    pol, val = np.empty(361, dtype=np.uint32), np.empty(361, dtype=np.uint32)
+    check(L.lb2_planes_from_position(_p(st), int(white_to_move), int(ko_point), int(last_move), int(prev_move), float(komi),
+                                     _p(pol), _p(val)))
+    return pol, val
 
 
 class Evaluator:

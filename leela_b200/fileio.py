@@ -107,3 +107,26 @@ def write_weights(path, nets) -> None:
                 f.write(np.array([p.n_in, p.n_out], dtype=np.int32).tobytes())
                 f.write(np.ascontiguousarray(pw, dtype=np.float32).tobytes())
                 f.write(np.ascontiguousarray(pb, dtype=np.float32).tobytes())
+
+
+@dataclasses.dataclass
+class RawPositions:
+    """What lb2_planes_from_position takes (engine --dump-planes writes OUT.raw, "LB2RAW01")."""
+    stones: np.ndarray     # uint8 [n, 361]: 0 empty, 1 black, 2 white
+    to_move: np.ndarray    # int32 [n]: 0 black, 1 white
+    ko: np.ndarray         # int32 [n]: idx or -1
+    last: np.ndarray       # int32 [n]: idx or -1 (none / pass)
+    prev: np.ndarray       # int32 [n]
+    komi: np.ndarray       # float32 [n]
+
+
+def read_raw_positions(path) -> RawPositions:
+    raw = np.fromfile(path, dtype=np.uint8)
+    if raw[:8].tobytes() != b"LB2RAW01":
+        raise ValueError(f"{path}: not a raw positions file")
+    n = int(raw[8:12].view(np.int32)[0])
+    off = 16
+    stones = raw[off:off + n * P].reshape(n, P).copy(); off += n * P
+    ints = raw[off:off + 16 * n].view(np.int32).reshape(4, n).copy(); off += 16 * n
+    komi = raw[off:off + 4 * n].view(np.float32).copy()
+    return RawPositions(stones, ints[0], ints[1], ints[2], ints[3], komi)

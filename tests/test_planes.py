@@ -1,0 +1,73 @@
+"""lb2_planes_from_position: feature planes from RAW positions with the library's own Go board
+(leela_b200/csrc/lb2_planes.cpp) — liberties, liberties after a move, the ladder readers — against
+the reference's gather_features_policy / _value + FastBoard (Network.cpp:883-1201,
+FastBoard.cpp:2482-2564, 2647-2837), bit for bit, on seeded self-play positions.
+
+The positions come out of the drop-in engine's --dump-planes (raw position + planes computed through
+the reference's board queries; tests/test_engine.py pins those planes to the unmodified reference)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from leela_b200 import capi, fileio
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ENGINE = os.path.join(ROOT, "engine", "_build", "leela_b200_engine")
+needs_engine = pytest.mark.skipif(not os.path.exists(ENGINE), reason="engine not built (needs the reference sources at build time)")
+
+
+@needs_engine
+@pytest.mark.parametrize("n,seed", [(2500, 11), (1500, 20261017)])
+def test_own_board_planes_bit_identical(tmp_path, n, seed):
+    out = str(tmp_path / "p.pos")
+    subprocess.run([ENGINE, "-q", "--dump-planes", out, str(n), str(seed)], check=True, timeout=600)
+    want, raw = fileio.read_positions(out), fileio.read_raw_positions(out + ".raw")
+    assert want.n == n and raw.stones.shape == (n, 361)
+    for i in range(n):
+        pol, val = capi.planes_from_position(raw.stones[i], raw.to_move[i], raw.ko[i], raw.last[i], raw.prev[i], raw.komi[i])
+        assert np.array_equal(pol, want.policy_planes[i]), f"policy planes differ at position {i} (move {want.movenum[i]})"
+        assert np.array_equal(val, want.value_planes[i]), f"value planes differ at position {i} (move {want.movenum[i]})"
+    # the set exercises what is hard: ladders (both kinds), captures, kos, full boards
+    assert (want.policy_planes >> 25 & 1).sum() > 50 and (want.policy_planes >> 26 & 1).sum() > 300
+    assert (want.policy_planes >> 27 & 1).sum() > 0 and want.movenum.max() > 300
+
+
+def test_hand_made_positions():
+    empty = np.zeros(361, np.uint8)
+    pol, val = capi.planes_from_position(empty, 0)
+    line3 = np.array([(i % 19 in (2, 16)) or (i // 19 in (2, 16)) for i in range(361)])
+    assert ((pol >> 0) & 1).all() and ((pol >> 31) & 1).astype(bool).tolist() == line3.tolist()
+    assert (((pol >> 13) & 0x3f) != 0).all()           # every point has a liberties-after-move plane set
+    corner_after = (pol[0] >> 13) & 0x3f
+    assert corner_after == 0b10                         # a corner stone has 2 liberties
+    assert ((val >> 30) & 1).astype(bool).tolist() == line3.tolist()
+    # a working ladder: white stone at (3,3) in atari after black's net of stones; black to move can capture in a ladder
+    st = empty.copy()
+    def at(x, y): return y * 19 + x
+    st[at(3, 3)] = 2
+    for x, y in ((2, 3), (3, 2), (4, 4)):
+        st[at(x, y)] = 1
+    pol, _ = capi.planes_from_position(st, 0, komi=7.5)
+    assert (pol[at(3, 3)] >> 2) & 1 and (pol[at(3, 3)] >> 9) & 1      # opponent stone with 2 liberties
+    assert (pol[at(3, 4)] >> 26) & 1 or (pol[at(4, 3)] >> 26) & 1      # one of the ataris starts a winning ladder
+    assert (pol[at(3, 3)] >> 30) & 1                                   # white stones carry the komi plane
+    pol0, _ = capi.planes_from_position(st, 0, komi=0.5)
+    assert not (pol0[at(3, 3)] >> 30) & 1
+    # history and ko planes
+    pol, val = capi.planes_from_position(st, 1, ko_point=at(10, 10), last_move=at(4, 4), prev_move=at(3, 3))
+    assert (pol[at(10, 10)] >> 27) & 1 and (pol[at(4, 4)] >> 28) & 1 and (pol[at(3, 3)] >> 29) & 1
+    assert (val[at(10, 10)] >> 31) & 1
+    pol, _ = capi.planes_from_position(st, 1, last_move=-1, prev_move=at(3, 3))   # no last move: no history at all
+    assert not ((pol >> 28) & 3).any()
+
+
+def test_bad_arguments_are_rejected():
+    st = np.zeros(361, np.uint8)
+    st[5] = 3
+    with pytest.raises(capi.Lb2Error) as e:
+        capi.planes_from_position(st, 0)
+    assert e.value.code == -1
+    with pytest.raises(capi.Lb2Error):
+        capi.planes_from_position(np.zeros(361, np.uint8), 0, ko_point=361)
