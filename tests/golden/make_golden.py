@@ -14,6 +14,9 @@ edge_golden.npz  hand-made edge cases (all-zero planes, all-one planes, single s
 layer_golden.npz one call of each convolve<> / innerproduct<> instantiation the nets use, on
                  the deterministic inputs of tests/golden/cases.py (large outputs strided by 5).
 bench_positions.npz  1024 self-play positions (planes only) for bench.py.
+bench_golden.npz the correctness set: the reference's policy (361 floats) and
+                 value for all 1024 bench positions, rotation i%8 (`make_golden.py correctness`
+                 regenerates only this file from the committed bench_positions.npz).
 """
 import os
 import sys
@@ -31,7 +34,20 @@ from tests.golden import cases  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+def correctness_set():
+    assert reference.build(), "reference harness unavailable"
+    bp = np.load(os.path.join(HERE, "bench_positions.npz"))
+    n = bp["policy_planes"].shape[0]
+    ps = fileio.Positions(bp["policy_planes"], bp["value_planes"], bp["rotation"], np.zeros(n, np.int32), np.zeros(n, np.int32))
+    out = reference.evaluate(ps)
+    np.savez_compressed(os.path.join(HERE, "bench_golden.npz"), policy=out.policy, value=out.value,
+                        softmax_temp=np.float32(out.softmax_temp))
+    print("bench_golden.npz", os.path.getsize(os.path.join(HERE, "bench_golden.npz")))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "correctness":
+        return correctness_set()
     assert reference.build(), "reference harness unavailable"
     with tempfile.TemporaryDirectory() as d:
         pre = os.path.join(d, "g")
@@ -75,6 +91,7 @@ def main():
         bp = fileio.read_positions(pre + "b.pos")
         np.savez_compressed(os.path.join(HERE, "bench_positions.npz"), policy_planes=bp.policy_planes,
                             value_planes=bp.value_planes, rotation=bp.rotation)
+    correctness_set()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))
 

@@ -48,6 +48,18 @@ def test_policy_and_value_vs_reference(ev, ref_golden):
     np.testing.assert_allclose(probs.sum(1), 1.0, atol=1e-4)
 
 
+def test_correctness_set_1024_positions(ev):
+    """SURVEY.md section 8d correctness set: all 1024 bench positions (rotation i%8) against the reference's
+    outputs — max / mean error of probabilities and value, top-1 agreement with ties counted separately."""
+    from tests import parity_report
+    r = parity_report.report(ev)
+    print(r)
+    assert r["positions"] == 1024
+    assert r["policy_max_abs_err"] < TOL_P and r["value_max_abs_err"] < TOL_V
+    assert r["policy_mean_abs_err"] < 3e-5 and r["value_mean_abs_err"] < 1e-3
+    assert r["top1_disagree"] == 0 and r["top1_agree"] >= 0.97 * r["positions"]
+
+
 def test_separate_entry_points_match_eval_both(ev, ref_golden):
     g = ref_golden
     probs, win = ev.eval_both(g["policy_planes"], g["value_planes"], g["rotation"], TEMP)
