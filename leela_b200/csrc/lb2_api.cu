@@ -99,7 +99,6 @@ struct NetDev {
     uint32_t* planes = nullptr;
     __half* x0[1 + kIoSlots] = {};                // first-conv input (S=21 row space)
     __half* act[2] = {nullptr, nullptr};
-    float* out = nullptr;    // probs [cap][361] or winrate [cap]
     uint32_t* flags = nullptr;
     int flags_stride = 0;
     CUtensorMap tm_x0[1 + kIoSlots], tm_act[2];
@@ -125,17 +124,12 @@ struct DeviceState {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     NetDev net[2];
-    uint8_t* rot = nullptr;
+    uint8_t* rot = nullptr;               // rotation buffer of lb2_debug_trunk
     lb2::LayerJob* jobs_dev[kSets] = {};   // one job table per workspace set (they differ in x0 / zbuf)
     uint32_t* item_counter = nullptr;     // dynamic scheduling: claim counter, never reset
     uint32_t claim_base = 0;              // its value at the start of the next trunk launch
-    // pinned staging
-    uint32_t* h_planes[2] = {nullptr, nullptr};
-    uint8_t* h_rot = nullptr;
-    float* h_probs = nullptr;
-    float* h_win = nullptr;
-    lb2::LayerJob* h_jobs[kSets] = {};
-    int cap = 0;
+    lb2::LayerJob* h_jobs[kSets] = {};    // pinned staging of the job tables
+    int cap = 0;                          // capacity of `rot`
     uint32_t epoch = 0;
     unsigned long long* trace = nullptr;   // debug timeline buffer (option "trace")
     std::vector<cudaEvent_t> prof_events;  // (start, stop) pairs around trunk launches
@@ -330,9 +324,9 @@ int make_act_tmap(CUtensorMap* tm, __half* base, int rows, int chunks, int halo)
 
 void free_workspace(NetDev* nd) {
     cudaFree(nd->planes); cudaFree(nd->act[0]); cudaFree(nd->act[1]);
-    cudaFree(nd->out); cudaFree(nd->flags);
+    cudaFree(nd->flags);
     for (int w = 0; w < kSets; w++) { cudaFree(nd->x0[w]); cudaFree(nd->zbuf[w]); nd->x0[w] = nullptr; nd->zbuf[w] = nullptr; }
-    nd->planes = nullptr; nd->act[0] = nd->act[1] = nullptr; nd->out = nullptr; nd->flags = nullptr;
+    nd->planes = nullptr; nd->act[0] = nd->act[1] = nullptr; nd->flags = nullptr;
     nd->cap = 0;
 }
 
@@ -353,8 +347,6 @@ int ensure_workspace(NetDev* nd, int kind, int cap) {
     CU_TRY(cudaMalloc(&nd->act[1], act_bytes));
     CU_TRY(cudaMemset(nd->act[0], 0, act_bytes));  // padding rows/columns must start (and stay) zero
     CU_TRY(cudaMemset(nd->act[1], 0, act_bytes));
-    const size_t out_elems = kind == LB2_POLICY ? (size_t)cap * lb2::kPoints : (size_t)cap;
-    CU_TRY(cudaMalloc(&nd->out, out_elems * sizeof(float)));
     nd->flags_stride = nd->rows5 / lb2::kTileRows + 2;
     const size_t n_flags = (size_t)lb2::kMaxLayers * lb2::kMaxSplit * nd->flags_stride;
     CU_TRY(cudaMalloc(&nd->flags, n_flags * sizeof(uint32_t)));
@@ -368,17 +360,12 @@ int ensure_workspace(NetDev* nd, int kind, int cap) {
     return LB2_OK;
 }
 
+// device-side rotation buffer of lb2_debug_trunk (host-buffer calls use their I/O slot's)
 int ensure_device_staging(DeviceState* d, int cap) {
     if (d->cap >= cap) return LB2_OK;
-    if (d->cap) {
-        cudaFree(d->rot); cudaFreeHost(d->h_planes[0]); cudaFreeHost(d->h_planes[1]); cudaFreeHost(d->h_rot);
-        cudaFreeHost(d->h_probs); cudaFreeHost(d->h_win);
-    }
+    cudaFree(d->rot);
+    d->rot = nullptr;
     CU_TRY(cudaMalloc(&d->rot, cap));
-    for (int k = 0; k < 2; k++) CU_TRY(cudaMallocHost(&d->h_planes[k], (size_t)cap * lb2::kPoints * sizeof(uint32_t)));
-    CU_TRY(cudaMallocHost(&d->h_rot, cap));
-    CU_TRY(cudaMallocHost(&d->h_probs, (size_t)cap * lb2::kPoints * sizeof(float)));
-    CU_TRY(cudaMallocHost(&d->h_win, (size_t)cap * sizeof(float)));
     d->cap = cap;
     return LB2_OK;
 }
@@ -983,8 +970,6 @@ void lb2_destroy(lb2_ctx* ctx) {
         if (d.ev_comp) cudaEventDestroy(d.ev_comp);
         cudaFree(d.rot); cudaFree(d.item_counter);
         for (int w = 0; w < kSets; w++) { cudaFree(d.jobs_dev[w]); cudaFreeHost(d.h_jobs[w]); }
-        cudaFreeHost(d.h_planes[0]); cudaFreeHost(d.h_planes[1]); cudaFreeHost(d.h_rot);
-        cudaFreeHost(d.h_probs); cudaFreeHost(d.h_win);
         cudaStreamDestroy(d.stream);
     }
     delete ctx;
