@@ -22,6 +22,10 @@
 #include "../../include/leela_b200.h"
 #include "lb2_kernels.cuh"
 
+#ifndef LB2_RESIDENT_DEFAULT
+#define LB2_RESIDENT_DEFAULT 0   // measured: -77 % weight traffic from L2, launch time unchanged within +-1 % -> off; tools/ab_variants.py builds both
+#endif
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -128,6 +132,7 @@ struct DeviceState {
     lb2::LayerJob* jobs_dev[kSets] = {};   // one job table per workspace set (they differ in x0 / zbuf)
     uint32_t* item_counter = nullptr;     // dynamic scheduling: claim counter, never reset
     uint32_t claim_base = 0;              // its value at the start of the next trunk launch
+    uint32_t net_claim_base[2] = {0, 0};  // the same for the per-net counters of the resident-weights mode
     lb2::LayerJob* h_jobs[kSets] = {};    // pinned staging of the job tables
     int cap = 0;                          // capacity of `rot`
     uint32_t epoch = 0;
@@ -173,6 +178,8 @@ struct lb2_ctx {
     long overlap_io = 0;   // 1: host-buffer calls run expand / heads on the I/O slot's stream, beside the trunk of another
                            // call. Measured 2-3 % slower end to end (the value head's blocks hold up the next trunk's CTAs): off.
     long dynamic_items = 1;
+    long resident_weights = LB2_RESIDENT_DEFAULT;   // keep each CTA's half of a layer's weights in shared memory across the layer's items
+    long policy_clusters = -1;   // resident mode: clusters that prefer the policy net (-1 = split by estimated work)
     std::atomic<long> launches{0};
     std::atomic<long> stat_positions{0}, stat_batches{0}, stat_requests{0};  // async queue: positions, device batches, requests
     std::mutex eval_mu;                 // guards enqueueing on the devices and the shared workspaces
@@ -380,19 +387,25 @@ struct JobPlan {
     int total_items = 0;
     const __half* last_act[2] = {nullptr, nullptr};
     int tmap_base[2] = {0, 3};
+    int net_begin[2] = {0, 0}, net_end[2] = {0, 0};   // net-major order: item index range of each net
+    double net_cost[2] = {0, 0};                      // tensor-pipe cycles, for splitting the clusters between the nets
 };
 
 // Interleave the two nets layer by layer: P1 V1 P2a P2b V2 ... so that one launch round holds the
 // independent jobs of equal depth (a layer wider than 128 channels contributes one job per column
 // split; they are consecutive in the table).
-JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2], bool pair, int ws) {
+// `net_major` (resident-weights mode): all policy jobs first, then all value jobs, every job a round of its own
+JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2], bool pair, int ws, bool net_major) {
     JobPlan pl;
     size_t depth = 0;
     for (int k = 0; k < 2; k++)
         if (run[k]) depth = std::max(depth, (size_t)std::min<int>(limit_layers[k], d->net[k].trunk.size()));
     int prev_job[2] = {-1, -1}, prev_split[2] = {1, 1};
-    for (size_t l = 0; l < depth; l++) {
-        for (int k = 0; k < 2; k++) {
+    for (size_t outer = 0; outer < (net_major ? (size_t)2 : depth); outer++) {
+        for (size_t inner = 0; inner < (net_major ? depth : (size_t)2); inner++) {
+            const size_t l = net_major ? inner : outer;
+            const int k = net_major ? (int)outer : (int)inner;
+            if (net_major && inner == 0) pl.net_begin[k] = pl.net_end[k] = pl.total_items;
             NetDev& nd = d->net[k];
             if (!run[k] || l >= nd.trunk.size() || (int)l >= limit_layers[k]) continue;
             const TrunkLayerDev& t = nd.trunk[l];
@@ -428,7 +441,7 @@ JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2], bool 
                 J.wpk2 = t.wpk2[sp];
                 J.bias = t.bias[sp];
                 J.flags = nd.flags + ((size_t)l * lb2::kMaxSplit + sp) * nd.flags_stride;
-                J.head_slot = k * lb2::kMaxSplit + sp;
+                J.head_slot = net_major ? k : k * lb2::kMaxSplit + sp;
                 if (l + 1 == nd.trunk.size() && limit_layers[k] > (int)nd.trunk.size()) {
                     // whole net: fold the final 3x3 conv to one channel into this layer's epilogue
                     J.head_taps = 9;
@@ -437,9 +450,15 @@ JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2], bool 
                     J.zparts = sp * lb2::kColParts;
                 }
                 pl.jobs.push_back(J);
-                pl.round_of.push_back((int)l);
+                pl.round_of.push_back(net_major ? (int)l + 1000 * k : (int)l);
+                {   // relative cost of an MMA by width, fitted to the best split measured (48 of 74 clusters on
+                    // the policy net at batch 256): N = 128 runs at 64 cycles, narrower ones are bound by the A read
+                    const double mma = J.n_out >= 128 ? 64.0 : (J.n_out > 64 ? 60.0 : 68.0);
+                    pl.net_cost[k] += (double)J.n_items * J.n_slabs * t.k * t.k * 2 * mma;
+                }
                 pl.tiles.push_back(n_tiles);
                 pl.total_items += J.n_items;
+                if (net_major) pl.net_end[k] = pl.total_items;
                 pl.last_act[k] = nd.act[l & 1];
             }
             prev_job[k] = first_job;
@@ -453,11 +472,25 @@ JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2], bool 
 int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers[2], cudaStream_t st,
               JobPlan* plan_out, int ws) {
     const bool pair = ctx->cta_pair != 0 && d->sm_count >= 2;
-    JobPlan pl = plan_jobs(d, run, n, limit_layers, pair, ws);
+    // resident-weights mode: CTA pairs, the single dataflow launch with dynamic claiming, and every layer's
+    // half of the packed weights must fit the resident area (c_in, c_out <= 128: no column splits)
+    bool resident = pair && ctx->resident_weights != 0 && ctx->trunk_mode == 1 && ctx->dynamic_items != 0;
+    int n_jobs_est = 0;
+    for (int k = 0; k < 2 && resident; k++) {
+        if (!run[k]) continue;
+        for (size_t l = 0; l < d->net[k].trunk.size() && (int)l < limit_layers[k]; l++) {
+            const TrunkLayerDev& t = d->net[k].trunk[l];
+            if (t.n_split != 1 || (size_t)t.k * t.k * t.c_in * (t.c_out / 2) * 2 > (size_t)lb2::kResWeightBytes) resident = false;
+            n_jobs_est++;
+        }
+    }
+    if (n_jobs_est > lb2::kResJobs) resident = false;
+    JobPlan pl = plan_jobs(d, run, n, limit_layers, pair, ws, resident);
     if (pl.jobs.empty()) return fail(LB2_ERR_STATE, "no trunk layers to run");
     if ((int)pl.jobs.size() > lb2::kMaxLaunchJobs) return fail(LB2_ERR_UNSUPPORTED, "too many layers");
     const long key[8] = {n, run[0], run[1], limit_layers[0], limit_layers[1],
-                         (long)reinterpret_cast<uintptr_t>(d->net[0].act[0]), (long)reinterpret_cast<uintptr_t>(d->net[1].act[0]), pair};
+                         (long)reinterpret_cast<uintptr_t>(d->net[0].act[0]), (long)reinterpret_cast<uintptr_t>(d->net[1].act[0]),
+                         (long)pair + 2 * (long)resident};
     if (memcmp(key, d->plan_key[ws], sizeof key)) {
         // the set's job table on the device is reused by back-to-back launches of the same shape;
         // rewrite it only when the shape changes, after earlier work has drained
@@ -512,12 +545,28 @@ int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers
         P.use_flags = 1;
         P.next_item = ctx->dynamic_items ? d->item_counter : nullptr;
         const int grid = pair ? std::min(d->sm_count & ~1, 2 * pl.total_items) : std::min(d->sm_count, pl.total_items);
-        if (P.next_item) {
+        const int n_clusters = pair ? grid / 2 : grid;
+        if (resident) {
+            // each cluster draws items of its preferred net until that counter runs past the end, then helps the
+            // other net: one end marker per cluster per net, i.e. items + clusters claims per net per launch
+            for (int k = 0; k < 2; k++) {
+                P.net_next_item[k] = d->item_counter + 1 + k;
+                P.net_claim_base[k] = d->net_claim_base[k];
+                P.net_item_begin[k] = pl.net_begin[k];
+                P.net_item_end[k] = pl.net_end[k];
+                d->net_claim_base[k] += (uint32_t)(pl.net_end[k] - pl.net_begin[k]) + (uint32_t)n_clusters;
+            }
+            const double total = pl.net_cost[0] + pl.net_cost[1];
+            int pc = total > 0 ? (int)(n_clusters * pl.net_cost[0] / total + 0.5) : n_clusters;
+            if (pl.net_cost[0] > 0 && pl.net_cost[1] > 0) pc = std::max(1, std::min(n_clusters - 1, pc));
+            if (ctx->policy_clusters >= 0 && pl.net_cost[0] > 0 && pl.net_cost[1] > 0) pc = (int)std::min<long>(n_clusters - 1, std::max<long>(1, ctx->policy_clusters));
+            P.policy_clusters = pc;
+        } else if (P.next_item) {
             // every cluster claims until it draws an index past the end: items + clusters claims per launch
             P.claim_base = d->claim_base;
-            d->claim_base += (uint32_t)pl.total_items + (uint32_t)(pair ? grid / 2 : grid);
+            d->claim_base += (uint32_t)pl.total_items + (uint32_t)n_clusters;
         }
-        CU_TRY(lb2::launch_trunk(P, grid, true, pair, st));
+        CU_TRY(lb2::launch_trunk(P, grid, true, pair, resident, st));
         ctx->launches++;
     } else {
         P.use_flags = 0;
@@ -526,7 +575,7 @@ int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers
             P.item_end = P.round_base[r + 1];
             const int items = P.item_end - P.item_begin;
             const int grid = pair ? std::min(d->sm_count & ~1, 2 * items) : std::min(d->sm_count, items);
-            CU_TRY(lb2::launch_trunk(P, grid, false, pair, st));
+            CU_TRY(lb2::launch_trunk(P, grid, false, pair, false, st));
             ctx->launches++;
         }
     }
@@ -929,8 +978,8 @@ int lb2_init(const int* device_ids, int n_devices, lb2_ctx** ctx_out) {
             CU_TRY(cudaMallocHost(&d.h_jobs[w], lb2::kMaxJobs * sizeof(lb2::LayerJob)));
             for (int i = 0; i < 8; i++) d.plan_key[w][i] = -1;
         }
-        CU_TRY(cudaMalloc(&d.item_counter, sizeof(uint32_t)));
-        CU_TRY(cudaMemset(d.item_counter, 0, sizeof(uint32_t)));
+        CU_TRY(cudaMalloc(&d.item_counter, 3 * sizeof(uint32_t)));   // [0] all items, [1 + net] resident-weights mode
+        CU_TRY(cudaMemset(d.item_counter, 0, 3 * sizeof(uint32_t)));
         CU_TRY(cudaEventCreateWithFlags(&d.ev_user, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&d.ev_comp, cudaEventDisableTiming));
         CU_TRY(lb2::trunk_kernel_setup());
@@ -1148,6 +1197,10 @@ int lb2_set_option(lb2_ctx* ctx, const char* name, long value) {
         ctx->dynamic_items = value ? 1 : 0;
     } else if (!strcmp(name, "overlap_io")) {
         ctx->overlap_io = value ? 1 : 0;
+    } else if (!strcmp(name, "resident_weights")) {
+        ctx->resident_weights = value ? 1 : 0;
+    } else if (!strcmp(name, "policy_clusters")) {
+        ctx->policy_clusters = value;
     } else if (!strcmp(name, "profile_trunk")) {
         ctx->profile_trunk = value;
     } else if (!strcmp(name, "max_batch")) {
@@ -1166,6 +1219,8 @@ long lb2_get_option(lb2_ctx* ctx, const char* name) {
     if (!strcmp(name, "cta_pair")) return ctx->cta_pair;
     if (!strcmp(name, "dynamic_items")) return ctx->dynamic_items;
     if (!strcmp(name, "overlap_io")) return ctx->overlap_io;
+    if (!strcmp(name, "resident_weights")) return ctx->resident_weights;
+    if (!strcmp(name, "policy_clusters")) return ctx->policy_clusters;
     if (!strcmp(name, "sm_count")) return ctx->dev.empty() ? 0 : ctx->dev[0].sm_count;
     if (!strcmp(name, "stat_positions")) return ctx->stat_positions.load();
     if (!strcmp(name, "stat_batches")) return ctx->stat_batches.load();

@@ -211,12 +211,21 @@ __device__ __forceinline__ uint32_t geom_pack(uint32_t k, const LayerJob* J) {
            ((uint32_t)J->n_slabs << 14) | ((uint32_t)(J->n_out >> 3) << 8) | (uint32_t)J->S;
 }
 
-template <bool kPair>
+// kRes (pairs only): resident-weights mode, see lb2_kernels.cuh. Shared memory:
+//   streaming:  [stages: A slab + B block][ctrl][bias][head weights][job table]
+//   resident:   [this CTA's half of the layer's weights][stages: A slab only][ctrl][bias][head weights][job table]
+template <bool kPair, bool kRes>
 __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_constant__ TrunkParams P) {
-    constexpr int kStages = kPair ? kStagesPair : kStagesSingle;
-    constexpr int kStageBytes = kPair ? kStageBytesPair : kStageBytesSingle;
+    static_assert(!kRes || kPair, "resident weights need CTA pairs");
+    constexpr int kStages = kRes ? kStagesRes : (kPair ? kStagesPair : kStagesSingle);
+    constexpr int kStageBytes = kRes ? kASlabBytes : (kPair ? kStageBytesPair : kStageBytesSingle);
+    constexpr int kRingOff = kRes ? kResWeightBytes : 0;
+    constexpr int kCtrlOff = kRes ? kResWeightBytes + kStagesRes * kASlabBytes : kTrunkRingBytes;
+    constexpr int kJobSlots = kRes ? kResJobs : kMaxLaunchJobs;
+    constexpr int kHeadW = kRes ? kResHeadSlots : kHeadSlots;
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kTrunkRingBytes);
+    uint8_t* ring = smem + kRingOff;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kCtrlOff);
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tfull_bar = empty_bar + kMaxStages;  // [2] accumulator ready   (MMA -> epilogue)
     uint64_t* tempty_bar = tfull_bar + 2;          // [2] accumulator drained (epilogue -> MMA)
@@ -228,9 +237,9 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
     uint32_t* item_ring = tmem_slot + 4;           // [kClaimRing] work-item entries (see item_pack)
     uint32_t* geom_ring = item_ring + kClaimRing;  // [kClaimRing] the MMA issuer's view of them (see geom_pack)
     // broadcast reads (one wavefront per warp-wide LDS.128), resident for the whole launch
-    float* bias_all = reinterpret_cast<float*>(smem + kTrunkRingBytes + kCtrlBytes);   // [kMaxLaunchJobs][128]
-    float* headw_all = bias_all + kMaxLaunchJobs * 128;                         // [kHeadSlots][9][128]
-    LayerJob* jobs_s = reinterpret_cast<LayerJob*>(headw_all + kHeadSlots * 9 * 128);    // [kMaxLaunchJobs] job table copy
+    float* bias_all = reinterpret_cast<float*>(smem + kCtrlOff + kCtrlBytes);   // [kJobSlots][128]
+    float* headw_all = bias_all + kJobSlots * 128;                              // [kHeadW][9][128]
+    LayerJob* jobs_s = reinterpret_cast<LayerJob*>(headw_all + kHeadW * 9 * 128);    // [kJobSlots] job table copy
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -293,6 +302,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         // The whole warp walks the item ring; one elected lane issues the copies. In pair mode each
         // CTA loads the A slab of its own tile and its half of the output channels of the B block.
         int stage = 0; uint32_t phase = 0; uint32_t pit = 0;
+        int resident_job = -1;   // kRes: the job whose weights (this CTA's half) are in shared memory
         const uint64_t ld_policy = LB2_L2_HINTS == 2 ? l2_policy_evict_last() : (LB2_L2_HINTS == 3 ? l2_policy_evict_first() : 0);
         for (int jj, idx; item_get(item_ring, pit, jj, idx); pit++) {
             const LayerJob& J = jobs[jj];
@@ -308,29 +318,49 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             const int ng = n_tap_groups(ksize);
             const int n_mine = kPair ? (n_out >> 1) : n_out;   // output channels whose weights this CTA stages
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(kPair ? J.wpk2 : J.wpk);
+            // kRes: a new job's weights replace the resident ones unit by unit (unit = the taps of one
+            // stage), each riding on its stage's barrier. Overwriting unit u is safe once the MMAs that
+            // read the bytes under it are done: for a job of the same geometry with at least kStages
+            // stages that is implied by owning the stage's ring slot (the old unit u was last read
+            // n_stages >= kStages stages ago); otherwise drain the pipeline first.
+            const bool reload = kRes && jj != resident_job;
+            bool drain = false;
+            if (reload && resident_job >= 0) {
+                const LayerJob& O = jobs[resident_job];
+                drain = !(O.ksize == ksize && O.n_out == n_out && O.n_slabs == n_slabs && n_slabs * ng >= kStages);
+            }
             if (elect_one()) {
                 int st = stage; uint32_t ph = phase;  // private walk; all lanes advance the shared view below
                 LB2_TRACE(pit, 1);
                 fence_proxy_async();  // order the TMA (async proxy) reads after the acquires above
+                if (drain) {
+                    for (int k = 0; k < kStages; k++) {   // the waits the next kStages stage fills would do, done now
+                        const int s2 = st + k;
+                        mbar_wait(empty_bar + s2 % kStages, (ph ^ (s2 >= kStages ? 1u : 0u)) ^ 1u);
+                    }
+                }
+                uint32_t unit_off = 0;   // kRes: byte offset of the stage's weights inside the resident area
                 for (int s = 0; s < n_slabs; s++) {
                     for (int g = 0; g < ng; g++) {
                         const uint32_t b_bytes = (tap_group_end(ksize, g) - tap_group_begin(g)) * n_mine * 32;
                         mbar_wait(empty_bar + st, ph ^ 1);
-                        uint8_t* sa = smem + st * kStageBytes;
-                        const bool skip_b = (P.debug_flags & 8) != 0, skip_a = (P.debug_flags & 16) != 0;
+                        uint8_t* sa = ring + st * kStageBytes;
+                        const bool skip_b = (P.debug_flags & 8) != 0 || (kRes && !reload), skip_a = (P.debug_flags & 16) != 0;
                         mbar_arrive_expect_tx(full_bar + st, (skip_a ? 0u : a_bytes) + (skip_b ? 0u : b_bytes));
                         if (!skip_a) {
                             if (LB2_L2_HINTS >= 2) tma_load_3d_hint(sa, &P.tmaps[tmap], full_bar + st, 0, row0_8, 2 * s, ld_policy);
                             else tma_load_3d(sa, &P.tmaps[tmap], full_bar + st, 0, row0_8, 2 * s);
                         }
-                        if (!skip_b) bulk_load_1d(sa + kASlabBytes, wsrc + (kPair ? rank * b_bytes : 0u), b_bytes, full_bar + st);
+                        if (!skip_b) bulk_load_1d(kRes ? smem + unit_off : sa + kASlabBytes, wsrc + (kPair ? rank * b_bytes : 0u), b_bytes, full_bar + st);
                         wsrc += kPair ? 2 * b_bytes : b_bytes;
+                        unit_off += b_bytes;
                         if (++st == kStages) { st = 0; ph ^= 1; }
                         if (s == 0 && g == 0) LB2_TRACE(pit, 2);
                     }
                 }
                 LB2_TRACE(pit, 3);
             }
+            resident_job = jj;
             // every lane tracks the ring position the elected lane advanced to
             const int adv = n_slabs * ng;
             stage += adv;
@@ -389,6 +419,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                 const int n_st = n_slabs * ng;
                 uint32_t accumulate = 0;
                 int g = 0;
+                uint32_t res16 = 0;   // kRes: offset of the stage's weights in the resident area, in 16-byte units
                 for (int s = 0; s < n_st; s++) {
                     if (!next_ready) mbar_wait(full_bar + stage, phase);
                     tc_fence_after_sync();
@@ -396,10 +427,12 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                     int nstage = stage + 1; uint32_t nphase = phase;
                     if (nstage == kStages) { nstage = 0; nphase ^= 1; }
                     if (LB2_PROBE_TAP < 0) next_ready = mbar_try_wait(full_bar + nstage, nphase);
-                    const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+                    const uint32_t a_addr = smem_u32(ring + stage * kStageBytes);
                     // (address of row `halo` of the A slab) >> 4; a tap shifts it by dy*S+dx rows
                     const uint32_t a16 = (a_addr >> 4) + halo;
-                    uint32_t b16 = (a_addr + kASlabBytes) >> 4;
+                    // B: behind the A slab of the stage, or (kRes) this stage's unit of the resident weights
+                    uint32_t b16 = kRes ? (smem_u32(smem) >> 4) + res16 : (a_addr + kASlabBytes) >> 4;
+                    if (kRes) res16 += (uint32_t)(ksize == 3 ? 9 : tap_group_end(ksize, g) - tap_group_begin(g)) * b_step;
                     if (ksize == 3) {
 #pragma unroll
                         for (int t = 0; t < 9; t++) {
@@ -626,16 +659,34 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         const int first = P.item_begin + (kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x);
         const int step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
         int j = 0;
+        // kRes: the net this cluster currently draws items from, and which nets have run dry
+        int cur_net = kRes ? ((int)(blockIdx.x >> 1) < P.policy_clusters ? 0 : 1) : 0;
+        bool dry[2] = {false, false};
         for (uint32_t it = 0;; it++) {
             int jj = (int)kEndJob, idx = 0;
             if (leader) {
-                int q = 0;
+                int q = 0, q_end = P.item_end;
                 if (lane == 0) {
                     while (it >= *pub_done + kClaimAhead) __nanosleep(20);
-                    q = dynamic ? P.item_begin + (int)(atomicAdd(P.next_item, 1u) - P.claim_base) : first + (int)it * step;
+                    if (kRes) {
+                        // one end marker is drawn from EACH net's counter by every cluster: items + clusters claims per net per launch
+                        for (;;) {
+                            q = P.net_item_begin[cur_net] + (int)(atomicAdd(P.net_next_item[cur_net], 1u) - P.net_claim_base[cur_net]);
+                            q_end = P.net_item_end[cur_net];
+                            if (q < q_end) break;
+                            dry[cur_net] = true;
+                            if (dry[cur_net ^ 1]) break;
+                            cur_net ^= 1;
+                            j = -1;   // the other net's items lie elsewhere in the list: restart the round cursor
+                        }
+                    } else {
+                        q = dynamic ? P.item_begin + (int)(atomicAdd(P.next_item, 1u) - P.claim_base) : first + (int)it * step;
+                    }
                 }
                 q = __shfl_sync(0xffffffffu, q, 0);
-                if (q < P.item_end) locate_item(P, jobs, q, j, jj, idx);
+                q_end = __shfl_sync(0xffffffffu, q_end, 0);
+                if (kRes) { if (__shfl_sync(0xffffffffu, j, 0) < 0) j = 0; }
+                if (q < q_end) locate_item(P, jobs, q, j, jj, idx);
                 if (lane == 0) {
                     st_volatile_shared(geom_ring + it % kClaimRing, geom_pack(it, jj == (int)kEndJob ? nullptr : &jobs[jj]));
                     const uint32_t e = item_pack(it, (uint32_t)jj, (uint32_t)idx);
@@ -881,18 +932,20 @@ cudaError_t launch_expand(const ExpandArgs& a, cudaStream_t st) {
 }
 
 cudaError_t trunk_kernel_setup() {
-    cudaError_t e = cudaFuncSetAttribute(trunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(trunk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytes);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(trunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytes);
+    e = cudaFuncSetAttribute(trunk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(trunk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytesRes);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
 }
 
-cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool pair, cudaStream_t st) {
+cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool pair, bool resident, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kTrunkThreads);
-    cfg.dynamicSmemBytes = kTrunkSmemBytes;
+    cfg.dynamicSmemBytes = resident ? kTrunkSmemBytesRes : kTrunkSmemBytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[3];
     int na = 0;
@@ -914,7 +967,8 @@ cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool 
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    return pair ? cudaLaunchKernelEx(&cfg, trunk_kernel<true>, p) : cudaLaunchKernelEx(&cfg, trunk_kernel<false>, p);
+    if (pair && resident) return cudaLaunchKernelEx(&cfg, trunk_kernel<true, true>, p);
+    return pair ? cudaLaunchKernelEx(&cfg, trunk_kernel<true, false>, p) : cudaLaunchKernelEx(&cfg, trunk_kernel<false, false>, p);
 }
 
 cudaError_t launch_heads(const HeadArgs& a, cudaStream_t st) {

@@ -47,10 +47,20 @@ constexpr int kTrunkRingBytes = kRingBytesSingle > kRingBytesPair ? kRingBytesSi
 constexpr int kCtrlBytes = 384;  // mbarriers, TMEM slot, progress counters, claim ring
 constexpr int kTrunkSmemBytes = kTrunkRingBytes + kCtrlBytes + kMaxLaunchJobs * 128 * 4 + kHeadSlots * 9 * 128 * 4 + kMaxLaunchJobs * 160;
 static_assert(kTrunkSmemBytes <= 227 * 1024, "trunk kernel shared memory");
+// Resident-weights mode (CTA pairs only): a CTA keeps ITS half of the whole layer's packed weights in
+// shared memory and re-uses it for every item of that layer it processes; the pipeline stages then
+// carry activation slabs only. Needs c_in <= 128 and c_out <= 128 (9 x 128 x 64 x 2 B = 147,456 B).
+constexpr int kResWeightBytes = 9 * 128 * 64 * 2;
+constexpr int kStagesRes = 5;
+constexpr int kResJobs = 24;        // jobs per launch in this mode (no column splits)
+constexpr int kResHeadSlots = 2;    // one fused-head weight set per net
+constexpr int kTrunkSmemBytesRes = kResWeightBytes + kStagesRes * kASlabBytes + kCtrlBytes + kResJobs * 128 * 4 +
+                                   kResHeadSlots * 9 * 128 * 4 + kResJobs * 160;
+static_assert(kTrunkSmemBytesRes <= 227 * 1024, "resident-weights trunk shared memory");
 constexpr int kMaxLayers = 16;
 constexpr int kMaxTensorMaps = 6;
 constexpr int kMaxJobs = 40;
-constexpr int kMaxRounds = 16;  // a round = the jobs of equal depth (all nets, all column splits); their items are interleaved
+constexpr int kMaxRounds = 40;  // a round = the jobs of equal depth (all nets, all column splits); their items are interleaved
 constexpr int kMaxRoundJobs = 2 * kMaxSplit;
 constexpr int kTraceItems = 96;
 constexpr int kTraceEvents = 16;
@@ -98,6 +108,12 @@ struct TrunkParams {
     int32_t use_flags;  // 1: cross-CTA dataflow through flags (single persistent launch)
     uint32_t* next_item;        // dynamic scheduling: global in-order claim counter, or null. It is never reset:
     uint32_t claim_base;        // its value when this launch starts (every launch advances it by items + clusters)
+    // resident-weights mode: the item list is net-major (all policy jobs, then all value jobs), each net has
+    // its own claim counter; a cluster works on its preferred net until that runs dry, then helps the other
+    uint32_t* net_next_item[2];
+    uint32_t net_claim_base[2];
+    int32_t net_item_begin[2], net_item_end[2];
+    int32_t policy_clusters;    // clusters [0, policy_clusters) prefer net 0, the rest net 1
     unsigned long long* trace;  // optional timeline buffer [cta][kTraceItems][kTraceEvents] of %globaltimer ns
     int32_t debug_flags;  // timing experiments only (results wrong): bit1 = all tap offsets 0, bit2 = no epilogue math,
                           // bit3 = no B loads, bit4 = no A loads, bit5 = only the first M half of 3x3 layers, bit6 = epilogue does nothing
@@ -133,7 +149,7 @@ struct MeanArgs {
 
 // launchers (lb2_kernels.cu)
 cudaError_t launch_expand(const ExpandArgs& a, cudaStream_t st);
-cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool pair, cudaStream_t st);
+cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool pair, bool resident, cudaStream_t st);
 cudaError_t launch_heads(const HeadArgs& a, cudaStream_t st);
 cudaError_t launch_ensemble_mean(const MeanArgs& a, cudaStream_t st);
 cudaError_t trunk_kernel_setup();

@@ -7,8 +7,8 @@ harsher than the real net):
   layer 1 (binary inputs, fp16 weights)      : <= 1 fp16 ulp of the output
   deeper layers vs same-rounding oracle      : <= 1.5e-2 abs (activations reach ~8, fp16 ulp 7.8e-3;
                                                accumulation order flips last-bit roundings)
-  policy probability, per point              : <= 6e-3 abs (measured max 3.8e-3), mean <= 5e-5
-  value winrate                              : <= 6e-3 abs (measured max 3.1e-3)
+  policy probability, per point              : <= 6e-3 abs (measured max 5.3e-3 over 1024 positions), mean <= 5e-5
+  value winrate                              : <= 6e-3 abs (measured max 3.0e-3)
   top-1 move agreement                       : >= 97 %, every miss must be a near tie (< 6e-3)
 The reference is fp32 end to end; the B200 path keeps fp16 operands with fp32 accumulation.
 """
@@ -161,6 +161,33 @@ def test_launch_modes_bit_identical(ev, ref_golden):
     ev.set_option("trunk_mode", 1)
     p1, v1 = ev.eval_both(*args)
     assert np.array_equal(p0, p1) and np.array_equal(v0, v1)
+
+
+def test_resident_weights_mode_bit_identical(ev, ref_golden, bench_positions):
+    """Resident-weights mode (each CTA keeps its half of a layer's weights in shared memory across the
+    layer's items, clusters split between the nets and help each other out) vs streaming the weight
+    blocks with every stage: same arithmetic, same bits — full batch, one net only, ragged sizes,
+    and with the cluster split forced to both extremes."""
+    g, b = ref_golden, bench_positions
+    cases = [(g["policy_planes"], g["value_planes"], g["rotation"]),
+             (b["policy_planes"][:256], b["value_planes"][:256], b["rotation"][:256]),
+             (b["policy_planes"][300:337], b["value_planes"][300:337], b["rotation"][300:337])]
+    want = [ev.eval_both(*c, TEMP) for c in cases]
+    want_p = ev.eval_policy(cases[1][0], cases[1][2], TEMP)
+    want_v = ev.eval_value(cases[2][1], cases[2][2])
+    ev.set_option("resident_weights", 1)
+    try:
+        for split in (-1, 1, 73):
+            ev.set_option("policy_clusters", split)
+            for c, w in zip(cases, want):
+                p, v = ev.eval_both(*c, TEMP)
+                assert np.array_equal(p, w[0]) and np.array_equal(v, w[1]), split
+        ev.set_option("policy_clusters", -1)
+        assert np.array_equal(ev.eval_policy(cases[1][0], cases[1][2], TEMP), want_p)
+        assert np.array_equal(ev.eval_value(cases[2][1], cases[2][2]), want_v)
+    finally:
+        ev.set_option("resident_weights", 0)
+        ev.set_option("policy_clusters", -1)
 
 
 def test_cta_pair_and_single_cta_bit_identical(ev, ref_golden):
