@@ -1,4 +1,4 @@
-/* boost::algorithm stand-ins used by SGFTree.cpp:186-213. Test infrastructure only. */
+/* boost::algorithm stand-ins used by SGFTree.cpp:186-213. Build aid where boost is not installed. */
 #pragma once
 #include <string>
 namespace boost { namespace algorithm {

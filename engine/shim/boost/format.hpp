@@ -1,6 +1,7 @@
 /* printf-style boost::format stand-in covering the reference's uses
  * (Network.cpp:855, Book.cpp:100, SGFTree.cpp:414-472): one directive per operator%.
- * Test infrastructure only. */
+ * Build aid for compiling the reference's sources where boost is not installed (engine/Makefile and
+ * oracle/ref/Makefile); a build with real boost headers does not need it. */
 #pragma once
 #include <cstdio>
 #include <ostream>
