@@ -9,6 +9,8 @@
 //   --weights FILE         network weights ("LB2WGT01", leela_b200/fileio.py); or LB2_WEIGHTS
 //   --max-outstanding N    async policy requests per search thread (reference: 2, OpenCL.cpp:453)
 //   --batch N              positions per device pass (lb2 option max_batch)
+//   --own-planes / --check-planes   feature planes through the library's own board, or both ways with a
+//                              comparison on every position the search evaluates
 //   --dump-planes OUT N SEED   write the feature planes of N seeded self-play positions and exit
 //                              (no GPU needed; tests compare them with the reference's own)
 //   -DLB2_REFERENCE_BUILD  the same main for the reference's own CPU engine (oracle/ref/Makefile
@@ -62,6 +64,8 @@ void usage() {
                  "      --extra_symmetry N  Visits per extra symmetry of the policy net (GPU default 350).\n"
                  "      --gpu ID            B200 device(s) to use (repeatable; weights replicated, batches sharded).\n"
                  "      --weights FILE      Network weights file (or LB2_WEIGHTS).\n"
+                 "      --own-planes        Build the feature planes with the library's own board (lb2_planes_from_position).\n"
+                 "      --check-planes      Build them both ways and abort on the first difference.\n"
                  "      --max-outstanding N Async policy requests per search thread (default 2).\n"
                  "      --batch N           Positions per device pass (default 256).\n"
                  "      --dump-planes OUT N SEED  Dump feature planes of seeded self-play positions and exit.\n";
@@ -150,6 +154,8 @@ void print_evaluator_stats() {
         const long pos = lb2_get_option(ctx, "stat_positions"), bat = lb2_get_option(ctx, "stat_batches");
         fprintf(stderr, "B200 evaluator: %ld positions in %ld device batches (mean batch %.1f), %ld requests\n", pos, bat,
                 bat ? (double)pos / bat : 0.0, lb2_get_option(ctx, "stat_requests"));
+        if (leela_b200::planes_checked())
+            fprintf(stderr, "feature planes cross-checked (own board vs reference board queries): %ld, all identical\n", leela_b200::planes_checked());
     }
 }
 #endif
@@ -199,6 +205,8 @@ int main(int argc, char* argv[]) {
 #ifndef LB2_REFERENCE_BUILD
         else if (a == "--gpu") cfg_gpus.push_back(atoi(value("--gpu")));
         else if (a == "--weights") leela_b200::set_weights_path(value("--weights"));
+        else if (a == "--own-planes") leela_b200::set_planes_mode(1);
+        else if (a == "--check-planes") leela_b200::set_planes_mode(2);
         else if (a == "--max-outstanding") leela_b200::set_max_outstanding(atoi(value("--max-outstanding")));
         else if (a == "--batch") batch = atol(value("--batch"));
         else if (a == "--dump-planes") {

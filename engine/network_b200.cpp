@@ -59,6 +59,9 @@ namespace {
 lb2_ctx* g_ctx = nullptr;
 std::string g_weights_path;
 int g_max_outstanding = 2;   // per search thread, as OpenCL::thread_can_issue (OpenCL.cpp:446-454)
+int g_planes_mode = 0;       // 0: planes through the reference's board queries; 1: lb2_planes_from_position (own board);
+                             // 2: both, and abort on the first difference (cross-check on the positions a real search visits)
+std::atomic<long> g_planes_checked{0};
 thread_local std::atomic<int> t_results_outstanding{0};
 
 [[noreturn]] void die(const char* what) {
@@ -127,14 +130,58 @@ inline uint32_t count_plane(int base, int count, int cap) { return count >= 1 ? 
 
 namespace leela_b200 {
 
+// The same planes from the raw position through the library's own board (lb2_planes_from_position).
+static void pack_features_own_board(FastState* state, bool value_net, uint32_t* packed) {
+    FastBoard& board = state->board;
+    uint8_t stones[361];
+    for (int idx = 0; idx < 361; idx++) {
+        const FastBoard::square_t sq = board.get_square(board.get_vertex(idx % 19, idx / 19));
+        stones[idx] = sq == FastBoard::BLACK ? 1 : (sq == FastBoard::WHITE ? 2 : 0);
+    }
+    auto index_of = [&](int vertex) {
+        if (vertex <= 0) return -1;   // none or pass
+        const std::pair<int, int> xy = board.get_xy(vertex);
+        return xy.second * 19 + xy.first;
+    };
+    if (lb2_planes_from_position(stones, state->get_to_move() == FastBoard::WHITE, index_of(state->get_komove()),
+                                 index_of(state->get_last_move()), index_of(state->get_prevlast_move()), state->get_komi(),
+                                 value_net ? nullptr : packed, value_net ? packed : nullptr))
+        die("lb2_planes_from_position");
+}
+
+static void pack_features_reference_board(FastState* state, bool value_net, uint32_t* packed);
+
 // packed[idx], idx = y*19 + x. `ladder` (optional) receives the losing-ladder plane, which the
 // callers need on the host to prune the result (Network.cpp:656-667).
 void pack_features(FastState* state, bool value_net, uint32_t* packed, Network::BoardPlane* ladder) {
+    if (g_planes_mode == 1) {
+        pack_features_own_board(state, value_net, packed);
+    } else {
+        pack_features_reference_board(state, value_net, packed);
+        if (g_planes_mode == 2) {
+            uint32_t own[361];
+            pack_features_own_board(state, value_net, own);
+            if (memcmp(own, packed, sizeof own)) {
+                fprintf(stderr, "leela_b200: PLANE MISMATCH between the own-board builder and the reference's board queries (%s net, move %d)\n",
+                        value_net ? "value" : "policy", (int)state->get_movenum());
+                abort();
+            }
+            g_planes_checked++;
+        }
+    }
+    if (ladder) {
+        const int bit = value_net ? kValuePlanes.ladder : kPolicyPlanes.ladder;
+        ladder->reset();
+        for (int idx = 0; idx < 361; idx++)
+            if ((packed[idx] >> bit) & 1u) ladder->set(idx);
+    }
+}
+
+static void pack_features_reference_board(FastState* state, bool value_net, uint32_t* packed) {
     const PlaneLayout& L = value_net ? kValuePlanes : kPolicyPlanes;
     FastBoard& board = state->board;
     const int tomove = state->get_to_move();
     const bool white_has_komi = std::fabs(state->get_komi()) > 0.75f;
-    if (ladder) ladder->reset();
     for (int idx = 0; idx < 361; idx++) {
         const int x = idx % 19, y = idx / 19;
         const int vtx = board.get_vertex(x, y);
@@ -151,10 +198,8 @@ void pack_features(FastState* state, bool value_net, uint32_t* packed, Network::
             bits |= count_plane(L.own_after, after.first, 6) | count_plane(L.opp_after, after.second, 6);
             // escaping move of a string in atari that still runs into a ladder
             if (board.count_pliberties(vtx) == 2 && board.saving_size(tomove, vtx) > 0 &&
-                board.check_losing_ladder(tomove, vtx)) {
+                board.check_losing_ladder(tomove, vtx))
                 bits |= plane(L.ladder);
-                if (ladder) ladder->set(idx);
-            }
             if (board.check_winning_ladder(tomove, vtx)) bits |= plane(L.ladder_win);
         }
         packed[idx] = bits;
@@ -169,6 +214,8 @@ void pack_features(FastState* state, bool value_net, uint32_t* packed, Network::
     mark(state->get_komove(), L.ko);
 }
 
+void set_planes_mode(int mode) { g_planes_mode = mode; }
+long planes_checked() { return g_planes_checked.load(); }
 void set_weights_path(const std::string& path) { g_weights_path = path; }
 void set_max_outstanding(int n) { g_max_outstanding = std::max(1, n); }
 lb2_ctx* context() { return g_ctx; }

@@ -14,6 +14,10 @@ namespace leela_b200 {
 // (idx = y*19 + x, bit c = plane c) — the input format of the C ABI.
 void pack_features(FastState* state, bool value_net, uint32_t* packed, Network::BoardPlane* ladder);
 
+// 0 (default): planes through the reference's FastBoard queries; 1: through lb2_planes_from_position (the
+// library's own board and ladder reader); 2: both, aborting on the first difference
+void set_planes_mode(int mode);
+long planes_checked();
 void set_weights_path(const std::string& path);   // "LB2WGT01" file, see leela_b200/fileio.py
 void set_max_outstanding(int n);                   // async policy requests a search thread may have in flight
 lb2_ctx* context();

@@ -110,3 +110,19 @@ def test_gtp_search_uses_batched_leaf_queue():
     assert m, err[-1500:]
     assert int(m.group(1)) > 100            # the nets were consulted
     assert int(m.group(1)) > int(m.group(2))   # requests of different search threads shared device batches
+
+
+@pytest.mark.gpu
+@needs_engine
+def test_search_positions_cross_check_own_board_planes():
+    """--check-planes: every position the search sends to the nets gets its planes built twice — through
+    the reference's FastBoard queries and through lb2_planes_from_position — and the engine aborts on the
+    first difference. These are positions from real search trees (captures, kos, ladders mid-sequence),
+    not the random playouts of tests/test_planes.py."""
+    cmds = ["boardsize 19", "clear_board", "komi 7.5"] + [f"genmove {'bw'[i % 2]}" for i in range(8)]
+    out, err = gtp(cmds, "-t", "16", "-p", "1500", "--check-planes", "--mature_threshold", "2", "--eval_thresh", "0")
+    m = re.search(r"feature planes cross-checked .*: (\d+), all identical", err)
+    assert m and int(m.group(1)) > 500, err[-1500:]
+    assert "PLANE MISMATCH" not in err
+    out2, err2 = gtp(["boardsize 19", "clear_board", "genmove b"], "-t", "8", "-p", "800", "--own-planes")
+    assert re.search(r"^= [A-T]\d+", out2, flags=re.M)
