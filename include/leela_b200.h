@@ -131,6 +131,18 @@ int lb2_drain(lb2_ctx* ctx);
 int lb2_planes_from_position(const uint8_t* stones, int white_to_move, int ko_point, int last_move, int prev_move,
                              float komi, uint32_t* policy_planes, uint32_t* value_planes);
 
+/* Raw positions in, results out: lb2_planes_from_position on the host's cores (the positions are
+ * spread over worker threads), then lb2_eval_both. For callers that have no Go board code at all.
+ * rotation may be NULL (symmetry 0 for every position); either output may be NULL. */
+typedef struct lb2_position {
+    uint8_t stones[LB2_BOARD_POINTS];   /* idx = y*19 + x: 0 empty, 1 black, 2 white */
+    uint8_t white_to_move;
+    int16_t ko_point, last_move, prev_move;   /* idx, or -1 */
+    float komi;
+} lb2_position;
+int lb2_eval_positions(lb2_ctx* ctx, const lb2_position* positions, const uint8_t* rotation, int n,
+                       float softmax_temp, float* probs_out, float* winrate_out);
+
 /* Replaces OpenCL::get_device_name / Network::get_backend (Network.cpp:1535-1553). */
 const char* lb2_backend_name(lb2_ctx* ctx);
 const char* lb2_last_error(void);

@@ -22,7 +22,7 @@ EXPORTS = [
     "lb2_init", "lb2_destroy", "lb2_net_create", "lb2_net_push_conv", "lb2_net_push_ip", "lb2_net_finalize",
     "lb2_eval_policy", "lb2_eval_value", "lb2_eval_both", "lb2_eval_ensemble", "lb2_eval_both_device", "lb2_submit_policy",
     "lb2_submit_value", "lb2_drain", "lb2_backend_name", "lb2_last_error", "lb2_device_count", "lb2_set_option",
-    "lb2_get_option", "lb2_launch_count", "lb2_debug_trunk", "lb2_debug_read_trace", "lb2_planes_from_position",
+    "lb2_get_option", "lb2_launch_count", "lb2_debug_trunk", "lb2_debug_read_trace", "lb2_planes_from_position", "lb2_eval_positions",
 ]
 
 CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_int)
@@ -56,6 +56,7 @@ def load():
     L.lb2_eval_both.argtypes = [vp, vp, vp, vp, ip, fp, vp, vp]
     L.lb2_eval_ensemble.argtypes = [vp, vp, vp, ip, fp, vp, vp]
     L.lb2_planes_from_position.argtypes = [vp, ip, ip, ip, ip, fp, vp, vp]
+    L.lb2_eval_positions.argtypes = [vp, vp, vp, ip, fp, vp, vp]
     L.lb2_eval_both_device.argtypes = [vp, ip, vp, vp, vp, ip, fp, vp, vp, vp]
     L.lb2_submit_policy.argtypes = [vp, vp, vp, ip, fp, vp, CALLBACK, vp]
     L.lb2_submit_value.argtypes = [vp, vp, vp, ip, vp, CALLBACK, vp]
@@ -89,6 +90,12 @@ def planes_from_position(stones, white_to_move, ko_point=-1, last_move=-1, prev_
     check(L.lb2_planes_from_position(_p(st), int(white_to_move), int(ko_point), int(last_move), int(prev_move), float(komi),
                                      _p(pol), _p(val)))
     return pol, val
+
+
+# numpy mirror of struct lb2_position (include/leela_b200.h)
+POSITION_DTYPE = np.dtype([("stones", np.uint8, 361), ("white_to_move", np.uint8), ("ko_point", np.int16),
+                           ("last_move", np.int16), ("prev_move", np.int16), ("komi", np.float32)], align=True)
+assert POSITION_DTYPE.itemsize == 372
 
 
 class Evaluator:
@@ -163,6 +170,15 @@ class Evaluator:
         probs = probs_out if probs_out is not None else np.empty((n, P), dtype=np.float32)
         win = win_out if win_out is not None else np.empty(n, dtype=np.float32)
         check(self._L.lb2_eval_both(self.ctx, _p(pp), _p(vp), _p(rotation), n, temp, _p(probs), _p(win)))
+        return probs, win
+
+    def eval_positions(self, positions, rotation=None, temp=0.75):
+        """positions: array of POSITION_DTYPE (raw boards); planes are built inside the library."""
+        pos = np.ascontiguousarray(positions, dtype=POSITION_DTYPE)
+        n = pos.shape[0]
+        rot = None if rotation is None else np.ascontiguousarray(rotation, dtype=np.uint8)
+        probs = np.empty((n, P), dtype=np.float32); win = np.empty(n, dtype=np.float32)
+        check(self._L.lb2_eval_positions(self.ctx, _p(pos), _p(rot), n, temp, _p(probs), _p(win)))
         return probs, win
 
     def eval_ensemble(self, policy_planes=None, value_planes=None, temp=0.75):

@@ -1109,6 +1109,34 @@ int lb2_eval_both(lb2_ctx* ctx, const uint32_t* pol, const uint32_t* val, const 
     return eval_host(ctx, pol, val, rotation, n, temp, probs, winrate);
 }
 
+int lb2_eval_positions(lb2_ctx* ctx, const lb2_position* pos, const uint8_t* rotation, int n, float temp, float* probs,
+                       float* winrate) {
+    if (!probs && !winrate && n > 0) return fail(LB2_ERR_INVALID, "null output pointers");
+    if (n < 0) return fail(LB2_ERR_INVALID, "n < 0");
+    if (n == 0) return LB2_OK;
+    if (!pos) return fail(LB2_ERR_INVALID, "null input pointer");
+    std::vector<uint32_t> pol(probs ? (size_t)n * lb2::kPoints : 0), val(winrate ? (size_t)n * lb2::kPoints : 0);
+    std::vector<uint8_t> rot(n, 0);
+    if (rotation) rot.assign(rotation, rotation + n);
+    // feature planes on the host's cores: ~0.1 ms per position each
+    const int n_threads = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 64, (n + 7) / 8}));
+    std::atomic<int> next{0}, bad{0};
+    auto work = [&]() {
+        for (int i; (i = next.fetch_add(1)) < n;) {
+            const lb2_position& p = pos[i];
+            if (lb2_planes_from_position(p.stones, p.white_to_move, p.ko_point, p.last_move, p.prev_move, p.komi,
+                                         probs ? &pol[(size_t)i * lb2::kPoints] : nullptr, winrate ? &val[(size_t)i * lb2::kPoints] : nullptr))
+                bad++;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; t++) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    if (bad) return fail(LB2_ERR_INVALID, "%d invalid position(s) (stone values must be 0..2, point indices < 361)", bad.load());
+    return eval_host(ctx, probs ? pol.data() : nullptr, winrate ? val.data() : nullptr, rot.data(), n, probs ? temp : 1.0f, probs, winrate);
+}
+
 int lb2_eval_ensemble(lb2_ctx* ctx, const uint32_t* pol, const uint32_t* val, int n, float temp, float* probs, float* winrate) {
     if (!probs && !winrate && n > 0) return fail(LB2_ERR_INVALID, "null output pointers");
     return eval_host(ctx, probs ? pol : nullptr, winrate ? val : nullptr, nullptr, n, probs ? temp : 1.0f, probs, winrate, true);

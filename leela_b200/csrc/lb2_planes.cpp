@@ -272,7 +272,10 @@ struct Board {
         Board t = *this;
         int atari = v;
         t.play(t.tomove, v);
-        for (;;) {                        // the side to move never changes: defender t.tomove, attacker the other
+        // (the side to move never changes: defender t.tomove, attacker the other. Every round adds two
+        // stones, so a real chase ends within the board's 361 points; the bound only guards against
+        // malformed input arriving through the ABI)
+        for (int round = 0; round < 400; round++) {
             if (t.sq[atari] == EMPTY) return true;                // the extension was suicide
             const int newlibs = t.libs[t.group[atari]];
             if (newlibs == 1) return true;                        // still in atari
@@ -307,8 +310,10 @@ struct Board {
             }
             t.play(attacker, gain0 > gain1 ? lib[0] : lib[1]);
             atari = t.in_atari(atari);    // the defender's only move: extend again
+            if (!atari) return false;     // (cannot happen on a legal board: the string was just put in atari)
             t.play(t.tomove, atari);
         }
+        return false;
     }
 
     // check_winning_ladder (FastBoard.cpp:2530-2564): `c` (== tomove) gives atari at v on a

@@ -316,6 +316,39 @@ def test_device_ensemble_equals_microbatch_and_reference(ev, ref_golden, bench_p
     assert np.allclose(big_p.sum(1), 1.0, atol=1e-4) and (big_v > 0).all() and (big_v < 1).all()
 
 
+def test_raw_positions_entry_point(ev):
+    """lb2_eval_positions (raw boards in: planes built inside the library on the host's cores) equals
+    lb2_planes_from_position + lb2_eval_both, and rejects a malformed position."""
+    from leela_b200 import capi
+    rng = np.random.default_rng(5)
+    n = 70
+    pos = np.zeros(n, dtype=capi.POSITION_DTYPE)
+    for i in range(n):
+        st = rng.choice([0, 1, 2], size=361, p=[0.6, 0.2, 0.2]).astype(np.uint8)
+        pos[i]["stones"] = st     # random stones: not legal Go, but every query must still terminate and agree
+        pos[i]["white_to_move"] = i & 1
+        pos[i]["ko_point"] = -1
+        empties = np.nonzero(st == 0)[0]
+        pos[i]["last_move"] = -1 if i % 5 == 0 else int(np.nonzero(st)[0][0])
+        pos[i]["prev_move"] = -1 if i % 3 == 0 else int(np.nonzero(st)[0][1])
+        if i % 7 == 0 and len(empties):
+            pos[i]["ko_point"] = int(empties[0])
+        pos[i]["komi"] = 7.5 if i % 4 else 0.5
+    rot = (np.arange(n) % 8).astype(np.uint8)
+    pp = np.empty((n, 361), np.uint32); vp = np.empty((n, 361), np.uint32)
+    for i in range(n):
+        pp[i], vp[i] = capi.planes_from_position(pos[i]["stones"], pos[i]["white_to_move"], pos[i]["ko_point"], pos[i]["last_move"],
+                                                 pos[i]["prev_move"], pos[i]["komi"])
+    want_p, want_v = ev.eval_both(pp, vp, rot, TEMP)
+    got_p, got_v = ev.eval_positions(pos, rot, TEMP)
+    assert np.array_equal(got_p, want_p) and np.array_equal(got_v, want_v)
+    bad = pos[:3].copy()
+    bad[1]["stones"][7] = 9
+    with pytest.raises(capi.Lb2Error) as e:
+        ev.eval_positions(bad, None, TEMP)
+    assert e.value.code == -1
+
+
 def test_softmax_temperature_is_runtime(ev, ref_golden, oracle_nets):
     from oracle import oracle
     g = ref_golden
