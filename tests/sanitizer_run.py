@@ -1,0 +1,22 @@
+"""Small run of every kernel mode (CTA pairs, single CTA, resident weights, ensemble, 192-wide net) for\ncompute-sanitizer: `compute-sanitizer --tool memcheck|synccheck|initcheck python tests/sanitizer_run.py` (0 errors, round 1)."""
+import os, sys
+sys.path.insert(0, os.getcwd())
+import numpy as np
+from leela_b200 import capi, synth
+g = np.load("tests/golden/ref_golden.npz")
+ev = capi.Evaluator(policy=synth.policy_weights(), value=synth.value_weights())
+p, v = ev.eval_both(g["policy_planes"][:5], g["value_planes"][:5], g["rotation"][:5], 0.75)
+print("both", float(np.abs(p - g["policy"][:5]).max()), float(np.abs(v - g["value"][:5]).max()))
+pe, ve = ev.eval_ensemble(g["policy_planes"][:2], g["value_planes"][:2], 0.75)
+print("ens", pe.sum(1), ve)
+ev.set_option("resident_weights", 1)
+p2, v2 = ev.eval_both(g["policy_planes"][:5], g["value_planes"][:5], g["rotation"][:5], 0.75)
+print("resident identical", np.array_equal(p, p2), np.array_equal(v, v2))
+ev.set_option("resident_weights", 0); ev.set_option("cta_pair", 0)
+p3, v3 = ev.eval_both(g["policy_planes"][:5], g["value_planes"][:5], g["rotation"][:5], 0.75)
+print("single identical", np.array_equal(p, p3), np.array_equal(v, v3))
+ev.close()
+e2 = capi.Evaluator(policy=synth.policy192_weights())
+q = e2.eval_policy(g["policy_planes"][:3], g["rotation"][:3], 0.75)
+print("192", q.sum(1))
+e2.close()
