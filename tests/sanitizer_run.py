@@ -1,4 +1,5 @@
-"""Small run of every kernel mode (CTA pairs, single CTA, resident weights, ensemble, 192-wide net) for\ncompute-sanitizer: `compute-sanitizer --tool memcheck|synccheck|initcheck python tests/sanitizer_run.py` (0 errors, round 1)."""
+"""Small run of every kernel mode (CTA pairs, single CTA, resident weights, ensemble, 192-wide net) for
+compute-sanitizer: `compute-sanitizer --tool memcheck|synccheck|initcheck python tests/sanitizer_run.py` (0 errors, round 1)."""
 import os, sys
 sys.path.insert(0, os.getcwd())
 import numpy as np
