@@ -108,7 +108,7 @@ int lb2_eval_both_device(lb2_ctx* ctx, int dev_index, const uint32_t* d_policy_p
 
 /* Asynchronous submission from many search threads; replaces forward(cb) +
  * thread_can_issue / join_outstanding_cb (OpenCL.cpp:446-454, 560-577). Requests are
- * coalesced into device batches by a worker thread; cb(user, status) runs on that thread once
+ * coalesced into device batches by two worker threads (one batch's copies overlap the other's kernels); cb(user, status) runs on such a thread once
  * the caller's output buffer is filled. Input buffers are copied before the call returns. */
 typedef void (*lb2_callback)(void* user, int status);
 int lb2_submit_policy(lb2_ctx* ctx, const uint32_t* planes, const uint8_t* rotation, int n,
