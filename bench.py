@@ -211,6 +211,8 @@ def run_ours(args):
     ev.set_option("max_batch", max(B, 256))
     if args.overlap_io:
         ev.set_option("overlap_io", 1)
+    if args.precise:
+        ev.set_option("precise", 1)
     pp, vp, rot = load_positions()
     n_pos = pp.shape[0]
     # input pool: every batch is a different window (stride 3, wrapping) over the distinct positions,
@@ -319,7 +321,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16 hi+lo split operands (3 MMA terms), f32 accumulation" if args.precise else "f16", "data": "synthetic",
             "config": {"workload": "policy NN128 + value NNValue, batch 256 positions per GPU per step "
                                    "(BASELINE.json configs[1] shape, policy+value as the metric names)",
                        "batch_per_gpu": B, "global_batch": B * n_gpus, "parallelism": f"replicas x{n_gpus}, positions sharded",
@@ -327,7 +329,7 @@ def run_ours(args):
                        "positions": f"Leela Playout self-play, {n_pos} distinct, {n_sets} different batches cycled",
                        "l2": "flushed between steps (256 MB write)" if args.flush_l2 else
                              f"inputs larger than L2: {n_sets} input batches = {n_sets * set_bytes / 2**20:.0f} MB, one per step; weights + workspace stay warm",
-                       "trunk_mode": ev.get_option("trunk_mode"), "cta_pair": ev.get_option("cta_pair"), "flops_per_position": netdefs.POLICY_FLOPS + netdefs.VALUE_FLOPS,
+                       "trunk_mode": ev.get_option("trunk_mode"), "cta_pair": ev.get_option("cta_pair"), "precise": ev.get_option("precise"), "flops_per_position": netdefs.POLICY_FLOPS + netdefs.VALUE_FLOPS,
                        "pct_of_bf16_sustained_peak_whole_step": 100.0 * (netdefs.POLICY_FLOPS + netdefs.VALUE_FLOPS) * value / n_gpus / (peak * 1e12),
                        "pct_of_bf16_burst_peak_whole_step": 100.0 * (netdefs.POLICY_FLOPS + netdefs.VALUE_FLOPS) * value / n_gpus / (peak_burst * 1e12)},
             "roofline": {"bound": "tensor", "kernel": "trunk_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -363,6 +365,8 @@ def main():
     ap.add_argument("--engine", action="store_true", help="engine-level benchmark instead: GTP genmove / netbench, ours vs the reference's CPU engine")
     ap.add_argument("--flush-l2", action="store_true", help="evict L2 before every step instead of cycling an input pool larger than L2")
     ap.add_argument("--overlap-io", action="store_true", help="A/B: expand/heads kernels of host-buffer calls on the I/O slot's stream")
+    ap.add_argument("--precise", action="store_true", help="split-operand mode (lb2_set_option precise=1): results within 1e-4 of the fp32 reference, "
+                    "3x the tensor work; the roofline still counts the ALGORITHMIC flops")
     ap.add_argument("--e2e-threads", type=int, default=2, help="host threads calling the C ABI concurrently in the e2e leg")
     args = ap.parse_args()
     if args.engine:

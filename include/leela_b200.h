@@ -155,6 +155,11 @@ int lb2_device_count(lb2_ctx* ctx);
  *   "resident_weights": 1 = each CTA keeps its half of a layer's packed weights in shared memory for all the
  *                 layer's items it processes (clusters are split between the two nets and help each other
  *                 out at the end); cuts the weight stream from L2 by 77 %, launch time unchanged: default 0
+ *   "precise":    1 = split-operand mode: activations and weights are carried as fp16 hi + fp16 lo and every layer
+ *                 accumulates three tensor-core terms (hi*Wh + hi*Wl + lo*Wh) in fp32. Results lie within 1e-4 of the
+ *                 reference's fp32 OpenBLAS path (measured max 8.9e-5 policy, 2.8e-5 value over the 1024-position
+ *                 correctness set, top-1 identical in all) at about 0.38x the throughput of the default, whose fp16
+ *                 operands give max 5.3e-3 / 3.0e-3. Default 0. May be switched between calls.
  *   "policy_clusters": resident mode: clusters that start on the policy net (-1 = split by estimated work)
  *   "overlap_io": 1 = host-buffer calls run their expand / heads kernels on the I/O slot's stream, beside the
  *                 trunk kernel of another call in flight; 0 = on the compute stream (default: measured faster)

@@ -78,6 +78,8 @@ struct TrunkLayerDev {
     int n_split = 1;
     __half* wpk[lb2::kMaxSplit] = {nullptr, nullptr};
     __half* wpk2[lb2::kMaxSplit] = {nullptr, nullptr};  // CTA-pair packing
+    __half* wpk_x[lb2::kMaxSplit] = {nullptr, nullptr};   // the same two packings for precise mode (virtual slabs, see
+    __half* wpk2_x[lb2::kMaxSplit] = {nullptr, nullptr};  // pack_trunk_weights)
     float* bias[lb2::kMaxSplit] = {nullptr, nullptr};
 };
 
@@ -179,6 +181,8 @@ struct lb2_ctx {
                            // call. Measured 2-3 % slower end to end (the value head's blocks hold up the next trunk's CTAs): off.
     long dynamic_items = 1;
     long resident_weights = LB2_RESIDENT_DEFAULT;   // keep each CTA's half of a layer's weights in shared memory across the layer's items
+    long precise = 0;      // split-operand mode: activations and weights as fp16 hi + fp16 lo, three MMA terms (hi*Wh + hi*Wl + lo*Wh)
+                           // accumulated in fp32 -> fp32-grade results at about a third of the throughput
     long policy_clusters = -1;   // resident mode: clusters that prefer the policy net (-1 = split by estimated work)
     std::atomic<long> launches{0};
     std::atomic<long> stat_positions{0}, stat_batches{0}, stat_requests{0};  // async queue: positions, device batches, requests
@@ -204,43 +208,51 @@ void tap_groups(int k, int* n, int* begin, int* end) {
     else { *n = 3; begin[0] = 0; end[0] = 9; begin[1] = 9; end[1] = 17; begin[2] = 17; end[2] = 25; }
 }
 
-// [slab][tap group][tap][2 chunks][c_out][8] fp16 — the smem image of each pipeline stage.
-std::vector<__half> pack_trunk_weights(const HostConv& c) {
+// Virtual K slabs of a layer. Plain mode: slab s = channels [16 s, 16 s + 16) of the fp16-rounded weights.
+// Precise mode (`terms` = 3, or 2 for the first layer whose binary inputs have no residual): fp32 weight
+// w = Wh + Wl (+ 2^-22 w) with Wh = fp16(w), Wl = fp16(w - Wh); activation a = hi + lo likewise. The K loop
+// runs over [hi x Wh | hi x Wl | lo x Wh], i.e. virtual slab v takes weights slab v % n from Wh (v < n or
+// v >= 2n) or Wl (n <= v < 2n); the kernel's producer maps v to the matching activation chunk planes.
+__half slab_weight(const HostConv& c, int v, int n_real, int co, int j, int e, int t) {
     const int kk = c.k * c.k;
-    std::vector<__half> out((size_t)kk * c.c_in * c.c_out);
+    const int ci = 16 * (v % n_real) + 8 * j + e;
+    const float w = c.w[((size_t)co * c.c_in + ci) * kk + t];
+    const __half wh = __float2half_rn(w);
+    if (v >= n_real && v < 2 * n_real) return __float2half_rn(w - __half2float(wh));
+    return wh;
+}
+
+// [slab][tap group][tap][2 chunks][c_out][8] fp16 — the smem image of each pipeline stage.
+std::vector<__half> pack_trunk_weights(const HostConv& c, int terms = 1) {
+    const int kk = c.k * c.k, n_real = c.c_in / 16;
+    std::vector<__half> out((size_t)kk * c.c_in * c.c_out * terms);
     int ng, gb[3], ge[3];
     tap_groups(c.k, &ng, gb, ge);
     size_t o = 0;
-    for (int s = 0; s < c.c_in / 16; s++)
+    for (int s = 0; s < n_real * terms; s++)
         for (int g = 0; g < ng; g++)
             for (int t = gb[g]; t < ge[g]; t++)
                 for (int j = 0; j < 2; j++)
                     for (int n = 0; n < c.c_out; n++)
-                        for (int e = 0; e < 8; e++) {
-                            const int ci = 16 * s + 8 * j + e;
-                            out[o++] = __float2half_rn(c.w[((size_t)n * c.c_in + ci) * kk + t]);
-                        }
+                        for (int e = 0; e < 8; e++) out[o++] = slab_weight(c, s, n_real, n, j, e, t);
     return out;
 }
 
 // CTA-pair packing: [slab][tap group][rank][tap][2 chunks][c_out/2][8]; rank r holds output channels
 // [r*c_out/2, (r+1)*c_out/2) — the half of the MMA's B operand that CTA r of the pair stages.
-std::vector<__half> pack_trunk_weights_pair(const HostConv& c) {
-    const int kk = c.k * c.k, nh = c.c_out / 2;
-    std::vector<__half> out((size_t)kk * c.c_in * c.c_out);
+std::vector<__half> pack_trunk_weights_pair(const HostConv& c, int terms = 1) {
+    const int kk = c.k * c.k, nh = c.c_out / 2, n_real = c.c_in / 16;
+    std::vector<__half> out((size_t)kk * c.c_in * c.c_out * terms);
     int ng, gb[3], ge[3];
     tap_groups(c.k, &ng, gb, ge);
     size_t o = 0;
-    for (int s = 0; s < c.c_in / 16; s++)
+    for (int s = 0; s < n_real * terms; s++)
         for (int g = 0; g < ng; g++)
             for (int r = 0; r < 2; r++)
                 for (int t = gb[g]; t < ge[g]; t++)
                     for (int j = 0; j < 2; j++)
                         for (int n = 0; n < nh; n++)
-                            for (int e = 0; e < 8; e++) {
-                                const int ci = 16 * s + 8 * j + e, co = r * nh + n;
-                                out[o++] = __float2half_rn(c.w[((size_t)co * c.c_in + ci) * kk + t]);
-                            }
+                            for (int e = 0; e < 8; e++) out[o++] = slab_weight(c, s, n_real, r * nh + n, j, e, t);
     return out;
 }
 
@@ -275,6 +287,11 @@ int upload_net(const lb2_net* net, NetDev* nd) {
             std::vector<__half> pk2 = pack_trunk_weights_pair(part);
             rc = upload(&t.wpk2[sp], pk2.data(), pk2.size() * sizeof(__half));
             if (rc) return rc;
+            const int terms = (l == 0) ? 2 : 3;   // precise mode; the first layer's inputs are 0/1: no residual term
+            pk = pack_trunk_weights(part, terms);
+            if ((rc = upload(&t.wpk_x[sp], pk.data(), pk.size() * sizeof(__half)))) return rc;
+            pk2 = pack_trunk_weights_pair(part, terms);
+            if ((rc = upload(&t.wpk2_x[sp], pk2.data(), pk2.size() * sizeof(__half)))) return rc;
             rc = upload(&t.bias[sp], part.b.data(), part.b.size() * sizeof(float));
             if (rc) return rc;
         }
@@ -343,7 +360,7 @@ int ensure_workspace(NetDev* nd, int kind, int cap) {
     nd->rows5 = round_up(cap * 441, 2 * lb2::kTileRows);  // whole CTA-pair items
     nd->rows3 = round_up(cap * 400, 2 * lb2::kTileRows);
     const size_t x0_bytes = (size_t)4 * nd->rows5 * 16;
-    const size_t act_bytes = (size_t)(nd->width / 8) * nd->rows3 * 16;
+    const size_t act_bytes = (size_t)(2 * nd->width / 8) * nd->rows3 * 16;   // hi planes + (precise mode) lo planes
     CU_TRY(cudaMalloc(&nd->planes, (size_t)cap * lb2::kPoints * sizeof(uint32_t)));
     for (int w = 0; w < kSets; w++) {
         CU_TRY(cudaMalloc(&nd->x0[w], x0_bytes));
@@ -361,8 +378,8 @@ int ensure_workspace(NetDev* nd, int kind, int cap) {
     int rc;
     for (int w = 0; w < kSets; w++)
         if ((rc = make_act_tmap(&nd->tm_x0[w], nd->x0[w], nd->rows5, 4, 48))) return rc;
-    if ((rc = make_act_tmap(&nd->tm_act[0], nd->act[0], nd->rows3, nd->width / 8, 24))) return rc;
-    if ((rc = make_act_tmap(&nd->tm_act[1], nd->act[1], nd->rows3, nd->width / 8, 24))) return rc;
+    if ((rc = make_act_tmap(&nd->tm_act[0], nd->act[0], nd->rows3, 2 * nd->width / 8, 24))) return rc;
+    if ((rc = make_act_tmap(&nd->tm_act[1], nd->act[1], nd->rows3, 2 * nd->width / 8, 24))) return rc;
     nd->cap = cap;
     return LB2_OK;
 }
@@ -395,7 +412,7 @@ struct JobPlan {
 // independent jobs of equal depth (a layer wider than 128 channels contributes one job per column
 // split; they are consecutive in the table).
 // `net_major` (resident-weights mode): all policy jobs first, then all value jobs, every job a round of its own
-JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2], bool pair, int ws, bool net_major) {
+JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2], bool pair, int ws, bool net_major, bool precise) {
     JobPlan pl;
     size_t depth = 0;
     for (int k = 0; k < 2; k++)
@@ -418,7 +435,9 @@ JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2], bool 
                 J.S = first ? 21 : 20;
                 J.ksize = t.k;
                 J.halo = first ? 48 : 24;
-                J.n_slabs = t.c_in / 16;
+                J.n_real_slabs = t.c_in / 16;
+                J.n_slabs = precise ? (first ? 2 : 3) * J.n_real_slabs : J.n_real_slabs;
+                J.lo_chunks = precise ? t.c_out / 8 : 0;   // the lo planes of a layer's output follow its c_out / 8 hi planes
                 J.n_out = w;
                 const int n_tiles = (n * J.S * J.S + lb2::kTileRows - 1) / lb2::kTileRows;
                 J.n_items = pair ? (n_tiles + 1) / 2 : n_tiles;
@@ -437,8 +456,8 @@ JobPlan plan_jobs(DeviceState* d, bool run[2], int n, int limit_layers[2], bool 
                 J.n_pos = n;
                 J.net = k;
                 J.layer = (int)l;
-                J.wpk = t.wpk[sp];
-                J.wpk2 = t.wpk2[sp];
+                J.wpk = precise ? t.wpk_x[sp] : t.wpk[sp];
+                J.wpk2 = precise ? t.wpk2_x[sp] : t.wpk2[sp];
                 J.bias = t.bias[sp];
                 J.flags = nd.flags + ((size_t)l * lb2::kMaxSplit + sp) * nd.flags_stride;
                 J.head_slot = net_major ? k : k * lb2::kMaxSplit + sp;
@@ -474,7 +493,8 @@ int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers
     const bool pair = ctx->cta_pair != 0 && d->sm_count >= 2;
     // resident-weights mode: CTA pairs, the single dataflow launch with dynamic claiming, and every layer's
     // half of the packed weights must fit the resident area (c_in, c_out <= 128: no column splits)
-    bool resident = pair && ctx->resident_weights != 0 && ctx->trunk_mode == 1 && ctx->dynamic_items != 0;
+    const bool precise = ctx->precise != 0;
+    bool resident = pair && !precise && ctx->resident_weights != 0 && ctx->trunk_mode == 1 && ctx->dynamic_items != 0;
     int n_jobs_est = 0;
     for (int k = 0; k < 2 && resident; k++) {
         if (!run[k]) continue;
@@ -485,12 +505,12 @@ int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers
         }
     }
     if (n_jobs_est > lb2::kResJobs) resident = false;
-    JobPlan pl = plan_jobs(d, run, n, limit_layers, pair, ws, resident);
+    JobPlan pl = plan_jobs(d, run, n, limit_layers, pair, ws, resident, precise);
     if (pl.jobs.empty()) return fail(LB2_ERR_STATE, "no trunk layers to run");
     if ((int)pl.jobs.size() > lb2::kMaxLaunchJobs) return fail(LB2_ERR_UNSUPPORTED, "too many layers");
     const long key[8] = {n, run[0], run[1], limit_layers[0], limit_layers[1],
                          (long)reinterpret_cast<uintptr_t>(d->net[0].act[0]), (long)reinterpret_cast<uintptr_t>(d->net[1].act[0]),
-                         (long)pair + 2 * (long)resident};
+                         (long)pair + 2 * (long)resident + 4 * (long)precise};
     if (memcmp(key, d->plan_key[ws], sizeof key)) {
         // the set's job table on the device is reused by back-to-back launches of the same shape;
         // rewrite it only when the shape changes, after earlier work has drained
@@ -566,7 +586,7 @@ int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers
             P.claim_base = d->claim_base;
             d->claim_base += (uint32_t)pl.total_items + (uint32_t)n_clusters;
         }
-        CU_TRY(lb2::launch_trunk(P, grid, true, pair, resident, st));
+        CU_TRY(lb2::launch_trunk(P, grid, true, pair, resident, precise, st));
         ctx->launches++;
     } else {
         P.use_flags = 0;
@@ -575,7 +595,7 @@ int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers
             P.item_end = P.round_base[r + 1];
             const int items = P.item_end - P.item_begin;
             const int grid = pair ? std::min(d->sm_count & ~1, 2 * items) : std::min(d->sm_count, items);
-            CU_TRY(lb2::launch_trunk(P, grid, false, pair, false, st));
+            CU_TRY(lb2::launch_trunk(P, grid, false, pair, false, precise, st));
             ctx->launches++;
         }
     }
@@ -1008,7 +1028,7 @@ void lb2_destroy(lb2_ctx* ctx) {
         for (int k = 0; k < 2; k++) {
             NetDev& nd = d.net[k];
             for (auto& t : nd.trunk)
-                for (int sp = 0; sp < lb2::kMaxSplit; sp++) { cudaFree(t.wpk[sp]); cudaFree(t.wpk2[sp]); cudaFree(t.bias[sp]); }
+                for (int sp = 0; sp < lb2::kMaxSplit; sp++) { cudaFree(t.wpk[sp]); cudaFree(t.wpk2[sp]); cudaFree(t.wpk_x[sp]); cudaFree(t.wpk2_x[sp]); cudaFree(t.bias[sp]); }
             for (int sp = 0; sp < lb2::kMaxSplit; sp++) cudaFree(nd.head_wt[sp]);
             cudaFree(nd.head_b); cudaFree(nd.ip1_wt); cudaFree(nd.ip1_b);
             cudaFree(nd.ip2_w); cudaFree(nd.ip2_b);
@@ -1227,6 +1247,8 @@ int lb2_set_option(lb2_ctx* ctx, const char* name, long value) {
         ctx->overlap_io = value ? 1 : 0;
     } else if (!strcmp(name, "resident_weights")) {
         ctx->resident_weights = value ? 1 : 0;
+    } else if (!strcmp(name, "precise")) {
+        ctx->precise = value ? 1 : 0;
     } else if (!strcmp(name, "policy_clusters")) {
         ctx->policy_clusters = value;
     } else if (!strcmp(name, "profile_trunk")) {
@@ -1248,6 +1270,7 @@ long lb2_get_option(lb2_ctx* ctx, const char* name) {
     if (!strcmp(name, "dynamic_items")) return ctx->dynamic_items;
     if (!strcmp(name, "overlap_io")) return ctx->overlap_io;
     if (!strcmp(name, "resident_weights")) return ctx->resident_weights;
+    if (!strcmp(name, "precise")) return ctx->precise;
     if (!strcmp(name, "policy_clusters")) return ctx->policy_clusters;
     if (!strcmp(name, "sm_count")) return ctx->dev.empty() ? 0 : ctx->dev[0].sm_count;
     if (!strcmp(name, "stat_positions")) return ctx->stat_positions.load();

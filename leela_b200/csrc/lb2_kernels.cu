@@ -214,9 +214,11 @@ __device__ __forceinline__ uint32_t geom_pack(uint32_t k, const LayerJob* J) {
 // kRes (pairs only): resident-weights mode, see lb2_kernels.cuh. Shared memory:
 //   streaming:  [stages: A slab + B block][ctrl][bias][head weights][job table]
 //   resident:   [this CTA's half of the layer's weights][stages: A slab only][ctrl][bias][head weights][job table]
-template <bool kPair, bool kRes>
+// kPrecise: split-operand mode (LayerJob::lo_chunks != 0 for every job): the epilogue also stores the fp16 residual.
+template <bool kPair, bool kRes, bool kPrecise>
 __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_constant__ TrunkParams P) {
     static_assert(!kRes || kPair, "resident weights need CTA pairs");
+    static_assert(!kRes || !kPrecise, "resident weights hold one fp16 image of a layer");
     constexpr int kStages = kRes ? kStagesRes : (kPair ? kStagesPair : kStagesSingle);
     constexpr int kStageBytes = kRes ? kASlabBytes : (kPair ? kStageBytesPair : kStageBytesSingle);
     constexpr int kRingOff = kRes ? kResWeightBytes : 0;
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         for (int jj, idx; item_get(item_ring, pit, jj, idx); pit++) {
             const LayerJob& J = jobs[jj];
             const int tile = tile_of(idx);
-            const int halo = J.halo, ksize = J.ksize, n_out = J.n_out, n_slabs = J.n_slabs, tmap = J.tmap;
+            const int halo = J.halo, ksize = J.ksize, n_out = J.n_out, n_slabs = J.n_slabs, tmap = J.tmap, n_real = J.n_real_slabs;
             if (lane == 0) { LB2_TRACE(pit, 0); if (P.trace && pit < (uint32_t)kTraceItems) P.trace[((size_t)blockIdx.x * kTraceItems + pit) * kTraceEvents + 15] = (unsigned long long)((jj << 21) | idx); }
             // the scout warp polls the dependency flags ahead of us; wait for its go-ahead
             while (ld_acquire_cta_shared(deps_ready) <= pit) {}
@@ -348,8 +350,10 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                         const bool skip_b = (P.debug_flags & 8) != 0 || (kRes && !reload), skip_a = (P.debug_flags & 16) != 0;
                         mbar_arrive_expect_tx(full_bar + st, (skip_a ? 0u : a_bytes) + (skip_b ? 0u : b_bytes));
                         if (!skip_a) {
-                            if (LB2_L2_HINTS >= 2) tma_load_3d_hint(sa, &P.tmaps[tmap], full_bar + st, 0, row0_8, 2 * s, ld_policy);
-                            else tma_load_3d(sa, &P.tmaps[tmap], full_bar + st, 0, row0_8, 2 * s);
+                            // precise mode: virtual slabs [0, n) and [n, 2n) read the hi planes, [2n, 3n) the lo planes behind them
+                            const int ac = kPrecise ? 2 * (s < n_real ? s : s - n_real) : 2 * s;
+                            if (LB2_L2_HINTS >= 2) tma_load_3d_hint(sa, &P.tmaps[tmap], full_bar + st, 0, row0_8, ac, ld_policy);
+                            else tma_load_3d(sa, &P.tmaps[tmap], full_bar + st, 0, row0_8, ac);
                         }
                         if (!skip_b) bulk_load_1d(kRes ? smem + unit_off : sa + kASlabBytes, wsrc + (kPair ? rank * b_bytes : 0u), b_bytes, full_bar + st);
                         wsrc += kPair ? 2 * b_bytes : b_bytes;
@@ -486,7 +490,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         for (int jj, idx; item_get(item_ring, it, jj, idx); it++) {
             const LayerJob& J = jobs[jj];
             const int tile = tile_of(idx);
-            const int n_out = J.n_out, chunk_rows = J.out_chunk_rows, n_pos = J.n_pos;
+            const int n_out = J.n_out, chunk_rows = J.out_chunk_rows, n_pos = J.n_pos, lo_chunks = kPrecise ? J.lo_chunks : 0;
             const bool head = J.head_taps != 0, remap = J.remap != 0, wide = (J.S == 21);
             __half* __restrict__ out = J.out;
             float* __restrict__ zbuf = J.zbuf;
@@ -535,13 +539,23 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                 float v[8];
                 activate(r, cc, v);
                 if (valid || !remap) {
-                    uint32_t pk[4];
+                    uint32_t pk[4], pl[4];
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
                         __half2 hh = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
                         pk[e] = valid ? *reinterpret_cast<uint32_t*>(&hh) : 0u;
+                        if (kPrecise) {   // what the fp16 rounding dropped, as a second fp16
+                            const float2 hf = __half22float2(hh);
+                            __half2 ll = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+                            pl[e] = valid ? *reinterpret_cast<uint32_t*>(&ll) : 0u;
+                        }
                     }
                     const int c8 = (col0 + cc) >> 3;
+                    if (kPrecise) {
+                        __half* lo = out + ((size_t)(lo_chunks + c8) * chunk_rows + out_row) * 8;
+                        if (LB2_L2_HINTS) st_global_v4_hint(lo, make_uint4(pl[0], pl[1], pl[2], pl[3]), st_policy);
+                        else *reinterpret_cast<uint4*>(lo) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                    }
                     if (LB2_L2_HINTS)
                         st_global_v4_hint(out + ((size_t)c8 * chunk_rows + out_row) * 8, make_uint4(pk[0], pk[1], pk[2], pk[3]), st_policy);
                     else
@@ -883,7 +897,8 @@ __device__ __forceinline__ void value_head_body(const float* __restrict__ zbuf, 
 }
 
 // Both heads in one launch: blocks [0, value_blocks) run the value head, the rest the policy head
-// (one position per block, first 384 threads).
+// (one position per block, first 384 threads). (Keeping the launch to one wave — the policy blocks
+// looping over positions on the SMs the value head leaves free — measured the same 20 us: dropped.)
 __global__ void __launch_bounds__(kValueThreads) heads_kernel(const HeadArgs A) {
     extern __shared__ __align__(128) uint8_t hsm[];
     const int value_blocks = (A.n_value + kValueGroup - 1) / kValueGroup;
@@ -932,16 +947,20 @@ cudaError_t launch_expand(const ExpandArgs& a, cudaStream_t st) {
 }
 
 cudaError_t trunk_kernel_setup() {
-    cudaError_t e = cudaFuncSetAttribute(trunk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(trunk_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytes);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(trunk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytes);
+    e = cudaFuncSetAttribute(trunk_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytes);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(trunk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytesRes);
+    e = cudaFuncSetAttribute(trunk_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(trunk_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(trunk_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytesRes);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
 }
 
-cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool pair, bool resident, cudaStream_t st) {
+cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool pair, bool resident, bool precise, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kTrunkThreads);
@@ -967,8 +986,9 @@ cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool 
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    if (pair && resident) return cudaLaunchKernelEx(&cfg, trunk_kernel<true, true>, p);
-    return pair ? cudaLaunchKernelEx(&cfg, trunk_kernel<true, false>, p) : cudaLaunchKernelEx(&cfg, trunk_kernel<false, false>, p);
+    if (pair && resident) return cudaLaunchKernelEx(&cfg, trunk_kernel<true, true, false>, p);
+    if (precise) return pair ? cudaLaunchKernelEx(&cfg, trunk_kernel<true, false, true>, p) : cudaLaunchKernelEx(&cfg, trunk_kernel<false, false, true>, p);
+    return pair ? cudaLaunchKernelEx(&cfg, trunk_kernel<true, false, false>, p) : cudaLaunchKernelEx(&cfg, trunk_kernel<false, false, false>, p);
 }
 
 cudaError_t launch_heads(const HeadArgs& a, cudaStream_t st) {

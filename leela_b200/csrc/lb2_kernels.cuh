@@ -87,6 +87,9 @@ struct LayerJob {
     int32_t head_slot;       // which resident fused-head weight set (net * kMaxSplit + split)
     int32_t zparts;          // fused head: zbuf parts written before this job's (split * kColParts)
     int32_t layer;           // layer index within the net
+    int32_t n_real_slabs;    // c_in / 16. Equal to n_slabs except in split-operand ("precise") mode, where the K loop
+                             // runs over virtual slabs: [hi x Wh] [hi x Wl] [lo x Wh] (see lb2_api.cu, pack_trunk_weights)
+    int32_t lo_chunks;       // precise mode: the fp16 residual of the output goes lo_chunks chunk planes behind `out`; 0 = off
     const __half* wpk;       // packed weights: per (slab, tap group): [tap][2 chunks][n_out][8]
     const __half* wpk2;      // CTA-pair packing: per (slab, tap group): [rank][tap][2 chunks][n_out/2][8]
     const float* bias;       // [n_out]
@@ -149,7 +152,7 @@ struct MeanArgs {
 
 // launchers (lb2_kernels.cu)
 cudaError_t launch_expand(const ExpandArgs& a, cudaStream_t st);
-cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool pair, bool resident, cudaStream_t st);
+cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool pair, bool resident, bool precise, cudaStream_t st);
 cudaError_t launch_heads(const HeadArgs& a, cudaStream_t st);
 cudaError_t launch_ensemble_mean(const MeanArgs& a, cudaStream_t st);
 cudaError_t trunk_kernel_setup();

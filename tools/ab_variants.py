@@ -23,7 +23,7 @@ def do_build(specs):
             with tempfile.TemporaryDirectory() as td:
                 os.makedirs(os.path.join(td, "leela_b200", "csrc")); os.makedirs(os.path.join(td, "include"))
                 for rel in ["leela_b200/csrc/lb2_api.cu", "leela_b200/csrc/lb2_kernels.cu", "leela_b200/csrc/lb2_kernels.cuh",
-                            "leela_b200/csrc/lb2_ptx.cuh", "include/leela_b200.h"]:
+                            "leela_b200/csrc/lb2_ptx.cuh", "leela_b200/csrc/lb2_planes.cpp", "include/leela_b200.h"]:
                     open(os.path.join(td, rel), "wb").write(subprocess.check_output(["git", "show", f"{rev}:{rel}"], cwd=ROOT))
                 build.build(defines=defines, out=out, csrc=os.path.join(td, "leela_b200", "csrc"))
         else:
