@@ -683,6 +683,8 @@ int eval_on_device(lb2_ctx* ctx, DeviceState* d, const uint32_t* d_pol, const ui
         ha.hidden = nd.hidden; ha.ip2_w = nd.ip2_w; ha.ip2_b = nd.ip2_b; ha.winrate = d_win; ha.n_value = n;
         ha.v_parts = nd.trunk.back().n_split * lb2::kColParts;
     }
+    ha.trace = d->trace;
+    ha.trace_ctas = d->sm_count;
     CU_TRY(lb2::launch_heads(ha, st_k));
     ctx->launches++;
     mark(st_k);

@@ -902,12 +902,16 @@ __device__ __forceinline__ void value_head_body(const float* __restrict__ zbuf, 
 __global__ void __launch_bounds__(kValueThreads) heads_kernel(const HeadArgs A) {
     extern __shared__ __align__(128) uint8_t hsm[];
     const int value_blocks = (A.n_value + kValueGroup - 1) / kValueGroup;
+    unsigned long long* tr = (A.trace && threadIdx.x == 0 && (int)blockIdx.x < A.trace_ctas)
+                                 ? A.trace + ((size_t)blockIdx.x * kTraceItems + (kTraceItems - 2)) * kTraceEvents : nullptr;
+    if (tr) tr[0] = global_ns();
     if ((int)blockIdx.x < value_blocks)
         value_head_body(A.v_zbuf, A.v_chunk_rows, A.v_parts, A.v_bias, A.ip1_wt, A.ip1_b, A.hidden, A.ip2_w, A.ip2_b, A.n_value,
                         A.winrate, blockIdx.x, hsm);
     else
         policy_head_body(A.p_zbuf, A.p_chunk_rows, A.p_parts, A.p_bias, A.rotation, A.ensemble, A.temp, A.probs, blockIdx.x - value_blocks,
                          reinterpret_cast<float*>(hsm));
+    if (tr) tr[8] = global_ns();
 }
 
 // AVERAGE_ALL: one thread per output element; the 8 addends are summed in the reference's order.

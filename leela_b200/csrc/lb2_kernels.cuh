@@ -141,6 +141,8 @@ struct HeadArgs {
     const float* v_zbuf; int32_t v_chunk_rows; const float* v_bias; const float* ip1_wt; const float* ip1_b; int32_t hidden;
     const float* ip2_w; const float* ip2_b; float* winrate; int32_t n_value; int32_t v_parts;
     int32_t ensemble;            // 1: position p was evaluated under symmetry p % 8 (rotation is unused)
+    unsigned long long* trace;   // debug timeline (option "trace"): block b < trace_ctas stamps %globaltimer at its start and end
+    int32_t trace_ctas;          // into slot [b][kTraceItems - 2][0 / 8] (tools/trace_heads.py)
 };
 
 // AVERAGE_ALL on the device: mean over the 8 symmetries of each position, summed in the reference's
