@@ -1,4 +1,4 @@
-"""Small run of every kernel mode (CTA pairs, single CTA, resident weights, ensemble, 192-wide net) for
+"""Small run of every kernel mode (CTA pairs, single CTA, resident weights, precise, ensemble, 192-wide net) for
 compute-sanitizer: `compute-sanitizer --tool memcheck|synccheck|initcheck python tests/sanitizer_run.py` (0 errors, round 1)."""
 import os, sys
 sys.path.insert(0, os.getcwd())
@@ -16,8 +16,15 @@ print("resident identical", np.array_equal(p, p2), np.array_equal(v, v2))
 ev.set_option("resident_weights", 0); ev.set_option("cta_pair", 0)
 p3, v3 = ev.eval_both(g["policy_planes"][:5], g["value_planes"][:5], g["rotation"][:5], 0.75)
 print("single identical", np.array_equal(p, p3), np.array_equal(v, v3))
+for pair in (0, 1):
+    ev.set_option("cta_pair", pair); ev.set_option("precise", 1)
+    p4, v4 = ev.eval_both(g["policy_planes"][:5], g["value_planes"][:5], g["rotation"][:5], 0.75)
+    print("precise pair=%d" % pair, float(np.abs(p4 - g["policy"][:5]).max()), float(np.abs(v4 - g["value"][:5]).max()))
 ev.close()
 e2 = capi.Evaluator(policy=synth.policy192_weights())
 q = e2.eval_policy(g["policy_planes"][:3], g["rotation"][:3], 0.75)
 print("192", q.sum(1))
+e2.set_option("precise", 1)
+q2 = e2.eval_policy(g["policy_planes"][:3], g["rotation"][:3], 0.75)
+print("192 precise", q2.sum(1), float(np.abs(q - q2).max()))
 e2.close()

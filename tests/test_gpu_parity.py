@@ -172,6 +172,17 @@ def test_wide_policy_net_192_vs_oracle(ref_golden, bench_positions):
         assert (got.argmax(1) == want.argmax(1)).mean() >= 0.9
         for k in results:
             np.testing.assert_array_equal(results[k], got)
+        # precise mode on column-split layers (hi and lo planes of both splits): fp32-grade against the fp32 oracle,
+        # bit-identical across launch modes
+        e.set_option("precise", 1)
+        prec = {}
+        for mode, pair in ((1, 1), (0, 1), (1, 0)):
+            e.set_option("trunk_mode", mode); e.set_option("cta_pair", pair)
+            prec[(mode, pair)] = e.eval_policy(planes, rot, temp)
+        e.set_option("trunk_mode", 1); e.set_option("cta_pair", 1); e.set_option("precise", 0)
+        assert np.abs(prec[(1, 1)] - want).max() < 2e-4
+        for k in prec:
+            np.testing.assert_array_equal(prec[k], prec[(1, 1)])
         # a full-size batch through the persistent launch: 34 jobs, 3 jobs per round
         m = 256
         big = e.eval_policy(bench_positions["policy_planes"][:m], bench_positions["rotation"][:m], temp)
