@@ -564,7 +564,8 @@ int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers
         P.item_end = pl.total_items;
         P.use_flags = 1;
         P.next_item = ctx->dynamic_items ? d->item_counter : nullptr;
-        const int grid = pair ? std::min(d->sm_count & ~1, 2 * pl.total_items) : std::min(d->sm_count, pl.total_items);
+        int grid = pair ? std::min(d->sm_count & ~1, 2 * pl.total_items) : std::min(d->sm_count, pl.total_items);
+        if (const char* g = getenv("LB2_GRID")) grid = std::max(2, std::min(grid, atoi(g) & ~1));   // experiment: fewer SMs (power-cap study)
         const int n_clusters = pair ? grid / 2 : grid;
         if (resident) {
             // each cluster draws items of its preferred net until that counter runs past the end, then helps the
