@@ -33,6 +33,15 @@ constexpr int kEpiGroup = LB2_EPI_GROUP;
 #ifndef LB2_L2_HINTS
 #define LB2_L2_HINTS 3    // L2 eviction priority. 1: activation stores evict_last; 2: + activation loads evict_last; 3: stores evict_last, loads evict_first (measured best: DRAM write-back 285 -> 173 MB per launch)
 #endif
+#ifndef LB2_RELAXED_HANDBACK
+#define LB2_RELAXED_HANDBACK 1   // peer CTA hands the accumulator back with a relaxed remote arrive (no fence behind its stores)
+#endif
+#ifndef LB2_RELAXED_FORWARD
+#define LB2_RELAXED_FORWARD 1    // the peer's "my stage landed" arrive on the leader's barrier carries no fence either: the stage was
+                                 // written by TMA and is complete when the peer's own barrier flips — the forwarding thread has
+                                 // no writes of its own to publish, and the MMA reads the peer's shared memory itself (no cache
+                                 // in between). `.release.cluster` cost a MEMBAR.ALL.GPU round trip per stage: trunk 331 -> 319 us.
+#endif
 #ifndef LB2_EPI_PIPE
 #define LB2_EPI_PIPE 1    // epilogue keeps the TMEM loads of the next two units in flight
 #endif
@@ -382,7 +391,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                 const int n_st = jobs[jj].n_slabs * n_tap_groups(jobs[jj].ksize);
                 for (int s = 0; s < n_st; s++) {
                     mbar_wait(full_bar + stage, phase);
-                    mbar_arrive_remote(full_bar + stage, 0);
+                    if (LB2_RELAXED_FORWARD) mbar_arrive_remote_relaxed(full_bar + stage, 0); else mbar_arrive_remote(full_bar + stage, 0);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -634,7 +643,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) {
-                if (kPair && !leader) mbar_arrive_remote(tempty_bar + acc, 0);
+                if (kPair && !leader) { if (LB2_RELAXED_HANDBACK) mbar_arrive_remote_relaxed(tempty_bar + acc, 0); else mbar_arrive_remote(tempty_bar + acc, 0); }
                 else mbar_arrive(tempty_bar + acc);
             }
             if (warp == 2 && lane == 0) LB2_TRACE(it, 10);

@@ -84,6 +84,18 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
         : "memory");
 }
 
+// the same without memory ordering: for signals that publish no memory of the signalling thread (the accumulator
+// hand-back: the TMEM loads it covers have already completed into registers; the peer's stage-landed forward: the
+// stage was written by TMA and completed on the peer's own barrier). `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR and
+// waits for every global store the thread has in flight.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)), "r"(cta)
+        : "memory");
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch
 // A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (and run its
 // prologue) while its predecessor in the stream is still finishing; grid_dep_wait() blocks until the
