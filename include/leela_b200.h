@@ -152,9 +152,11 @@ int lb2_device_count(lb2_ctx* ctx);
  *   "trunk_mode": 0 = one launch per layer, 1 = single persistent dataflow launch (default)
  *   "cta_pair":   1 = tensor-core work issued for CTA pairs (tcgen05 cta_group::2, default), 0 = per CTA
  *   "dynamic_items": 1 = clusters claim work items from a global in-order counter (default), 0 = round robin
- *   "resident_weights": 1 = each CTA keeps its half of a layer's packed weights in shared memory for all the
- *                 layer's items it processes (clusters are split between the two nets and help each other
- *                 out at the end); cuts the weight stream from L2 by 77 %, launch time unchanged: default 0
+ *   "resident_weights": each CTA keeps its half of a layer's packed weights in shared memory for all the layer's items
+ *                 it processes, the clusters are split between the two nets (by estimated work; each helps the other
+ *                 out when its own net runs dry) and the pipeline stages carry activation slabs only. 0 = off, 1 = whenever
+ *                 every layer fits (c_in, c_out <= 128, not in precise mode), 2 = only for launches that run both nets
+ *                 (default: 4 % faster there, no gain for one net alone). Bit-identical to the streaming form.
  *   "precise":    1 = split-operand mode: activations and weights are carried as fp16 hi + fp16 lo and every layer
  *                 accumulates three tensor-core terms (hi*Wh + hi*Wl + lo*Wh) in fp32. Results lie within 1e-4 of the
  *                 reference's fp32 OpenBLAS path (measured max 8.9e-5 policy, 2.8e-5 value over the 1024-position

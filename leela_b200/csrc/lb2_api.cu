@@ -23,7 +23,10 @@
 #include "lb2_kernels.cuh"
 
 #ifndef LB2_RESIDENT_DEFAULT
-#define LB2_RESIDENT_DEFAULT 0   // measured: -77 % weight traffic from L2, launch time unchanged within +-1 % -> off; tools/ab_variants.py builds both
+#define LB2_RESIDENT_DEFAULT 2   // 0 off, 1 whenever the layers fit, 2 when both nets run in the launch. Measured at batch 256 once the
+                                 // remote arrives had lost their fences: both nets 324 -> 311 us (the clusters of a net see only its own
+                                 // item mix: no short value item waits for the accumulator behind a policy epilogue), one net alone
+                                 // +-1 % (policy) / +4 % (value): hence 2
 #endif
 
 namespace {
@@ -494,7 +497,8 @@ int run_trunk(lb2_ctx* ctx, DeviceState* d, bool run[2], int n, int limit_layers
     // resident-weights mode: CTA pairs, the single dataflow launch with dynamic claiming, and every layer's
     // half of the packed weights must fit the resident area (c_in, c_out <= 128: no column splits)
     const bool precise = ctx->precise != 0;
-    bool resident = pair && !precise && ctx->resident_weights != 0 && ctx->trunk_mode == 1 && ctx->dynamic_items != 0;
+    const bool want_resident = ctx->resident_weights == 1 || (ctx->resident_weights == 2 && run[0] && run[1]);
+    bool resident = pair && !precise && want_resident && ctx->trunk_mode == 1 && ctx->dynamic_items != 0;
     int n_jobs_est = 0;
     for (int k = 0; k < 2 && resident; k++) {
         if (!run[k]) continue;
@@ -1249,7 +1253,8 @@ int lb2_set_option(lb2_ctx* ctx, const char* name, long value) {
     } else if (!strcmp(name, "overlap_io")) {
         ctx->overlap_io = value ? 1 : 0;
     } else if (!strcmp(name, "resident_weights")) {
-        ctx->resident_weights = value ? 1 : 0;
+        if (value < 0 || value > 2) return fail(LB2_ERR_INVALID, "resident_weights must be 0, 1 or 2");
+        ctx->resident_weights = value;
     } else if (!strcmp(name, "precise")) {
         ctx->precise = value ? 1 : 0;
     } else if (!strcmp(name, "policy_clusters")) {

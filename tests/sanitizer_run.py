@@ -6,6 +6,7 @@ import numpy as np
 from leela_b200 import capi, synth
 g = np.load("tests/golden/ref_golden.npz")
 ev = capi.Evaluator(policy=synth.policy_weights(), value=synth.value_weights())
+ev.set_option("resident_weights", 0)
 p, v = ev.eval_both(g["policy_planes"][:5], g["value_planes"][:5], g["rotation"][:5], 0.75)
 print("both", float(np.abs(p - g["policy"][:5]).max()), float(np.abs(v - g["value"][:5]).max()))
 pe, ve = ev.eval_ensemble(g["policy_planes"][:2], g["value_planes"][:2], 0.75)

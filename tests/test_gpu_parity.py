@@ -213,9 +213,15 @@ def test_resident_weights_mode_bit_identical(ev, ref_golden, bench_positions):
     cases = [(g["policy_planes"], g["value_planes"], g["rotation"]),
              (b["policy_planes"][:256], b["value_planes"][:256], b["rotation"][:256]),
              (b["policy_planes"][300:337], b["value_planes"][300:337], b["rotation"][300:337])]
+    assert ev.get_option("resident_weights") == 2   # default: resident for launches that run both nets
+    ev.set_option("resident_weights", 0)
     want = [ev.eval_both(*c, TEMP) for c in cases]
     want_p = ev.eval_policy(cases[1][0], cases[1][2], TEMP)
     want_v = ev.eval_value(cases[2][1], cases[2][2])
+    ev.set_option("resident_weights", 2)
+    for c, w in zip(cases, want):
+        p, v = ev.eval_both(*c, TEMP)
+        assert np.array_equal(p, w[0]) and np.array_equal(v, w[1])
     ev.set_option("resident_weights", 1)
     try:
         for split in (-1, 1, 73):
@@ -227,7 +233,7 @@ def test_resident_weights_mode_bit_identical(ev, ref_golden, bench_positions):
         assert np.array_equal(ev.eval_policy(cases[1][0], cases[1][2], TEMP), want_p)
         assert np.array_equal(ev.eval_value(cases[2][1], cases[2][2]), want_v)
     finally:
-        ev.set_option("resident_weights", 0)
+        ev.set_option("resident_weights", 2)
         ev.set_option("policy_clusters", -1)
 
 

@@ -1,6 +1,8 @@
 """A/B timing of tuning builds of libleela_b200.so on ONE box, interleaved (boxes differ by a few %).
 Here:   python tools/ab_variants.py build name[@rev][:DEF=VAL,DEF2=VAL2] ...   (name 'head' = last commit's sources, name@rev = that commit's)
-On GPU: python tools/ab_variants.py run [reps]       -> trunk/step us per variant, interleaved rounds"""
+On GPU: python tools/ab_variants.py run [reps]       -> trunk/step us per variant, interleaved rounds
+        python tools/ab_variants.py opts reps "name=value,name=value" "..." ...  -> the same for ONE library (LB2_LIB or the
+        in-tree one) under different run-time option sets ("" = defaults), one fresh process per measurement"""
 import os, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -45,6 +47,8 @@ rot = torch.from_numpy(g["rotation"][:B].copy()).to(dev)
 probs = torch.empty((B, 361), device=dev); win = torch.empty((B,), device=dev)
 ev = capi.Evaluator(policy=synth.policy_weights(), value=synth.value_weights())
 ev.set_option("max_batch", max(B, 512))
+for kv in filter(None, os.environ.get("LB2_OPTS", "").split(",")):
+    ev.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 a = (pp.data_ptr(), vp.data_ptr(), rot.data_ptr(), B, 0.75, probs.data_ptr() if {which!r} != "value" else None, win.data_ptr() if {which!r} != "policy" else None)
 for _ in range(10): ev.eval_both_device(*a, stream=st.cuda_stream)
 torch.cuda.synchronize()
@@ -55,7 +59,9 @@ for _ in range(50): ev.eval_both_device(*a, stream=st.cuda_stream)
 e1.record(st); torch.cuda.synchronize()
 print("RES %.1f %.1f %.6f" % (e0.elapsed_time(e1) / 50 * 1e3, ev.get_option("trunk_ns") / 50 / 1e3, float(probs.sum()) + float(win.sum())))
 """
-    env = dict(os.environ, LB2_LIB=lib)
+    env = dict(os.environ)
+    if lib:
+        env["LB2_LIB"] = lib
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     for line in r.stdout.splitlines():
         if line.startswith("RES"):
@@ -78,8 +84,25 @@ def do_run(reps, B=256, which="both"):
         if ok:
             print(f"{l:28s} trunk {statistics.median(x[1] for x in ok):8.1f}  step {statistics.median(x[0] for x in ok):8.1f}  (n={len(ok)})")
 
+def do_opts(reps, optsets, B=256, which="both"):
+    import statistics
+    res = {o: [] for o in optsets}
+    for r in range(reps):
+        for o in optsets:
+            os.environ["LB2_OPTS"] = o
+            step, trunk, chk = one(os.environ.get("LB2_LIB", ""), B, which)
+            res[o].append((step, trunk))
+            print(f"round {r} {o or 'defaults':44s} step {step} us trunk {trunk} us checksum {chk}", flush=True)
+    print("--- median trunk us / step us")
+    for o in optsets:
+        ok = [x for x in res[o] if x[0] is not None]
+        if ok:
+            print(f"{o or 'defaults':44s} trunk {statistics.median(x[1] for x in ok):8.1f}  step {statistics.median(x[0] for x in ok):8.1f}  (n={len(ok)})")
+
 if __name__ == "__main__":
     if sys.argv[1] == "build":
         do_build(sys.argv[2:])
+    elif sys.argv[1] == "opts":
+        do_opts(int(sys.argv[2]), sys.argv[3:], int(os.environ.get("AB_B", "256")), os.environ.get("AB_WHICH", "both"))
     else:
         do_run(int(sys.argv[2]) if len(sys.argv) > 2 else 3, int(sys.argv[3]) if len(sys.argv) > 3 else 256, sys.argv[4] if len(sys.argv) > 4 else "both")

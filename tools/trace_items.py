@@ -18,6 +18,8 @@ rot = torch.from_numpy(g["rotation"][:B].copy()).to(dev)
 probs = torch.empty((B, 361), device=dev); win = torch.empty((B,), device=dev)
 ev = capi.Evaluator(policy=synth.policy_weights(), value=synth.value_weights())
 ev.set_option("max_batch", 512)
+for kv in filter(None, os.environ.get("LB2_OPTS", "").split(",")):   # e.g. LB2_OPTS=resident_weights=1,policy_clusters=48
+    ev.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 a = (pp.data_ptr(), vp.data_ptr(), rot.data_ptr(), B, 0.75, probs.data_ptr() if which != "value" else None,
      win.data_ptr() if which != "policy" else None)
 for _ in range(20):
@@ -30,6 +32,16 @@ for _ in range(3):
 torch.cuda.synchronize()
 T = ev.read_trace().astype(np.int64)
 print("launch %.1f us" % ((T[:, 95, 2].max() - T[:, 95, 0][T[:, 95, 0] > 0].min()) / 1e3))
+t0 = T[:, 95, 0][T[:, 95, 0] > 0].min()
+lead = T[0::2]
+busy = []
+for c in range(lead.shape[0]):
+    n = int((lead[c, :94, 7] > 0).sum())
+    j = lead[c, :n, 15] >> 21
+    busy.append(((lead[c, :n, 7] - lead[c, :n, 6]).sum() / 1e3, n, (lead[c, n - 1, 7] - t0) / 1e3 if n else 0, int((j[: n] == j[0]).sum()) if n else 0))
+busy = np.array(busy)
+print("per cluster: MMA issue time min %.0f median %.0f max %.0f us; items min %d max %d; last MMA issued at min %.0f median %.0f max %.0f us" % (
+    busy[:, 0].min(), np.median(busy[:, 0]), busy[:, 0].max(), busy[:, 1].min(), busy[:, 1].max(), busy[:, 2].min(), np.median(busy[:, 2]), busy[:, 2].max()))
 for rank in (0, 1):
     L = T[rank::2]
     rows = {}
