@@ -42,6 +42,14 @@ constexpr int kEpiGroup = LB2_EPI_GROUP;
                                  // no writes of its own to publish, and the MMA reads the peer's shared memory itself (no cache
                                  // in between). `.release.cluster` cost a MEMBAR.ALL.GPU round trip per stage: trunk 331 -> 319 us.
 #endif
+#ifndef LB2_EPI_PAIR_HALVES
+#define LB2_EPI_PAIR_HALVES 1    // ordinary epilogue: unit u = (half u & 1, column block u >> 1): the two units of a group share
+                                 // their eight bias values — one shared-memory read (the port the tensor core's operands come
+                                 // through) instead of two
+#endif
+#ifndef LB2_CONSUMER_PROXY_FENCE
+#define LB2_CONSUMER_PROXY_FENCE 1   // producer: fence.proxy.async (MEMBAR.ALL.GPU) between seeing an item's dependencies and its TMA loads
+#endif
 #ifndef LB2_EPI_PIPE
 #define LB2_EPI_PIPE 1    // epilogue keeps the TMEM loads of the next two units in flight
 #endif
@@ -343,7 +351,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             if (elect_one()) {
                 int st = stage; uint32_t ph = phase;  // private walk; all lanes advance the shared view below
                 LB2_TRACE(pit, 1);
-                fence_proxy_async();  // order the TMA (async proxy) reads after the acquires above
+                if (LB2_CONSUMER_PROXY_FENCE) fence_proxy_async();  // order the TMA (async proxy) reads after the acquires above
                 if (drain) {
                     for (int k = 0; k < kStages; k++) {   // the waits the next kStages stage fills would do, done now
                         const int s2 = st + k;
@@ -522,9 +530,23 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                 out_row2[h] = remap ? pos * 400 + y * 20 + x : row;
             }
             const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256 + col0;
+            // unit -> (half, column block). The fused-head path walks half-major; the ordinary path pairs the halves
             auto unit_addr = [&](int u) { const int h = u >= upc ? 1 : 0; return tbase + h * 128 + (u - h * upc) * 8; };
+            auto unit_half = [&](int u) { return LB2_EPI_PAIR_HALVES ? (u & 1) : (u >= upc ? 1 : 0); };
+            auto unit_col = [&](int u) { return LB2_EPI_PAIR_HALVES ? (u >> 1) * 8 : (u - (u >= upc ? upc : 0)) * 8; };
+            auto unit_addr2 = [&](int u) { return tbase + unit_half(u) * 128 + unit_col(u); };
 
             // bias + ELU of one unit
+            auto activate_b = [&](const uint32_t (&r)[8], const float4& b0, const float4& b1, float (&v)[8]) {
+                v[0] = __uint_as_float(r[0]) + b0.x; v[1] = __uint_as_float(r[1]) + b0.y;
+                v[2] = __uint_as_float(r[2]) + b0.z; v[3] = __uint_as_float(r[3]) + b0.w;
+                v[4] = __uint_as_float(r[4]) + b1.x; v[5] = __uint_as_float(r[5]) + b1.y;
+                v[6] = __uint_as_float(r[6]) + b1.z; v[7] = __uint_as_float(r[7]) + b1.w;
+                if (!(P.debug_flags & 4)) {
+#pragma unroll
+                    for (int e = 0; e < 8; e++) v[e] = elu_fast(v[e]);
+                }
+            };
             auto activate = [&](const uint32_t (&r)[8], int cc, float (&v)[8]) {
                 const float* bp = bs + col0 + cc;
                 const float4 b0 = *reinterpret_cast<const float4*>(bp), b1 = *reinterpret_cast<const float4*>(bp + 4);
@@ -540,13 +562,13 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             // ordinary layer: pack to fp16 and store one 16-byte chunk row. Padding rows/columns of
             // the row space are written as zeros (whole sectors: partial-sector writes cost L2 fills);
             // layer 1 re-addresses S=21 rows into the S=20 space and must skip them instead.
-            auto store_unit = [&](const uint32_t (&r)[8], int u) {
-                const int h = u >= upc ? 1 : 0;
-                const int cc = (u - h * upc) * 8;
+            auto store_unit = [&](const uint32_t (&r)[8], int u, const float4& b0, const float4& b1) {
+                const int h = unit_half(u);
+                const int cc = unit_col(u);
                 const bool valid = h ? valid2[1] : valid2[0];
                 const int out_row = h ? out_row2[1] : out_row2[0];
                 float v[8];
-                activate(r, cc, v);
+                activate_b(r, b0, b1, v);
                 if (valid || !remap) {
                     uint32_t pk[4], pl[4];
 #pragma unroll
@@ -609,13 +631,21 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                 auto load_group = [&](int u, uint32_t (&r)[G][8]) {
 #pragma unroll
                     for (int g = 0; g < G; g++)
-                        if (u + g < n_units) tmem_ld_32x8(unit_addr(u + g), r[g]);
+                        if (u + g < n_units) tmem_ld_32x8(unit_addr2(u + g), r[g]);
                 };
                 auto store_group = [&](int u, const uint32_t (&r)[G][8]) {
+                    float4 b0, b1;
 #pragma unroll
                     for (int g = 0; g < G; g++)
-                        if (u + g < n_units) store_unit(r[g], u + g);
+                        if (u + g < n_units) {
+                            if (!LB2_EPI_PAIR_HALVES || !(g & 1)) {   // (u is even: G is)
+                                const float* bp = bs + col0 + unit_col(u + g);
+                                b0 = *reinterpret_cast<const float4*>(bp); b1 = *reinterpret_cast<const float4*>(bp + 4);
+                            }
+                            store_unit(r[g], u + g, b0, b1);
+                        }
                 };
+                static_assert(!LB2_EPI_PAIR_HALVES || G % 2 == 0, "paired halves need an even group");
 #if LB2_EPI_PIPE
                 uint32_t ra[G][8], rb[G][8];
                 load_group(0, ra);
