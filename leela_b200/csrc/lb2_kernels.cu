@@ -602,30 +602,56 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                 // last trunk layer: the net's final 3x3 conv to ONE channel is folded in here as nine
                 // per-tap dot products over this warp's channels, z[t] += sum_c w[t][c] * v[c] (fp32,
                 // unrounded v); the heads kernel gathers them. zbuf[part][t][row]; padding rows give 0.
-#pragma unroll 1
-                for (int h = 0; h < 2 && n_units; h++) {
-                    float z[9];
+                // Both row halves of a column block go through the taps together: one read of the eight bias values and
+                // of the 72 head weights (shared memory: the tensor core's operand port) serves two rows; the next block's
+                // TMEM loads are in flight meanwhile. Per row the sums run in the same order as ever.
+                if (n_units) {
+                    float z0[9], z1[9];
 #pragma unroll
-                    for (int t = 0; t < 9; t++) z[t] = 0.0f;
-#pragma unroll 1
-                    for (int k = 0; k < upc; k++) {
-                        uint32_t r[8]; float v[8];
-                        tmem_ld_32x8(unit_addr(h * upc + k), r);
-                        tmem_ld_wait();
-                        activate(r, k * 8, v);
+                    for (int t = 0; t < 9; t++) z0[t] = z1[t] = 0.0f;
+                    uint32_t ra[2][8], rb[2][8];
+                    tmem_ld_32x8(unit_addr(0), ra[0]);
+                    tmem_ld_32x8(unit_addr(upc), ra[1]);
+                    tmem_ld_wait();
+                    auto taps = [&](const uint32_t (&r)[2][8], int k) {
+                        const float* bp = bs + col0 + k * 8;
+                        const float4 b0 = *reinterpret_cast<const float4*>(bp), b1 = *reinterpret_cast<const float4*>(bp + 4);
+                        float v0[8], v1[8];
+                        activate_b(r[0], b0, b1, v0);
+                        activate_b(r[1], b0, b1, v1);
 #pragma unroll
                         for (int t = 0; t < 9; t++) {
                             const float* wt = headw_s + t * 128 + col0 + k * 8;
                             const float4 w0 = *reinterpret_cast<const float4*>(wt), w1 = *reinterpret_cast<const float4*>(wt + 4);
-                            z[t] = fmaf(v[0], w0.x, z[t]); z[t] = fmaf(v[1], w0.y, z[t]);
-                            z[t] = fmaf(v[2], w0.z, z[t]); z[t] = fmaf(v[3], w0.w, z[t]);
-                            z[t] = fmaf(v[4], w1.x, z[t]); z[t] = fmaf(v[5], w1.y, z[t]);
-                            z[t] = fmaf(v[6], w1.z, z[t]); z[t] = fmaf(v[7], w1.w, z[t]);
+                            z0[t] = fmaf(v0[0], w0.x, z0[t]); z0[t] = fmaf(v0[1], w0.y, z0[t]);
+                            z0[t] = fmaf(v0[2], w0.z, z0[t]); z0[t] = fmaf(v0[3], w0.w, z0[t]);
+                            z0[t] = fmaf(v0[4], w1.x, z0[t]); z0[t] = fmaf(v0[5], w1.y, z0[t]);
+                            z0[t] = fmaf(v0[6], w1.z, z0[t]); z0[t] = fmaf(v0[7], w1.w, z0[t]);
+                            z1[t] = fmaf(v1[0], w0.x, z1[t]); z1[t] = fmaf(v1[1], w0.y, z1[t]);
+                            z1[t] = fmaf(v1[2], w0.z, z1[t]); z1[t] = fmaf(v1[3], w0.w, z1[t]);
+                            z1[t] = fmaf(v1[4], w1.x, z1[t]); z1[t] = fmaf(v1[5], w1.y, z1[t]);
+                            z1[t] = fmaf(v1[6], w1.z, z1[t]); z1[t] = fmaf(v1[7], w1.w, z1[t]);
                         }
+                    };
+#pragma unroll 1
+                    for (int k = 0; k < upc; k += 2) {   // upc is even (n_out is a multiple of 32, two column parts)
+                        tmem_ld_32x8(unit_addr(k + 1), rb[0]);
+                        tmem_ld_32x8(unit_addr(upc + k + 1), rb[1]);
+                        taps(ra, k);
+                        tmem_ld_wait();
+                        if (k + 2 < upc) {
+                            tmem_ld_32x8(unit_addr(k + 2), ra[0]);
+                            tmem_ld_32x8(unit_addr(upc + k + 2), ra[1]);
+                        }
+                        taps(rb, k + 1);
+                        tmem_ld_wait();
                     }
-                    float* zb = zbuf + (size_t)(J.zparts + part) * 9 * chunk_rows + out_row2[h];
+                    float* zb = zbuf + (size_t)(J.zparts + part) * 9 * chunk_rows;
 #pragma unroll
-                    for (int t = 0; t < 9; t++) zb[(size_t)t * chunk_rows] = valid2[h] ? z[t] : 0.0f;
+                    for (int t = 0; t < 9; t++) {
+                        zb[(size_t)t * chunk_rows + out_row2[0]] = valid2[0] ? z0[t] : 0.0f;
+                        zb[(size_t)t * chunk_rows + out_row2[1]] = valid2[1] ? z1[t] : 0.0f;
+                    }
                 }
             } else if (n_units) {
                 auto load_group = [&](int u, uint32_t (&r)[G][8]) {
