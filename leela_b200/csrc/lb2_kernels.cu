@@ -190,7 +190,10 @@ __device__ __forceinline__ void locate_item(const TrunkParams& P, const LayerJob
 }
 
 constexpr int kClaimRing = 16;  // work-item ring entries per CTA (claimed-but-unpublished items)
-constexpr int kClaimAhead = 4;  // how far ahead of the last published item the scout may hand out items
+#ifndef LB2_CLAIM_AHEAD
+#define LB2_CLAIM_AHEAD 4
+#endif
+constexpr int kClaimAhead = LB2_CLAIM_AHEAD;  // how far ahead of the last published item the scout may hand out items
 constexpr uint32_t kEndJob = 63;  // job field of the ring entry that ends a CTA's walk
 
 // Work-item ring. The scout warp of the cluster leader decides which item the cluster processes
