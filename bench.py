@@ -144,6 +144,10 @@ def cpu_reference(sample, warmup, steps, threads=None):
                             "sample": f"{steps} steps x {k} positions through oracle/leela_oracle.c"}
 
 
+WORKLOAD = ("policy NN128 + value NNValue, batch 256 positions per GPU per step "
+            "(BASELINE.json configs[1] shape, policy+value as the metric names)")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -160,8 +164,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sample / v, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"policy NN128 + value NNValue, {sample} positions per step on host cores "
-                                   f"(reference evaluates batch 1 per thread)", "batch_per_step": sample},
+            # the same workload as the GPU arm names; how the CPU arm samples it is in cpu_baseline.sample
+            "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch},
             "cpu_baseline": info,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -189,6 +193,66 @@ def run_engine(args):
     return 0
 
 
+def kernel_source_sha():
+    """Identifies the kernel sources a profile was taken from (profiles/trunk_traffic.json carries the same hash)."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("lb2_kernels.cu", "lb2_kernels.cuh", "lb2_ptx.cuh"):
+        with open(os.path.join(ROOT, "leela_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def parity_check(ev, pp, vp, rot):
+    """The GPU path against the reference's own outputs for the 1024 bench positions (tests/golden/bench_golden.npz,
+    generated by running the reference here), in the precision mode being benchmarked."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "bench_golden.npz"))
+    probs, win = ev.eval_both(pp, vp, rot, float(g["softmax_temp"]))
+    dp, dv = np.abs(probs - g["policy"]), np.abs(win - g["value"])
+    return {"policy_max": float(dp.max()), "value_max": float(dv.max()), "policy_p99_9": float(np.quantile(dp, 0.999)),
+            "top1_agree": int((probs.argmax(1) == g["policy"].argmax(1)).sum()), "positions": int(len(win)),
+            "mode": {"policy_precision": ev.get_option("policy_precision"), "value_precision": ev.get_option("value_precision")},
+            "against": "reference fp32 OpenBLAS outputs (tests/golden/bench_golden.npz), softmax temperature %.2f" % float(g["softmax_temp"])}
+
+
+def e2e_leg(ev, B, h_in, n_threads, total_steps, sync):
+    """`n_threads` persistent host threads make blocking lb2_eval_both calls on pinned host buffers (H2D, kernels and D2H
+    inside every call). The threads are started and warmed up first, then released together; the clock runs from the
+    release to the last thread's last result. Returns (seconds, checksum)."""
+    import threading
+    import torch
+    h_pp, h_vp, h_rot = h_in
+    outs = [(torch.empty((B, 361), dtype=torch.float32).pin_memory(), torch.empty((B,), dtype=torch.float32).pin_memory())
+            for _ in range(n_threads)]
+    gate = threading.Barrier(n_threads + 1)
+    done = threading.Barrier(n_threads + 1)
+    bounds = [total_steps * t // n_threads for t in range(n_threads + 1)]
+
+    def caller(t):
+        probs, win = outs[t]
+        def step(i):
+            s = i % len(h_pp)
+            ev.eval_both_raw(h_pp[s].data_ptr(), h_vp[s].data_ptr(), h_rot[s].data_ptr(), B, TEMP, probs.data_ptr(), win.data_ptr())
+        for i in range(2):
+            step(i + t)
+        gate.wait()
+        for i in range(bounds[t], bounds[t + 1]):
+            step(i)
+        done.wait()
+
+    threads = [threading.Thread(target=caller, args=(t,)) for t in range(n_threads)]
+    for th in threads:
+        th.start()
+    sync()
+    gate.wait()
+    t0 = time.perf_counter()
+    done.wait()
+    dt = time.perf_counter() - t0
+    for th in threads:
+        th.join()
+    return dt, float(outs[0][0].sum()) + float(outs[0][1].sum())
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -202,17 +266,23 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200; there is no CPU fallback (use --impl reference for the CPU path)")
     torch.cuda.set_device(local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")   # host-side barriers that put no kernel on any GPU
     dev = torch.device("cuda", local)
     B = args.batch
 
     ev = capi.Evaluator(policy=synth.policy_weights(), value=synth.value_weights(), devices=[local])
     ev.set_option("max_batch", max(B, 256))
-    if args.overlap_io:
-        ev.set_option("overlap_io", 1)
     if args.precise:
-        ev.set_option("precise", 1)
+        args.policy_precision, args.value_precision = 2, 2
+    if args.policy_precision is not None or args.value_precision is not None:
+        ev.set_precision(args.policy_precision if args.policy_precision is not None else ev.get_option("policy_precision"),
+                         args.value_precision if args.value_precision is not None else ev.get_option("value_precision"))
+    if args.no_graphs:
+        ev.set_option("use_graphs", 0)
+    prec = (ev.get_option("policy_precision"), ev.get_option("value_precision"))
     pp, vp, rot = load_positions()
     n_pos = pp.shape[0]
     # input pool: every batch is a different window (stride 3, wrapping) over the distinct positions,
@@ -242,17 +312,22 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    parity = parity_check(ev, pp, vp, rot) if rank == 0 else None
+
     # ---------------------------------------------------------------- kernels, inputs in HBM
-    for i in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    ev.set_option("profile_reserve", args.steps + warm + 8)   # the trunk's event pairs exist before the clock starts
+    ev.set_option("profile_trunk", 1)
+    for i in range(warm):
         step(i)
     barrier()
+    ev.get_option("trunk_ns")   # discard the warm-up's record
     sampler = ClockSampler(local) if rank == 0 else None
-    ev.set_option("profile_trunk", 1)
-    ev.get_option("trunk_ns")
-    launches0 = ev.launch_count
+    launches0, graphs0 = ev.launch_count, ev.get_option("graph_launches")
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
+    t_host0 = time.perf_counter()
     for i in range(args.steps):
         if flush is not None:
             flush.fill_(i & 0xFF)        # evict L2 between steps; outside the timed region
@@ -260,88 +335,128 @@ def run_ours(args):
         step(i)
         stops[i].record(stream)
     barrier()
+    timed_wall_s = time.perf_counter() - t_host0
     launches = ev.launch_count - launches0
+    graph_launches = ev.get_option("graph_launches") - graphs0
     step_ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
     total_ms = sum(step_ms)
     trunk_ns = ev.get_option("trunk_ns")
     ev.set_option("profile_trunk", 0)
-
-    # ---------------------------------------------------------------- end to end through the C ABI
-    import threading
-    n_host = max(1, args.e2e_threads)
-    host_sets = min(n_sets, 16)
-    h_pp = [torch.from_numpy(pp[w].astype(np.int32)).pin_memory() for w in window[:host_sets]]
-    h_vp = [torch.from_numpy(vp[w].astype(np.int32)).pin_memory() for w in window[:host_sets]]
-    h_rot = [torch.from_numpy(rot[w].copy()).pin_memory() for w in window[:host_sets]]
-    h_probs = [torch.empty((B, 361), dtype=torch.float32).pin_memory() for _ in range(n_host)]
-    h_win = [torch.empty((B,), dtype=torch.float32).pin_memory() for _ in range(n_host)]
-
-    def step_e2e(i, t):
-        s = i % host_sets
-        ev.eval_both_raw(h_pp[s].data_ptr(), h_vp[s].data_ptr(), h_rot[s].data_ptr(), B, TEMP,
-                         h_probs[t].data_ptr(), h_win[t].data_ptr())   # blocking: returns after the D2H of this step's results
-
-    def caller(t, lo, hi):
-        for i in range(lo, hi):
-            step_e2e(i, t)
-
-    for i in range(3):
-        step_e2e(i, 0)
-    barrier()
-    bounds = [args.steps * t // n_host for t in range(n_host + 1)]
-    threads = [threading.Thread(target=caller, args=(t, bounds[t], bounds[t + 1])) for t in range(n_host)]
-    t0 = time.perf_counter()
-    for th in threads:
-        th.start()
-    for th in threads:
-        th.join()
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    checksum = float(h_probs[0].sum()) + float(h_win[0].sum())
-    barrier()
     clocks = sampler.stop() if sampler else None
 
-    total_ms, e2e_ms = shard.max_over_ranks([total_ms, e2e_s * 1e3], dist if world > 1 else None, dev)
+    # ---------------------------------------------------------------- end to end through the C ABI
+    host_sets = min(n_sets, 16)
+    h_in = ([torch.from_numpy(pp[w].astype(np.int32)).pin_memory() for w in window[:host_sets]],
+            [torch.from_numpy(vp[w].astype(np.int32)).pin_memory() for w in window[:host_sets]],
+            [torch.from_numpy(rot[w].copy()).pin_memory() for w in window[:host_sets]])
+    # at least half a second of calls: k x steps
+    k = max(1, int(np.ceil(0.5 / max(1e-6, total_ms * 1e-3))))
+    e2e_steps = k * args.steps
+    e2e = {}
+    for n_host in sorted({1, max(1, args.e2e_threads)}):
+        barrier()
+        dt, checksum = e2e_leg(ev, B, h_in, n_host, e2e_steps, barrier)
+        e2e[n_host] = (dt, checksum)
+    barrier()
+
+    n_main = max(1, args.e2e_threads)
+    per_rank = torch.tensor([total_ms] + [e2e[t][0] * 1e3 for t in sorted(e2e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        gathered = [torch.zeros_like(per_rank) for _ in range(world)]
+        dist.all_gather(gathered, per_rank)
+        table = torch.stack(gathered).cpu().numpy()
+    else:
+        table = per_rank.cpu().numpy()[None, :]
+    mx = table.max(0)   # slowest rank bounds the job
+    total_ms_max = float(mx[0])
+    e2e_ms_max = {t: float(mx[1 + i]) for i, t in enumerate(sorted(e2e))}
+
+    # ---------------------------------------------------------------- all N GPUs from ONE process (rank 0), the others idle
+    in_process = None
+    if world > 1:
+        dist.barrier(group=cpu_group)
+        if rank == 0:
+            ev_all = capi.Evaluator(policy=synth.policy_weights(), value=synth.value_weights(), devices=list(range(world)))
+            ev_all.set_option("max_batch", max(B, 256))
+            ev_all.set_precision(*prec)
+            nb = world * B
+            idx = [np.arange(f, f + nb) % n_pos for f in (0, 7, 13, 29)]
+            h_all = ([torch.from_numpy(pp[w].astype(np.int32)).pin_memory() for w in idx],
+                     [torch.from_numpy(vp[w].astype(np.int32)).pin_memory() for w in idx],
+                     [torch.from_numpy(rot[w].copy()).pin_memory() for w in idx])
+            dt, _ = e2e_leg(ev_all, nb, h_all, 2, max(8, e2e_steps // 4), lambda: None)
+            in_process = {"value": nb * max(8, e2e_steps // 4) / dt, "unit": UNIT, "devices": world, "host_threads": 2,
+                          "positions_per_call": nb,
+                          "what": "ONE process drives all GPUs through lb2_init(devices=0..N-1) + lb2_eval_both on host buffers; "
+                                  "every call is cut into 256-position batches dealt to the devices' I/O slots"}
+            ev_all.close()
+        dist.barrier(group=cpu_group)
 
     if rank == 0:
         n_gpus = world
-        value = shard.aggregate_throughput(B, args.steps, n_gpus, total_ms)
-        e2e_value = shard.aggregate_throughput(B, args.steps, n_gpus, e2e_ms)
+        value = shard.aggregate_throughput(B, args.steps, n_gpus, total_ms_max)
+        e2e_values = {t: shard.aggregate_throughput(B, e2e_steps, n_gpus, e2e_ms_max[t]) for t in e2e_ms_max}
         peaks, peak_src = measured_peaks()
         trunk_s = trunk_ns * 1e-9 / args.steps
         achieved = TRUNK_FLOPS * B / trunk_s / 1e12 if trunk_s > 0 else 0.0
         peak_burst = float(peaks["bf16_tflops"])
-        peak = float(peaks.get("bf16_tflops_sustained", peak_burst))
-        traffic = None
+        peak_sustained = float(peaks.get("bf16_tflops_sustained", peak_burst))
+        # which peak the kernel is held against follows from THIS run's own record: the sustained figure only when the timed
+        # region lasted at least a second and the clock samples show the power cap; otherwise the burst figure
+        capped = bool(clocks and "sw_power_cap" in (clocks.get("reasons") or []))
+        sustained = capped and total_ms_max >= 1000.0
+        peak = peak_sustained if sustained else peak_burst
+        traffic, traffic_note = None, "no ncu capture on record"
         try:
             with open(os.path.join(ROOT, "profiles", "trunk_traffic.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                tj = json.load(f)
+            if tj.get("kernel_source_sha16") == kernel_source_sha() and tj.get("mode", list(prec)) == list(prec):
+                traffic, traffic_note = tj.get("dram_bytes_per_launch"), tj.get("source", "profiles/trunk_traffic.json")
+            else:
+                traffic_note = "profiles/trunk_traffic.json was captured from other kernel sources or another precision mode: dropped"
         except OSError:
             pass
+        flops_pos = netdefs.POLICY_FLOPS + netdefs.VALUE_FLOPS
+        names = {0: "f16", 1: "f16 + e4m3 correction terms", 2: "f16 hi+lo split operands (3 terms)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f16 hi+lo split operands (3 MMA terms), f32 accumulation" if args.precise else "f16", "data": "synthetic",
-            "config": {"workload": "policy NN128 + value NNValue, batch 256 positions per GPU per step "
-                                   "(BASELINE.json configs[1] shape, policy+value as the metric names)",
+            "warmup": warm, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": f"policy {names[prec[0]]}, value {names[prec[1]]}; f32 accumulation", "data": "synthetic",
+            "config": {"workload": WORKLOAD,
                        "batch_per_gpu": B, "global_batch": B * n_gpus, "parallelism": f"replicas x{n_gpus}, positions sharded",
                        "weights": "synthetic U(+-sqrt(6/fan_in)), seed 20260001, policy gain 2 (in-repo weights missing)",
                        "positions": f"Leela Playout self-play, {n_pos} distinct, {n_sets} different batches cycled",
                        "l2": "flushed between steps (256 MB write)" if args.flush_l2 else
                              f"inputs larger than L2: {n_sets} input batches = {n_sets * set_bytes / 2**20:.0f} MB, one per step; weights + workspace stay warm",
-                       "trunk_mode": ev.get_option("trunk_mode"), "cta_pair": ev.get_option("cta_pair"), "precise": ev.get_option("precise"), "flops_per_position": netdefs.POLICY_FLOPS + netdefs.VALUE_FLOPS,
-                       "pct_of_bf16_sustained_peak_whole_step": 100.0 * (netdefs.POLICY_FLOPS + netdefs.VALUE_FLOPS) * value / n_gpus / (peak * 1e12),
-                       "pct_of_bf16_burst_peak_whole_step": 100.0 * (netdefs.POLICY_FLOPS + netdefs.VALUE_FLOPS) * value / n_gpus / (peak_burst * 1e12)},
+                       "precision": {"policy": prec[0], "value": prec[1], "legend": "0 fp16 operands, 1 lite (fp16 + e4m3 corrections), 2 full split operands"},
+                       "parity": parity,
+                       "cuda_graphs": {"enabled": bool(ev.get_option("use_graphs")), "graph_launches_in_timed_region": graph_launches},
+                       "flops_per_position": flops_pos,
+                       "pct_of_bf16_burst_peak_whole_step": 100.0 * flops_pos * value / n_gpus / (peak_burst * 1e12),
+                       "pct_of_bf16_sustained_peak_whole_step": 100.0 * flops_pos * value / n_gpus / (peak_sustained * 1e12),
+                       "timed_region_s": total_ms_max * 1e-3, "timed_region_wall_s": timed_wall_s},
             "roofline": {"bound": "tensor", "kernel": "trunk_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": f"{peak_src} sustained cuBLAS bf16 under the power cap (MEASURED_PEAKS.json bf16_tflops_sustained): "
-                                        "the kernel is timed inside a long back-to-back run with sw_power_cap active",
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note,
+                         "peak_source": (f"{peak_src} cuBLAS bf16 {'sustained under the power cap' if sustained else 'burst'} "
+                                         f"(MEASURED_PEAKS.json): timed region {total_ms_max * 1e-3:.3f} s, sw_power_cap "
+                                         f"{'seen' if capped else 'not seen'} in this run's clock samples"),
                          "peak_burst": peak_burst, "frac_of_burst": achieved / peak_burst,
-                         "flops_per_launch": TRUNK_FLOPS * B, "launch_ms": trunk_s * 1e3},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (2 * 1444 + 1),
-                    "d2h_bytes_per_step": B * (1444 + 4), "timing": f"host clock around {n_host} host thread(s) each making blocking C-ABI calls", "host_threads": n_host, "checksum": checksum},
+                         "peak_sustained": peak_sustained, "frac_of_sustained": achieved / peak_sustained,
+                         "flops_per_launch": TRUNK_FLOPS * B, "launch_ms": trunk_s * 1e3,
+                         "flops_note": "algorithmic (dense im2col-GEMM count of the reference); the correction terms of the "
+                                       "split-operand modes are extra tensor work and are not counted"},
+            "e2e": {"value": e2e_values[n_main], "unit": UNIT, "h2d_bytes_per_step": B * (2 * 1444 + 1),
+                    "d2h_bytes_per_step": B * (1444 + 4), "host_threads": n_main, "steps": e2e_steps,
+                    "timing": f"host clock from the release of {n_main} persistent, warmed-up caller thread(s) to the last result; "
+                              f"{k} x steps = {e2e_steps} blocking lb2_eval_both calls on pinned host buffers",
+                    "one_thread": e2e_values.get(1), "checksum": e2e[n_main][1],
+                    "per_rank_min": float(B * e2e_steps / (table[:, 1 + sorted(e2e).index(n_main)].max() * 1e-3)),
+                    "per_rank_max": float(B * e2e_steps / (table[:, 1 + sorted(e2e).index(n_main)].min() * 1e-3))},
             "gpu_launches": launches, "clocks": clocks,
         }
+        if in_process:
+            line["config"]["in_process_e2e"] = in_process
         if n_gpus == 1 and not args.no_cpu:
             v, info = cpu_reference(min(B, 256), 1, 8)
             info["value"] = v
@@ -364,9 +479,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--engine", action="store_true", help="engine-level benchmark instead: GTP genmove / netbench, ours vs the reference's CPU engine")
     ap.add_argument("--flush-l2", action="store_true", help="evict L2 before every step instead of cycling an input pool larger than L2")
-    ap.add_argument("--overlap-io", action="store_true", help="A/B: expand/heads kernels of host-buffer calls on the I/O slot's stream")
-    ap.add_argument("--precise", action="store_true", help="split-operand mode (lb2_set_option precise=1): results within 1e-4 of the fp32 reference, "
-                    "3x the tensor work; the roofline still counts the ALGORITHMIC flops")
+    ap.add_argument("--policy-precision", type=int, default=None, choices=[0, 1, 2], help="0 fp16 operands, 1 lite (fp16 + e4m3 corrections), "
+                    "2 full split operands; default: the library's (policy 0, value 1)")
+    ap.add_argument("--value-precision", type=int, default=None, choices=[0, 1, 2])
+    ap.add_argument("--precise", action="store_true", help="both nets in full split-operand precision (2, 2): 3x the tensor work; the roofline "
+                    "still counts the ALGORITHMIC flops")
+    ap.add_argument("--no-graphs", action="store_true", help="A/B: separate kernel launches instead of one CUDA graph per evaluation")
     ap.add_argument("--e2e-threads", type=int, default=2, help="host threads calling the C ABI concurrently in the e2e leg")
     args = ap.parse_args()
     if args.engine:
@@ -378,7 +496,10 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__), "--gpus", str(args.gpus),
                "--steps", str(args.steps), "--warmup", str(args.warmup), "--batch", str(args.batch),
-               "--e2e-threads", str(args.e2e_threads)] + (["--flush-l2"] if args.flush_l2 else []) + (["--no-cpu"] if args.no_cpu else [])
+               "--e2e-threads", str(args.e2e_threads)] + (["--flush-l2"] if args.flush_l2 else []) + (["--no-cpu"] if args.no_cpu else []) + \
+              (["--precise"] if args.precise else []) + (["--no-graphs"] if args.no_graphs else []) + \
+              (["--policy-precision", str(args.policy_precision)] if args.policy_precision is not None else []) + \
+              (["--value-precision", str(args.value_precision)] if args.value_precision is not None else [])
         return subprocess.call(cmd)
     return run_ours(args)
 

@@ -242,17 +242,22 @@ struct Waiter {
     std::condition_variable cv;
     bool done = false;
     int status = 0;
+    std::string text;   // the failure's text: lb2_last_error() is per thread, and the callback runs on the dispatcher's
     static void signal(void* user, int status) {
         Waiter* w = static_cast<Waiter*>(user);
         std::lock_guard<std::mutex> lk(w->mu);
         w->status = status;
+        if (status) w->text = lb2_last_error();
         w->done = true;
         w->cv.notify_one();
     }
     void wait(const char* what) {
         std::unique_lock<std::mutex> lk(mu);
         cv.wait(lk, [&] { return done; });
-        if (status) die(what);
+        if (status) {
+            myprintf("leela_b200: %s failed: %s\n", what, text.c_str());
+            throw std::runtime_error(std::string("leela_b200: ") + what + ": " + text);
+        }
     }
 };
 

@@ -28,6 +28,7 @@
 #ifndef LEELA_B200_H
 #define LEELA_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -52,8 +53,10 @@ typedef struct lb2_ctx lb2_ctx;
 typedef struct lb2_net lb2_net;
 
 /* Replaces OpenCL::initialize (OpenCL.cpp:764-908). device_ids == NULL or n_devices == 0
- * selects CUDA device 0. With several devices, weights are replicated on each and every
- * eval call shards its positions over them in contiguous slices (no collective). */
+ * selects CUDA device 0. With several devices, weights are replicated on each; a call of up to
+ * max_batch positions runs as ONE batch on whichever device has a free I/O slot, larger calls
+ * are cut into max_batch chunks that are dealt to the devices as they become free (no collective,
+ * and never slivers of one batch on every device). */
 int lb2_init(const int* device_ids, int n_devices, lb2_ctx** ctx_out);
 void lb2_destroy(lb2_ctx* ctx);
 
@@ -107,15 +110,28 @@ int lb2_eval_both_device(lb2_ctx* ctx, int dev_index, const uint32_t* d_policy_p
                          void* cuda_stream);
 
 /* Asynchronous submission from many search threads; replaces forward(cb) +
- * thread_can_issue / join_outstanding_cb (OpenCL.cpp:446-454, 560-577). Requests are
- * coalesced into device batches by two worker threads (one batch's copies overlap the other's kernels); cb(user, status) runs on such a thread once
- * the caller's output buffer is filled. Input buffers are copied before the call returns. */
+ * thread_can_issue / join_outstanding_cb (OpenCL.cpp:446-454, 560-577). A request's planes are
+ * copied straight into the pinned buffer of the batch that is filling up (so the input buffers are
+ * free again when the call returns); two dispatcher threads per device take whatever has accumulated
+ * as soon as they are free — the batch size follows the load — and run it as one device batch;
+ * cb(user, status) runs on such a thread once the caller's output buffer is filled. When status is
+ * not LB2_OK, lb2_last_error() inside the callback (or lb2_queue_error later, from any thread) gives
+ * the text. */
 typedef void (*lb2_callback)(void* user, int status);
 int lb2_submit_policy(lb2_ctx* ctx, const uint32_t* planes, const uint8_t* rotation, int n,
                       float softmax_temp, float* probs_out, lb2_callback cb, void* user);
 int lb2_submit_value(lb2_ctx* ctx, const uint32_t* planes, const uint8_t* rotation, int n,
                      float* winrate_out, lb2_callback cb, void* user);
 int lb2_drain(lb2_ctx* ctx);
+/* Text of the most recent asynchronous failure (empty if none), copied into buf. */
+int lb2_queue_error(lb2_ctx* ctx, char* buf, int len);
+
+/* Optional: page-lock a caller buffer (cudaHostRegister) so that lb2_eval_* copy to / from it directly
+ * instead of through the library's pinned staging; a buffer that is already page-locked (cudaMallocHost,
+ * another library) is only remembered. Unregistered pointers are still recognised as pinned or pageable —
+ * one cudaPointerGetAttributes the first time an address is seen — so this is about skipping even that. */
+int lb2_register_host_buffer(lb2_ctx* ctx, void* ptr, size_t bytes);
+int lb2_unregister_host_buffer(lb2_ctx* ctx, void* ptr);
 
 /* Feature planes from a RAW position — replaces Network::gather_features_policy / _value
  * (Network.cpp:883-1201) together with the FastBoard queries they make (liberties, liberties after a
@@ -155,21 +171,30 @@ int lb2_device_count(lb2_ctx* ctx);
  *   "resident_weights": each CTA keeps its half of a layer's packed weights in shared memory for all the layer's items
  *                 it processes, the clusters are split between the two nets (by estimated work; each helps the other
  *                 out when its own net runs dry) and the pipeline stages carry activation slabs only. 0 = off, 1 = whenever
- *                 every layer fits (c_in, c_out <= 128, not in precise mode), 2 = only for launches that run both nets
- *                 (default: 4 % faster there, no gain for one net alone). Bit-identical to the streaming form.
- *   "precise":    1 = split-operand mode: activations and weights are carried as fp16 hi + fp16 lo and every layer
- *                 accumulates three tensor-core terms (hi*Wh + hi*Wl + lo*Wh) in fp32. Results lie within 1e-4 of the
- *                 reference's fp32 OpenBLAS path (measured max 8.9e-5 policy, 2.8e-5 value over the 1024-position
- *                 correctness set, top-1 identical in all) at about 0.38x the throughput of the default, whose fp16
- *                 operands give max 5.3e-3 / 3.0e-3. Default 0. May be switched between calls.
+ *                 every layer fits (no column splits; policy layers only in fp16 precision), 2 = only for launches that run
+ *                 both nets (default: 4 % faster there, no gain for one net alone). Bit-identical to the streaming form.
+ *   "policy_precision", "value_precision": arithmetic of a net's conv stack (accumulation, epilogue and heads are always fp32):
+ *                 0 = fp16 operands, one tensor-core term per layer. Measured against the reference's fp32 OpenBLAS path over
+ *                     the 1024-position correctness set: policy max |dp| 5.3e-3, value max 3.3e-3.
+ *                 1 = "lite" split operands: the fp16 term plus ONE e4m3 (kind::f8f6f4, K = 32) correction term per 16
+ *                     channels, [e4m3(a) | e4m3((a - fp16(a)) 2^12)] x [e4m3(w - fp16(w)) ; e4m3(w)], scaled by powers of two
+ *                     into e4m3's range and accumulated in the same fp32 accumulator: twice the tensor work, value max 1.3e-4.
+ *                 2 = "full" split operands: fp16 hi + fp16 lo for activations and weights, three fp16 terms (hi*Wh + hi*Wl +
+ *                     lo*Wh): three times the tensor work, policy max 8.9e-5, value max 2.8e-5.
+ *                 Default: policy 0, value 1 (north_star: value within 1e-3; the policy tolerance is stated from measurement).
+ *                 Lite and full cannot be mixed between the two nets. May be switched between calls.
+ *   "precise":    shorthand: 1 = both nets full (2, 2); 0 = the default (0, 1).
  *   "policy_clusters": resident mode: clusters that start on the policy net (-1 = split by estimated work)
- *   "overlap_io": 1 = host-buffer calls run their expand / heads kernels on the I/O slot's stream, beside the
- *                 trunk kernel of another call in flight; 0 = on the compute stream (default: measured faster)
+ *   "use_graphs": 1 = from the second use of a batch shape on, its kernels (expand, trunk, heads) are launched as one
+ *                 cached CUDA graph (default); 0 = always as separate launches
+ *   "spin_wait":  1 = a blocking call polls for its results, yielding the core between polls (default); 0 = it sleeps
+ *                 on a blocking-sync event (frees the core, adds wake-up latency)
  *   "max_batch":  positions per device pass (larger calls are chunked), default 256
- *   "profile_trunk": 1 = bracket every trunk launch with CUDA events; lb2_get_option("trunk_ns")
- *                 then returns the device nanoseconds accumulated since the last query
+ *   "profile_trunk": 1 = bracket every trunk launch with CUDA events (nodes of the graph when graphs are on);
+ *                 lb2_get_option("trunk_ns") then returns the device nanoseconds accumulated since the last query.
+ *                 "profile_reserve" = N creates N event pairs per device ahead of time (none is then created inside a timed loop)
  *   read-only: "stat_positions", "stat_batches", "stat_requests" = positions, device batches and
- *                 requests that went through lb2_submit_* so far (mean batch = positions / batches) */
+ *                 requests that went through lb2_submit_* so far (mean batch = positions / batches); "graph_launches" */
 int lb2_set_option(lb2_ctx* ctx, const char* name, long value);
 long lb2_get_option(lb2_ctx* ctx, const char* name);
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */

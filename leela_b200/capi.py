@@ -23,6 +23,7 @@ EXPORTS = [
     "lb2_eval_policy", "lb2_eval_value", "lb2_eval_both", "lb2_eval_ensemble", "lb2_eval_both_device", "lb2_submit_policy",
     "lb2_submit_value", "lb2_drain", "lb2_backend_name", "lb2_last_error", "lb2_device_count", "lb2_set_option",
     "lb2_get_option", "lb2_launch_count", "lb2_debug_trunk", "lb2_debug_read_trace", "lb2_planes_from_position", "lb2_eval_positions",
+    "lb2_queue_error", "lb2_register_host_buffer", "lb2_unregister_host_buffer",
 ]
 
 CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_int)
@@ -69,6 +70,9 @@ def load():
     L.lb2_launch_count.argtypes = [vp]; L.lb2_launch_count.restype = C.c_long
     L.lb2_debug_trunk.argtypes = [vp, ip, vp, vp, ip, ip, vp]
     L.lb2_debug_read_trace.argtypes = [vp, vp, C.c_long]
+    L.lb2_queue_error.argtypes = [vp, C.c_char_p, ip]
+    L.lb2_register_host_buffer.argtypes = [vp, vp, C.c_size_t]
+    L.lb2_unregister_host_buffer.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -223,6 +227,13 @@ class Evaluator:
 
     def get_option(self, name):
         return int(self._L.lb2_get_option(self.ctx, name.encode()))
+
+    def set_precision(self, policy, value):
+        """Trunk precision of the two nets: 0 fp16 operands, 1 lite (fp16 + e4m3 corrections), 2 full split operands.
+        (Lite and full cannot be mixed between the nets: go through fp16 so that no intermediate state is rejected.)"""
+        self.set_option("policy_precision", 0)
+        self.set_option("value_precision", value)
+        self.set_option("policy_precision", policy)
 
     @property
     def launch_count(self):

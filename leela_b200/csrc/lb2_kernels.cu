@@ -11,6 +11,9 @@
 //                         (Network.cpp:806-808, 450-469, 820-823)
 //   value_head_kernel     last conv (C -> 1) + ELU + ip 361->H + ELU + ip H->1 + (1+tanh)/2
 //                         (Network.cpp:731-737, 395-423; OpenCL innerproduct OpenCL.cpp:407-438)
+#include <cuda_fp8.h>
+#include <cstdio>
+
 #include "lb2_kernels.cuh"
 #include "lb2_ptx.cuh"
 
@@ -50,8 +53,19 @@ constexpr int kEpiGroup = LB2_EPI_GROUP;
 #ifndef LB2_CONSUMER_PROXY_FENCE
 #define LB2_CONSUMER_PROXY_FENCE 1   // producer: fence.proxy.async (MEMBAR.ALL.GPU) between seeing an item's dependencies and its TMA loads
 #endif
+// LB2_LITE_SEPARATE_ACC (default 0, lb2_kernels.cuh): lite mode: 1 = the e4m3 correction terms accumulate in TMEM columns of their own (kCorrCols to the right,
+                                  // c_out <= 64 only) and the epilogue adds the two sums; 0 = straight onto the fp16 sum. kind::f8f6f4
+                                  // adds an addend 2^-24 of the accumulator exactly (tools/mma_mixed_test.cu) and the results are
+                                  // the same either way (value max 9.3e-5), so: 0
 #ifndef LB2_EPI_PIPE
 #define LB2_EPI_PIPE 1    // epilogue keeps the TMEM loads of the next two units in flight
+#endif
+
+// timing experiments (results are wrong under them) exist only in builds with -DLB2_DEBUG_KNOBS
+#ifdef LB2_DEBUG_KNOBS
+#define kDebugFlags(P) ((P).debug_flags)
+#else
+#define kDebugFlags(P) 0
 #endif
 
 // Network::rotate_nn_idx (Network.cpp:1348-1379): bit2 swaps x/y first, bit0 flips y, bit1 flips x.
@@ -77,6 +91,13 @@ __device__ __forceinline__ float elu1(float v) { return v > 0.0f ? v : (__expf(v
 __global__ void __launch_bounds__(256) expand_planes_kernel(const ExpandArgs A) {
     if (LB2_PDL) grid_dep_launch();   // the trunk may set itself up while we run; it waits for us before reading
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0 && A.sched) {
+        // start of an evaluation: new flag epoch, work-item claim counters back to zero. Everything that used the old values
+        // precedes this kernel in its stream; the trunk launch(es) of this evaluation follow it. Keeping this state on the
+        // device makes a launch sequence independent of its history, i.e. replayable from a CUDA graph.
+        A.sched[kSchedEpoch] += 1u;
+        A.sched[0] = A.sched[1] = A.sched[2] = 0u;
+    }
     const size_t per_net = (size_t)A.n * 441;
     const size_t total = per_net * A.n_nets;
     if (t >= total) {
@@ -153,6 +174,13 @@ __device__ __forceinline__ unsigned long long global_ns() {
             P.trace[((size_t)blockIdx.x * kTraceItems + (it)) * kTraceEvents + (e)] = global_ns();   \
     } while (0)
 
+// two floats -> two e4m3 (round to nearest even, saturating at +-448) in the low 16 bits: lo = first, hi = second
+__device__ __forceinline__ uint32_t cvt_e4m3x2(float first, float second) {
+    uint16_t r;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(second), "f"(first));
+    return (uint32_t)r;
+}
+
 // ELU(alpha = 1): v > 0 ? v : exp(v) - 1, written branch-free as max(v, min(exp(v) - 1, 0)).
 __device__ __forceinline__ float elu_fast(float v) {
     float e;
@@ -223,22 +251,23 @@ __device__ __forceinline__ bool item_get(const uint32_t* ring, uint32_t k, int& 
 }
 
 // The MMA issuer's own ring: everything it needs to know about item k in one word
-// [tag:5 | end:1 | 5x5:1 | halo/8:4 | c_in/16:6 | c_out/8:6 | S:8], so that a single shared-memory
-// load separates the last MMA of one item from the first of the next.
+// [tag:5 | end:1 | 5x5:1 | halo/8:4 | virtual slabs:6 | c_out/8:6 | S == 21:1 | kind::f16 slabs:7], so that a single
+// shared-memory load separates the last MMA of one item from the first of the next.
 __device__ __forceinline__ uint32_t geom_pack(uint32_t k, const LayerJob* J) {
     if (!J) return (item_tag(k) << 27) | (1u << 25);
     return (item_tag(k) << 27) | ((J->ksize == 5 ? 1u : 0u) << 24) | ((uint32_t)(J->halo >> 3) << 20) |
-           ((uint32_t)J->n_slabs << 14) | ((uint32_t)(J->n_out >> 3) << 8) | (uint32_t)J->S;
+           ((uint32_t)J->n_slabs << 14) | ((uint32_t)(J->n_out >> 3) << 8) | ((J->S == 21 ? 1u : 0u) << 7) | (uint32_t)J->n_f16_slabs;
 }
 
 // kRes (pairs only): resident-weights mode, see lb2_kernels.cuh. Shared memory:
 //   streaming:  [stages: A slab + B block][ctrl][bias][head weights][job table]
 //   resident:   [this CTA's half of the layer's weights][stages: A slab only][ctrl][bias][head weights][job table]
-// kPrecise: split-operand mode (LayerJob::lo_chunks != 0 for every job): the epilogue also stores the fp16 residual.
-template <bool kPair, bool kRes, bool kPrecise>
+// kOutModes: which LayerJob::out_mode values besides kOutPlain may occur in the launch (bit kOutLo16 - 1: precise, bit
+// kOutFp8 - 1: lite) — the epilogue's extra stores are compiled in only where a launch can need them.
+template <bool kPair, bool kRes, int kOutModes>
 __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_constant__ TrunkParams P) {
     static_assert(!kRes || kPair, "resident weights need CTA pairs");
-    static_assert(!kRes || !kPrecise, "resident weights hold one fp16 image of a layer");
+    constexpr bool kLo16 = (kOutModes & 1) != 0, kFp8 = (kOutModes & 2) != 0;
     constexpr int kStages = kRes ? kStagesRes : (kPair ? kStagesPair : kStagesSingle);
     constexpr int kStageBytes = kRes ? kASlabBytes : (kPair ? kStageBytesPair : kStageBytesSingle);
     constexpr int kRingOff = kRes ? kResWeightBytes : 0;
@@ -313,6 +342,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         grid_dep_launch();
     }
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t epoch = P.sched[kSchedEpoch];   // set by the expand kernel in front of this launch
     jobs = jobs_s;  // from here on every role reads the shared-memory copy
     if (P.trace && threadIdx.x == 0) {  // effective SM clock: cycle and wall timestamps at both ends
         unsigned long long* t = P.trace + ((size_t)blockIdx.x * kTraceItems + (kTraceItems - 1)) * kTraceEvents;
@@ -330,6 +360,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             const LayerJob& J = jobs[jj];
             const int tile = tile_of(idx);
             const int halo = J.halo, ksize = J.ksize, n_out = J.n_out, n_slabs = J.n_slabs, tmap = J.tmap, n_real = J.n_real_slabs;
+            const int tb0 = J.term_base[0], tb1 = J.term_base[1], tb2 = J.term_base[2];
             if (lane == 0) { LB2_TRACE(pit, 0); if (P.trace && pit < (uint32_t)kTraceItems) P.trace[((size_t)blockIdx.x * kTraceItems + pit) * kTraceEvents + 15] = (unsigned long long)((jj << 21) | idx); }
             // the scout warp polls the dependency flags ahead of us; wait for its go-ahead
             while (ld_acquire_cta_shared(deps_ready) <= pit) {}
@@ -362,16 +393,17 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                     }
                 }
                 uint32_t unit_off = 0;   // kRes: byte offset of the stage's weights inside the resident area
+                int term = 0, ts = 0;    // virtual slab s = term * n_real + ts
                 for (int s = 0; s < n_slabs; s++) {
                     for (int g = 0; g < ng; g++) {
                         const uint32_t b_bytes = (tap_group_end(ksize, g) - tap_group_begin(g)) * n_mine * 32;
                         mbar_wait(empty_bar + st, ph ^ 1);
                         uint8_t* sa = ring + st * kStageBytes;
-                        const bool skip_b = (P.debug_flags & 8) != 0 || (kRes && !reload), skip_a = (P.debug_flags & 16) != 0;
+                        const bool skip_b = (kDebugFlags(P) & 8) != 0 || (kRes && !reload), skip_a = (kDebugFlags(P) & 16) != 0;
                         mbar_arrive_expect_tx(full_bar + st, (skip_a ? 0u : a_bytes) + (skip_b ? 0u : b_bytes));
                         if (!skip_a) {
-                            // precise mode: virtual slabs [0, n) and [n, 2n) read the hi planes, [2n, 3n) the lo planes behind them
-                            const int ac = kPrecise ? 2 * (s < n_real ? s : s - n_real) : 2 * s;
+                            // split-operand modes: every term of the K loop has its own set of input chunk planes
+                            const int ac = (term == 0 ? tb0 : (term == 1 ? tb1 : tb2)) + 2 * ts;
                             if (LB2_L2_HINTS >= 2) tma_load_3d_hint(sa, &P.tmaps[tmap], full_bar + st, 0, row0_8, ac, ld_policy);
                             else tma_load_3d(sa, &P.tmaps[tmap], full_bar + st, 0, row0_8, ac);
                         }
@@ -381,6 +413,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                         if (++st == kStages) { st = 0; ph ^= 1; }
                         if (s == 0 && g == 0) LB2_TRACE(pit, 2);
                     }
+                    if (++ts == n_real) { ts = 0; term++; }
                 }
                 LB2_TRACE(pit, 3);
             }
@@ -423,7 +456,8 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                 if (gw & (1u << 25)) break;
                 const int ksize = (gw & (1u << 24)) ? 5 : 3, halo = (int)((gw >> 20) & 15u) << 3;
                 const int n_slabs = (int)((gw >> 14) & 63u), n_out = (int)((gw >> 8) & 63u) << 3;
-                const int S = (P.debug_flags & 2) ? 0 : (int)(gw & 255u), DX = (P.debug_flags & 2) ? 0 : 1;
+                const int S = (kDebugFlags(P) & 2) ? 0 : ((gw & 128u) ? 21 : 20), DX = (kDebugFlags(P) & 2) ? 0 : 1;
+                const int n_f16 = (int)(gw & 127u);   // 3x3 layers: slabs from this one on are e4m3 (K = 32) MMAs
                 const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
                 LB2_TRACE(it, 4);
                 mbar_wait(tempty_bar + acc, acc_phase ^ 1);
@@ -457,14 +491,30 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                     // B: behind the A slab of the stage, or (kRes) this stage's unit of the resident weights
                     uint32_t b16 = kRes ? (smem_u32(smem) >> 4) + res16 : (a_addr + kASlabBytes) >> 4;
                     if (kRes) res16 += (uint32_t)(ksize == 3 ? 9 : tap_group_end(ksize, g) - tap_group_begin(g)) * b_step;
-                    if (ksize == 3) {
+                    if (ksize == 3 && kFp8 && s >= n_f16) {
+                        // lite mode's correction slab: same operand geometry in bytes (16-byte rows = 16 e4m3 channels),
+                        // K = 32 = [a8 | lo8] against [Wl8 ; W8], onto the fp16 sum in the same fp32 accumulator (or, see
+                        // LB2_LITE_SEPARATE_ACC, into columns of its own)
+                        const uint32_t acc_c = (!LB2_LITE_SEPARATE_ACC || s > n_f16) ? 1u : 0u;
+                        constexpr uint32_t kCorr = LB2_LITE_SEPARATE_ACC ? kCorrCols : 0;
+#pragma unroll
+                        for (int t = 0; t < 9; t++) {
+                            const int off = (t / 3 - 1) * S + (t % 3 - 1) * DX;
+                            const uint64_t bdesc = desc_hi | (b_lo_base | (b16 & 0x3FFFu));
+                            const uint32_t a0 = a16 + off;
+                            umma_f8<kPair>(d0 + kCorr, desc_hi | (a_lo_base | (a0 & 0x3FFFu)), bdesc, idesc, t ? 1u : acc_c);
+                            umma_f8<kPair>(d1 + kCorr, desc_hi | (a_lo_base | ((a0 + 128) & 0x3FFFu)), bdesc, idesc, t ? 1u : acc_c);
+                            b16 += b_step;
+                            if (t == LB2_PROBE_TAP) next_ready = mbar_test_wait(full_bar + nstage, nphase);
+                        }
+                    } else if (ksize == 3) {
 #pragma unroll
                         for (int t = 0; t < 9; t++) {
                             const int off = (t / 3 - 1) * S + (t % 3 - 1) * DX;
                             const uint64_t bdesc = desc_hi | (b_lo_base | (b16 & 0x3FFFu));
                             const uint32_t a0 = a16 + off;
                             umma_f16<kPair>(d0, desc_hi | (a_lo_base | (a0 & 0x3FFFu)), bdesc, idesc, accumulate);
-                            if (!(P.debug_flags & 32))
+                            if (!(kDebugFlags(P) & 32))
                                 umma_f16<kPair>(d1, desc_hi | (a_lo_base | ((a0 + 128) & 0x3FFFu)), bdesc, idesc, accumulate);
                             accumulate = 1;
                             b16 += b_step;
@@ -510,7 +560,12 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         for (int jj, idx; item_get(item_ring, it, jj, idx); it++) {
             const LayerJob& J = jobs[jj];
             const int tile = tile_of(idx);
-            const int n_out = J.n_out, chunk_rows = J.out_chunk_rows, n_pos = J.n_pos, lo_chunks = kPrecise ? J.lo_chunks : 0;
+            const int n_out = J.n_out, chunk_rows = J.out_chunk_rows, n_pos = J.n_pos, lo_chunks = kOutModes ? J.lo_chunks : 0;
+            const int out_mode = kOutModes ? J.out_mode : kOutPlain;
+            const float sc = kOutModes ? J.acc_scale : 1.0f;   // packed weights of the split-operand modes carry a power-of-two scale
+            // lite jobs: the e4m3 correction terms sit in an accumulator of their own, kCorrCols columns to the right
+            const bool has_corr = LB2_LITE_SEPARATE_ACC && kFp8 && J.n_f16_slabs < J.n_slabs;
+
             const bool head = J.head_taps != 0, remap = J.remap != 0, wide = (J.S == 21);
             __half* __restrict__ out = J.out;
             float* __restrict__ zbuf = J.zbuf;
@@ -520,7 +575,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             const int cols = n_out / kColParts;   // columns handled by this warp
             const int col0 = part * cols;
             const int upc = cols >> 3;            // 8-column units per 128-row half tile
-            const int n_units = (P.debug_flags & 64) ? 0 : 2 * upc;
+            const int n_units = (kDebugFlags(P) & 64) ? 0 : 2 * upc;
             // this thread's row in each of the two half tiles
             int out_row2[2]; bool valid2[2];
 #pragma unroll
@@ -540,24 +595,31 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             auto unit_addr2 = [&](int u) { return tbase + unit_half(u) * 128 + unit_col(u); };
 
             // bias + ELU of one unit
-            auto activate_b = [&](const uint32_t (&r)[8], const float4& b0, const float4& b1, float (&v)[8]) {
-                v[0] = __uint_as_float(r[0]) + b0.x; v[1] = __uint_as_float(r[1]) + b0.y;
-                v[2] = __uint_as_float(r[2]) + b0.z; v[3] = __uint_as_float(r[3]) + b0.w;
-                v[4] = __uint_as_float(r[4]) + b1.x; v[5] = __uint_as_float(r[5]) + b1.y;
-                v[6] = __uint_as_float(r[6]) + b1.z; v[7] = __uint_as_float(r[7]) + b1.w;
-                if (!(P.debug_flags & 4)) {
+            auto activate_b = [&](const uint32_t (&r)[8], uint32_t taddr, const float4& b0, const float4& b1, float (&v)[8]) {
+                if (kOutModes) {   // x * 1 + b rounds exactly like x + b: plain jobs of such a launch stay bit-identical
+                    float a[8];
 #pragma unroll
-                    for (int e = 0; e < 8; e++) v[e] = elu_fast(v[e]);
+                    for (int e = 0; e < 8; e++) a[e] = __uint_as_float(r[e]);
+                    if (has_corr) {   // (the wait also covers the caller's loads in flight: harmless)
+                        uint32_t c[8];
+                        tmem_ld_32x8(taddr + kCorrCols, c);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 8; e++) a[e] += __uint_as_float(c[e]);
+#ifdef LB2_DEBUG_KNOBS
+                        if ((kDebugFlags(P) & 128) && blockIdx.x == 0 && warp == 2 && lane == 5 && it < 40)
+                            printf("it %u job %d: main %g corr %g sc %g n_f16 %d n_slabs %d\n", it, jj, __uint_as_float(r[0]), __uint_as_float(c[0]), sc, (int)J.n_f16_slabs, J.n_slabs);
+#endif
+                    }
+                    v[0] = fmaf(a[0], sc, b0.x); v[1] = fmaf(a[1], sc, b0.y); v[2] = fmaf(a[2], sc, b0.z); v[3] = fmaf(a[3], sc, b0.w);
+                    v[4] = fmaf(a[4], sc, b1.x); v[5] = fmaf(a[5], sc, b1.y); v[6] = fmaf(a[6], sc, b1.z); v[7] = fmaf(a[7], sc, b1.w);
+                } else {
+                    v[0] = __uint_as_float(r[0]) + b0.x; v[1] = __uint_as_float(r[1]) + b0.y;
+                    v[2] = __uint_as_float(r[2]) + b0.z; v[3] = __uint_as_float(r[3]) + b0.w;
+                    v[4] = __uint_as_float(r[4]) + b1.x; v[5] = __uint_as_float(r[5]) + b1.y;
+                    v[6] = __uint_as_float(r[6]) + b1.z; v[7] = __uint_as_float(r[7]) + b1.w;
                 }
-            };
-            auto activate = [&](const uint32_t (&r)[8], int cc, float (&v)[8]) {
-                const float* bp = bs + col0 + cc;
-                const float4 b0 = *reinterpret_cast<const float4*>(bp), b1 = *reinterpret_cast<const float4*>(bp + 4);
-                v[0] = __uint_as_float(r[0]) + b0.x; v[1] = __uint_as_float(r[1]) + b0.y;
-                v[2] = __uint_as_float(r[2]) + b0.z; v[3] = __uint_as_float(r[3]) + b0.w;
-                v[4] = __uint_as_float(r[4]) + b1.x; v[5] = __uint_as_float(r[5]) + b1.y;
-                v[6] = __uint_as_float(r[6]) + b1.z; v[7] = __uint_as_float(r[7]) + b1.w;
-                if (!(P.debug_flags & 4)) {
+                if (!(kDebugFlags(P) & 4)) {
 #pragma unroll
                     for (int e = 0; e < 8; e++) v[e] = elu_fast(v[e]);
                 }
@@ -571,21 +633,21 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                 const bool valid = h ? valid2[1] : valid2[0];
                 const int out_row = h ? out_row2[1] : out_row2[0];
                 float v[8];
-                activate_b(r, b0, b1, v);
+                activate_b(r, unit_addr2(u), b0, b1, v);
                 if (valid || !remap) {
                     uint32_t pk[4], pl[4];
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
                         __half2 hh = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
                         pk[e] = valid ? *reinterpret_cast<uint32_t*>(&hh) : 0u;
-                        if (kPrecise) {   // what the fp16 rounding dropped, as a second fp16
+                        if (kLo16 && out_mode == kOutLo16) {   // what the fp16 rounding dropped, as a second fp16
                             const float2 hf = __half22float2(hh);
                             __half2 ll = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
                             pl[e] = valid ? *reinterpret_cast<uint32_t*>(&ll) : 0u;
                         }
                     }
                     const int c8 = (col0 + cc) >> 3;
-                    if (kPrecise) {
+                    if (kLo16 && out_mode == kOutLo16) {
                         __half* lo = out + ((size_t)(lo_chunks + c8) * chunk_rows + out_row) * 8;
                         if (LB2_L2_HINTS) st_global_v4_hint(lo, make_uint4(pl[0], pl[1], pl[2], pl[3]), st_policy);
                         else *reinterpret_cast<uint4*>(lo) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
@@ -594,6 +656,52 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                         st_global_v4_hint(out + ((size_t)c8 * chunk_rows + out_row) * 8, make_uint4(pk[0], pk[1], pk[2], pk[3]), st_policy);
                     else
                         *reinterpret_cast<uint4*>(out + ((size_t)c8 * chunk_rows + out_row) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+            };
+            // Lite mode (kOutFp8): 16 channels (column blocks cc, cc + 8) of one row half. Besides the two fp16 chunk rows
+            // the consumer's correction MMAs need, per 16 channels, one 16-byte row of e4m3(a) and one of e4m3((a - fp16(a)) * 2^12):
+            // chunk planes lo_chunks + 2 * (channel / 16) and the one behind it.
+            auto store_pair_fp8 = [&](const uint32_t (&r)[2][8], int h, int cc) {
+                const bool valid = h ? valid2[1] : valid2[0];
+                const int out_row = h ? out_row2[1] : out_row2[0];
+                uint32_t qa[4], ql[4];
+#pragma unroll
+                for (int g = 0; g < 2; g++) {
+                    const float* bp = bs + col0 + cc + 8 * g;
+                    const float4 b0 = *reinterpret_cast<const float4*>(bp), b1 = *reinterpret_cast<const float4*>(bp + 4);
+                    float v[8];
+                    activate_b(r[g], tbase + h * 128 + cc + 8 * g, b0, b1, v);
+                    uint32_t pk[4], q8[4], q9[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        __half2 hh = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                        pk[e] = valid ? *reinterpret_cast<uint32_t*>(&hh) : 0u;
+                        const float2 hf = __half22float2(hh);
+                        q8[e] = cvt_e4m3x2(v[2 * e], v[2 * e + 1]);
+                        q9[e] = cvt_e4m3x2((v[2 * e] - hf.x) * kLoScale, (v[2 * e + 1] - hf.y) * kLoScale);
+                    }
+#ifdef LB2_DEBUG_KNOBS
+                    if ((kDebugFlags(P) & 128) && blockIdx.x == 0 && warp == 2 && lane == 5 && it < 40 && g == 0)
+                        printf("it %u job %d store: v %g %g a8 %04x lo8 %04x valid %d row %d lo_chunks %d\n", it, jj, v[0], v[1], q8[0], q9[0], (int)valid, out_row, lo_chunks);
+#endif
+                    qa[2 * g] = valid ? (q8[0] | (q8[1] << 16)) : 0u; qa[2 * g + 1] = valid ? (q8[2] | (q8[3] << 16)) : 0u;
+                    ql[2 * g] = valid ? (q9[0] | (q9[1] << 16)) : 0u; ql[2 * g + 1] = valid ? (q9[2] | (q9[3] << 16)) : 0u;
+                    if (valid || !remap) {
+                        __half* ph = out + ((size_t)((col0 + cc) / 8 + g) * chunk_rows + out_row) * 8;
+                        if (LB2_L2_HINTS) st_global_v4_hint(ph, make_uint4(pk[0], pk[1], pk[2], pk[3]), st_policy);
+                        else *reinterpret_cast<uint4*>(ph) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+                if (valid || !remap) {
+                    __half* pa = out + ((size_t)(lo_chunks + 2 * ((col0 + cc) >> 4)) * chunk_rows + out_row) * 8;
+                    __half* pl = pa + (size_t)chunk_rows * 8;
+                    if (LB2_L2_HINTS) {
+                        st_global_v4_hint(pa, make_uint4(qa[0], qa[1], qa[2], qa[3]), st_policy);
+                        st_global_v4_hint(pl, make_uint4(ql[0], ql[1], ql[2], ql[3]), st_policy);
+                    } else {
+                        *reinterpret_cast<uint4*>(pa) = make_uint4(qa[0], qa[1], qa[2], qa[3]);
+                        *reinterpret_cast<uint4*>(pl) = make_uint4(ql[0], ql[1], ql[2], ql[3]);
+                    }
                 }
             };
 
@@ -620,8 +728,8 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                         const float* bp = bs + col0 + k * 8;
                         const float4 b0 = *reinterpret_cast<const float4*>(bp), b1 = *reinterpret_cast<const float4*>(bp + 4);
                         float v0[8], v1[8];
-                        activate_b(r[0], b0, b1, v0);
-                        activate_b(r[1], b0, b1, v1);
+                        activate_b(r[0], unit_addr(k), b0, b1, v0);
+                        activate_b(r[1], unit_addr(upc + k), b0, b1, v1);
 #pragma unroll
                         for (int t = 0; t < 9; t++) {
                             const float* wt = headw_s + t * 128 + col0 + k * 8;
@@ -655,6 +763,29 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                         zb[(size_t)t * chunk_rows + out_row2[0]] = valid2[0] ? z0[t] : 0.0f;
                         zb[(size_t)t * chunk_rows + out_row2[1]] = valid2[1] ? z1[t] : 0.0f;
                     }
+                }
+            } else if (kFp8 && out_mode == kOutFp8) {
+                // lite jobs: pair p = (row half p & 1, 16 channels p >> 1); the next pair's TMEM loads are in flight meanwhile
+                // (c_out is a multiple of 32, so every warp has an even number of 8-column blocks)
+                const int n_pairs = n_units >> 1;
+                auto load_pair = [&](int p, uint32_t (&r)[2][8]) {
+                    if (p < n_pairs) {
+                        const uint32_t a = tbase + (p & 1) * 128 + (p >> 1) * 16;
+                        tmem_ld_32x8(a, r[0]);
+                        tmem_ld_32x8(a + 8, r[1]);
+                    }
+                };
+                uint32_t ra[2][8], rb[2][8];
+                load_pair(0, ra);
+                tmem_ld_wait();
+#pragma unroll 1
+                for (int p = 0; p < n_pairs; p += 2) {
+                    load_pair(p + 1, rb);
+                    store_pair_fp8(ra, p & 1, (p >> 1) * 16);
+                    tmem_ld_wait();
+                    load_pair(p + 2, ra);
+                    store_pair_fp8(rb, (p + 1) & 1, ((p + 1) >> 1) * 16);
+                    tmem_ld_wait();
                 }
             } else if (n_units) {
                 auto load_group = [&](int u, uint32_t (&r)[G][8]) {
@@ -725,7 +856,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                 LB2_TRACE(it, 11);
                 if (P.use_flags) {
                     fence_proxy_async();  // generic-proxy stores -> visible to other CTAs' TMA loads
-                    st_release_gpu(jobs[jj].flags + tile_of(idx), P.epoch);
+                    st_release_gpu(jobs[jj].flags + tile_of(idx), epoch);
                 }
                 LB2_TRACE(it, 12);
                 *pub_done = it + 1;
@@ -737,7 +868,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         // published. Every CTA: polls (acquire, gpu scope, lanes in parallel) the <= 3 tile flags of
         // the previous layer that cover an item's rows +- halo ahead of the producer and publishes
         // its progress in shared memory — the L2 round trips of the polling stay off the load path.
-        const bool dynamic = P.next_item != nullptr;
+        const bool dynamic = P.dynamic != 0;
         const int first = P.item_begin + (kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x);
         const int step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
         int j = 0;
@@ -753,7 +884,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                     if (kRes) {
                         // one end marker is drawn from EACH net's counter by every cluster: items + clusters claims per net per launch
                         for (;;) {
-                            q = P.net_item_begin[cur_net] + (int)(atomicAdd(P.net_next_item[cur_net], 1u) - P.net_claim_base[cur_net]);
+                            q = P.net_item_begin[cur_net] + (int)atomicAdd(P.sched + 1 + cur_net, 1u);
                             q_end = P.net_item_end[cur_net];
                             if (q < q_end) break;
                             dry[cur_net] = true;
@@ -762,7 +893,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                             j = -1;   // the other net's items lie elsewhere in the list: restart the round cursor
                         }
                     } else {
-                        q = dynamic ? P.item_begin + (int)(atomicAdd(P.next_item, 1u) - P.claim_base) : first + (int)it * step;
+                        q = dynamic ? P.item_begin + (int)(atomicAdd(P.sched, 1u) - P.claim_base) : first + (int)it * step;
                     }
                 }
                 q = __shfl_sync(0xffffffffu, q, 0);
@@ -786,7 +917,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                 for (int sp = 0; sp < J.dep_n_split; sp++) {   // every column split of the producing layer
                     const uint32_t* flags = jobs[J.dep_job + sp].flags;
                     if (lo + lane <= hi)
-                        while (ld_acquire_gpu(flags + lo + lane) != P.epoch) __nanosleep(20);
+                        while (ld_acquire_gpu(flags + lo + lane) != epoch) __nanosleep(20);
                 }
             }
             __syncwarp();
@@ -1005,6 +1136,11 @@ __global__ void __launch_bounds__(256) ensemble_mean_kernel(const MeanArgs A) {
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+// host-side addresses of the kernels whose arguments hold caller pointers (the host API patches their graph nodes)
+const void* kernel_address(int which) {
+    return which == 0 ? (const void*)expand_planes_kernel : (which == 1 ? (const void*)heads_kernel : (const void*)ensemble_mean_kernel);
+}
+
 cudaError_t launch_ensemble_mean(const MeanArgs& a, cudaStream_t st) {
     const int total = a.n_policy * kPoints + a.n_value;
     if (total == 0) return cudaSuccess;
@@ -1018,21 +1154,20 @@ cudaError_t launch_expand(const ExpandArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// Instances: plain-only epilogue (kOutModes 0) and one that can also store the split-operand planes (3), each as single CTA,
+// CTA pair, CTA pair with resident weights.
+#define LB2_FOR_EACH_TRUNK(X) X(false, false, 0) X(true, false, 0) X(true, true, 0) X(false, false, 1) X(true, false, 1) X(true, true, 1) X(false, false, 2) X(true, false, 2) X(true, true, 2)
 cudaError_t trunk_kernel_setup() {
-    cudaError_t e = cudaFuncSetAttribute(trunk_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(trunk_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(trunk_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(trunk_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(trunk_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrunkSmemBytesRes);
-    if (e != cudaSuccess) return e;
+    cudaError_t e;
+#define LB2_SET(p, r, m)                                                                                                       \
+    if ((e = cudaFuncSetAttribute(trunk_kernel<p, r, m>, cudaFuncAttributeMaxDynamicSharedMemorySize,                          \
+                                  r ? kTrunkSmemBytesRes : kTrunkSmemBytes)) != cudaSuccess) return e;
+    LB2_FOR_EACH_TRUNK(LB2_SET)
+#undef LB2_SET
     return cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
 }
 
-cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool pair, bool resident, bool precise, cudaStream_t st) {
+cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool pair, bool resident, int out_modes, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kTrunkThreads);
@@ -1058,9 +1193,12 @@ cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool 
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    if (pair && resident) return cudaLaunchKernelEx(&cfg, trunk_kernel<true, true, false>, p);
-    if (precise) return pair ? cudaLaunchKernelEx(&cfg, trunk_kernel<true, false, true>, p) : cudaLaunchKernelEx(&cfg, trunk_kernel<false, false, true>, p);
-    return pair ? cudaLaunchKernelEx(&cfg, trunk_kernel<true, false, false>, p) : cudaLaunchKernelEx(&cfg, trunk_kernel<false, false, false>, p);
+    resident = resident && pair;
+#define LB2_LAUNCH(p_, r_, m_) \
+    if (pair == p_ && resident == r_ && out_modes == m_) return cudaLaunchKernelEx(&cfg, trunk_kernel<p_, r_, m_>, p);
+    LB2_FOR_EACH_TRUNK(LB2_LAUNCH)
+#undef LB2_LAUNCH
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_heads(const HeadArgs& a, cudaStream_t st) {

@@ -45,7 +45,7 @@ constexpr int kRingBytesPair = kStagesPair * kStageBytesPair;         // 178,176
 constexpr int kTrunkRingBytes = kRingBytesSingle > kRingBytesPair ? kRingBytesSingle : kRingBytesPair;
 // ring | mbarriers etc. | bias [jobs][128] f32 | fused-head weights [kHeadSlots][9][128] f32 | job table
 constexpr int kCtrlBytes = 384;  // mbarriers, TMEM slot, progress counters, claim ring
-constexpr int kTrunkSmemBytes = kTrunkRingBytes + kCtrlBytes + kMaxLaunchJobs * 128 * 4 + kHeadSlots * 9 * 128 * 4 + kMaxLaunchJobs * 160;
+constexpr int kTrunkSmemBytes = kTrunkRingBytes + kCtrlBytes + kMaxLaunchJobs * 128 * 4 + kHeadSlots * 9 * 128 * 4 + kMaxLaunchJobs * 176;
 static_assert(kTrunkSmemBytes <= 227 * 1024, "trunk kernel shared memory");
 // Resident-weights mode (CTA pairs only): a CTA keeps ITS half of the whole layer's packed weights in
 // shared memory and re-uses it for every item of that layer it processes; the pipeline stages then
@@ -55,7 +55,7 @@ constexpr int kStagesRes = 5;
 constexpr int kResJobs = 24;        // jobs per launch in this mode (no column splits)
 constexpr int kResHeadSlots = 2;    // one fused-head weight set per net
 constexpr int kTrunkSmemBytesRes = kResWeightBytes + kStagesRes * kASlabBytes + kCtrlBytes + kResJobs * 128 * 4 +
-                                   kResHeadSlots * 9 * 128 * 4 + kResJobs * 160;
+                                   kResHeadSlots * 9 * 128 * 4 + kResJobs * 176;
 static_assert(kTrunkSmemBytesRes <= 227 * 1024, "resident-weights trunk shared memory");
 constexpr int kMaxLayers = 16;
 constexpr int kMaxTensorMaps = 6;
@@ -64,6 +64,14 @@ constexpr int kMaxRounds = 40;  // a round = the jobs of equal depth (all nets, 
 constexpr int kMaxRoundJobs = 2 * kMaxSplit;
 constexpr int kTraceItems = 96;
 constexpr int kTraceEvents = 16;
+constexpr int kSchedEpoch = 3, kSchedWords = 4;
+constexpr int kOutPlain = 0, kOutLo16 = 1, kOutFp8 = 2;
+#ifndef LB2_LITE_SEPARATE_ACC
+#define LB2_LITE_SEPARATE_ACC 0
+#endif
+constexpr bool kLiteSeparateAcc = LB2_LITE_SEPARATE_ACC != 0;
+constexpr int kCorrCols = 64;   // lite mode: TMEM columns between an accumulator and the one of its e4m3 correction terms (c_out <= 64)
+constexpr float kLoScale = 4096.0f;   // lite mode: the activation residual is stored as e4m3((a - fp16(a)) * 2^12)
 
 // One trunk layer of one net over the whole batch.
 struct LayerJob {
@@ -87,9 +95,17 @@ struct LayerJob {
     int32_t head_slot;       // which resident fused-head weight set (net * kMaxSplit + split)
     int32_t zparts;          // fused head: zbuf parts written before this job's (split * kColParts)
     int32_t layer;           // layer index within the net
-    int32_t n_real_slabs;    // c_in / 16. Equal to n_slabs except in split-operand ("precise") mode, where the K loop
-                             // runs over virtual slabs: [hi x Wh] [hi x Wl] [lo x Wh] (see lb2_api.cu, pack_trunk_weights)
-    int32_t lo_chunks;       // precise mode: the fp16 residual of the output goes lo_chunks chunk planes behind `out`; 0 = off
+    int32_t n_real_slabs;    // c_in / 16. Equal to n_slabs except in the split-operand modes, where the K loop runs over
+                             // virtual slabs, term after term (see lb2_api.cu, pack_trunk_weights):
+                             //   precise: [hi x Wh] [hi x Wl] [lo x Wh], all kind::f16
+                             //   lite:    [hi x Wh] kind::f16, then [a8 | lo8] x [Wl8 ; W8] kind::f8f6f4 (e4m3, K = 32)
+    int32_t lo_chunks;       // chunk planes of the OUTPUT buffer in front of the extra planes this job's epilogue stores
+    int16_t term_base[3];    // virtual slab v = term * n_real_slabs + s reads input chunk planes term_base[term] + 2 s
+    int16_t n_f16_slabs;     // virtual slabs [0, n_f16_slabs) are kind::f16 MMAs, the rest kind::f8f6f4
+    int32_t out_mode;        // what the epilogue stores besides the fp16 activations (for the consuming layer):
+                             //   kOutPlain nothing, kOutLo16 the fp16 residual planes (precise consumer),
+                             //   kOutFp8 per 16 channels one e4m3 plane of the activations and one of the residual x 2^12
+    float acc_scale;         // the accumulator is acc_scale^-1 x the true sum (weights are packed scaled); 1 in plain mode
     const __half* wpk;       // packed weights: per (slab, tap group): [tap][2 chunks][n_out][8]
     const __half* wpk2;      // CTA-pair packing: per (slab, tap group): [rank][tap][2 chunks][n_out/2][8]
     const float* bias;       // [n_out]
@@ -101,20 +117,22 @@ struct LayerJob {
 
 struct TrunkParams {
     CUtensorMap tmaps[kMaxTensorMaps];
-    const LayerJob* jobs;
+    LayerJob jobs[kMaxJobs];       // the launch's job table travels in the kernel parameters (no device copy to keep in step)
     int32_t n_jobs;
     int32_t item_begin, item_end;  // launch-wide item index range handled by this launch
     int32_t n_rounds;
     int32_t round_base[kMaxRounds + 1];             // first item index of each round
     int16_t round_first[kMaxRounds], round_jobs[kMaxRounds];  // its jobs: round_jobs consecutive entries of the job table
-    uint32_t epoch;
+    // Per-device scheduler words, reset by the expand kernel at the start of every evaluation (so that a launch does not
+    // depend on its history and can be replayed from a CUDA graph): [0] in-order claim counter over all items, [1 + net] the
+    // per-net claim counters of the resident-weights mode, [kSchedEpoch] the flag epoch of the evaluation.
+    uint32_t* sched;
     int32_t use_flags;  // 1: cross-CTA dataflow through flags (single persistent launch)
-    uint32_t* next_item;        // dynamic scheduling: global in-order claim counter, or null. It is never reset:
-    uint32_t claim_base;        // its value when this launch starts (every launch advances it by items + clusters)
+    int32_t dynamic;            // 1: clusters claim items from sched[0] (or sched[1 + net]) in order; 0: static round robin
+    uint32_t claim_base;        // sched[0] when this launch starts: per-layer launches (trunk_mode 0) share the counter, every
+                                // launch advancing it by items + clusters
     // resident-weights mode: the item list is net-major (all policy jobs, then all value jobs), each net has
     // its own claim counter; a cluster works on its preferred net until that runs dry, then helps the other
-    uint32_t* net_next_item[2];
-    uint32_t net_claim_base[2];
     int32_t net_item_begin[2], net_item_end[2];
     int32_t policy_clusters;    // clusters [0, policy_clusters) prefer net 0, the rest net 1
     unsigned long long* trace;  // optional timeline buffer [cta][kTraceItems][kTraceEvents] of %globaltimer ns
@@ -131,6 +149,7 @@ struct ExpandArgs {
     int32_t n, n_nets;
     const uint8_t* pf;           // optional buffer to pull into L2
     size_t pf_bytes;
+    uint32_t* sched;             // the device's scheduler words (TrunkParams::sched): new epoch, claim counters to zero
 };
 
 struct HeadArgs {
@@ -154,10 +173,12 @@ struct MeanArgs {
 
 // launchers (lb2_kernels.cu)
 cudaError_t launch_expand(const ExpandArgs& a, cudaStream_t st);
-cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool pair, bool resident, bool precise, cudaStream_t st);
+cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool pair, bool resident, int out_modes, cudaStream_t st);
 cudaError_t launch_heads(const HeadArgs& a, cudaStream_t st);
 cudaError_t launch_ensemble_mean(const MeanArgs& a, cudaStream_t st);
 cudaError_t trunk_kernel_setup();
+const void* kernel_address(int which);   // 0 expand, 1 heads, 2 ensemble mean
 
 }  // namespace lb2
-static_assert(sizeof(lb2::LayerJob) <= 160 && sizeof(lb2::LayerJob) % 4 == 0, "job table slot size");
+static_assert(sizeof(lb2::TrunkParams) < 32000, "kernel parameter space");
+static_assert(sizeof(lb2::LayerJob) <= 176 && sizeof(lb2::LayerJob) % 4 == 0, "job table slot size");

@@ -246,6 +246,28 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
             : "memory");
     }
 }
+// The same for kind::f8f6f4 with e4m3 operands (K = 32 per instruction: a 16-byte core-matrix row holds 16 channels); the
+// instruction descriptor has the same bit pattern as the fp16 one (format code 0 = F16 there, E4M3 here), the accumulator
+// is the same fp32 TMEM tile and may be shared with kind::f16 MMAs (tools/mma_mixed_test.cu: exact, same issue rate).
+template <bool kPair = false>
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+    if (kPair) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
 // all previously issued MMAs of this thread arrive on the mbarrier when they complete
 // (kPair: on the barrier at this offset in BOTH CTAs of the pair)
 template <bool kPair = false>
