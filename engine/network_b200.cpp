@@ -23,6 +23,7 @@
 // one device batch (the reference evaluates batch 1 per thread).
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cassert>
 #include <cmath>
 #include <condition_variable>
@@ -478,13 +479,17 @@ void Network::async_scored_moves(std::atomic<int>* nodecount, FastState* state, 
 
 // Network::benchmark (Network.cpp:147-199): 2000 policy and 10000 value evaluations spread over the
 // search threads, each a single-position request as in the reference; the library batches them.
+// Network::benchmark (Network.cpp:147-199): cfg_num_threads threads call get_scored_moves / get_value on copies of the state,
+// batch 1 per call. Same legs and the same output lines; the amounts are 50x the reference's 2000 / 10000 (sized for a CPU
+// that does ~1 k/s — here they would be over before the reference's 10 ms timer ticks twice) and the clock is
+// std::chrono. A third line says what one call costs on the host before anything reaches the device.
 void Network::benchmark(FastState* state) {
     const int cpus = cfg_num_threads;
     struct Leg { const char* what; int amount; bool policy; };
-    const Leg legs[2] = {{"predictions", 2000, true}, {"evaluations", 10000, false}};
+    const Leg legs[2] = {{"predictions", 50 * 2000, true}, {"evaluations", 50 * 10000, false}};
     for (const Leg& leg : legs) {
         const int iters_per_thread = (leg.amount + cpus - 1) / cpus;
-        Time start;
+        const auto start = std::chrono::steady_clock::now();
         ThreadGroup tg(thread_pool);
         for (int i = 0; i < cpus; i++) {
             tg.add_task([iters_per_thread, state, &leg]() {
@@ -496,9 +501,17 @@ void Network::benchmark(FastState* state) {
             });
         }
         tg.wait_all();
-        Time end;
-        const float seconds = (float)Time::timediff(start, end) / 100.0f;
-        myprintf("%5d %s in %5.2f seconds -> %d p/s\n", leg.amount, leg.what, seconds, (int)((float)leg.amount / seconds));
+        const float seconds = std::chrono::duration<float>(std::chrono::steady_clock::now() - start).count();
+        const int done = iters_per_thread * cpus;
+        myprintf("%5d %s in %5.2f seconds -> %d p/s\n", done, leg.what, seconds, (int)((float)done / seconds));
+    }
+    {
+        FastState mystate = *state;
+        uint32_t packed[361];
+        const auto start = std::chrono::steady_clock::now();
+        for (int i = 0; i < 2000; i++) leela_b200::pack_features(&mystate, (i & 1) != 0, packed, nullptr);
+        const float us = std::chrono::duration<float>(std::chrono::steady_clock::now() - start).count() * 1e6f / 2000.0f;
+        myprintf("feature planes: %.1f us per position on one core (host work in front of every request)\n", us);
     }
 }
 

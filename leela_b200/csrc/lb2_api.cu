@@ -122,6 +122,7 @@ struct NetDev {
 };
 
 constexpr int kIoSlots = 2;
+constexpr int kDispatchersPerDevice = 4;   // threads of the submit queue per device
 
 // Input/output buffers of one host-buffer call (or one batch of the submit queue) in flight on a device. Two slots per
 // device let the copies of one call overlap the kernels of another.
@@ -276,7 +277,7 @@ struct lb2_ctx {
     int q_cap = 0;                         // positions per batch buffer
     bool worker_run = false;
     int workers_busy = 0;
-    std::vector<std::thread> workers;      // kIoSlots per device
+    std::vector<std::thread> workers;      // kDispatchersPerDevice per device
     std::string q_error;                   // text of the last asynchronous failure (reported by lb2_drain)
 };
 
@@ -1199,31 +1200,39 @@ int finish_chunk(const HostCall& c, const Chunk& ch) {
     return rc;
 }
 
+// Checks a host-buffer call and fills in everything a chunk needs to know about it.
+int prepare_host_call(lb2_ctx* ctx, const uint32_t* pol, const uint32_t* val, const uint8_t* rot, int n, float temp,
+                      float* probs, float* win, bool ensemble, HostCall* c) {
+    c->ctx = ctx;
+    c->need[0] = probs != nullptr; c->need[1] = win != nullptr;
+    int rc = check_ready(ctx, c->need);
+    if (rc) return rc;
+    if (n < 0) return fail(LB2_ERR_INVALID, "n < 0");
+    if (n == 0) return LB2_OK;
+    if ((!ensemble && !rot) || (c->need[0] && !pol) || (c->need[1] && !val)) return fail(LB2_ERR_INVALID, "null input pointer");
+    if (c->need[0] && !(temp > 0.0f)) return fail(LB2_ERR_INVALID, "softmax temperature must be > 0");
+    if (!ensemble && (rc = check_rotations(rot, n))) return rc;
+    c->opt = snapshot(ctx);
+    c->src[0] = pol; c->src[1] = val; c->rot = rot; c->temp = temp; c->probs = probs; c->win = win; c->ensemble = ensemble;
+    // caller buffers that are already page-locked are used directly; pageable ones go through the slot's pinned staging
+    const size_t pb = (size_t)n * lb2::kPoints * 4;
+    c->pin_in[0] = c->need[0] && is_pinned(ctx, pol, pb);
+    c->pin_in[1] = c->need[1] && is_pinned(ctx, val, pb);
+    c->pin_rot = ensemble || is_pinned(ctx, rot, n);
+    c->pin_probs = c->need[0] && is_pinned(ctx, probs, pb);
+    c->pin_win = c->need[1] && is_pinned(ctx, win, (size_t)n * 4);
+    return LB2_OK;
+}
+
 // Host-buffer evaluation. The call is cut into chunks of at most max_batch positions; every chunk is one device batch
 // on whichever (device, slot) is free — whole batches per device. A caller blocks for a slot only while it holds none
 // itself (two callers each holding one slot and waiting for a second would otherwise deadlock): with chunks of its own
 // in flight it first collects the oldest.
 int eval_host(lb2_ctx* ctx, const uint32_t* pol, const uint32_t* val, const uint8_t* rot, int n, float temp,
-              float* probs, float* win, bool ensemble = false, int prefer_dev = -1) {
+              float* probs, float* win, bool ensemble = false) {
     HostCall c;
-    c.ctx = ctx;
-    c.need[0] = probs != nullptr; c.need[1] = win != nullptr;
-    int rc = check_ready(ctx, c.need);
-    if (rc) return rc;
-    if (n < 0) return fail(LB2_ERR_INVALID, "n < 0");
-    if (n == 0) return LB2_OK;
-    if ((!ensemble && !rot) || (c.need[0] && !pol) || (c.need[1] && !val)) return fail(LB2_ERR_INVALID, "null input pointer");
-    if (c.need[0] && !(temp > 0.0f)) return fail(LB2_ERR_INVALID, "softmax temperature must be > 0");
-    if (!ensemble && (rc = check_rotations(rot, n))) return rc;
-    c.opt = snapshot(ctx);
-    c.src[0] = pol; c.src[1] = val; c.rot = rot; c.temp = temp; c.probs = probs; c.win = win; c.ensemble = ensemble;
-    // caller buffers that are already page-locked are used directly; pageable ones go through the slot's pinned staging
-    const size_t pb = (size_t)n * lb2::kPoints * 4;
-    c.pin_in[0] = c.need[0] && is_pinned(ctx, pol, pb);
-    c.pin_in[1] = c.need[1] && is_pinned(ctx, val, pb);
-    c.pin_rot = ensemble || is_pinned(ctx, rot, n);
-    c.pin_probs = c.need[0] && is_pinned(ctx, probs, pb);
-    c.pin_win = c.need[1] && is_pinned(ctx, win, (size_t)n * 4);
+    int rc = prepare_host_call(ctx, pol, val, rot, n, temp, probs, win, ensemble, &c);
+    if (rc || n == 0) return rc;
     // an ensemble position occupies 8 device positions (+1 for its mean in the output buffers)
     const int chunk = (int)std::min<long>(ensemble ? std::max<long>(1, c.opt.max_batch / 8) : c.opt.max_batch, n);
     std::deque<Chunk> flying;
@@ -1238,7 +1247,7 @@ int eval_host(lb2_ctx* ctx, const uint32_t* pol, const uint32_t* val, const uint
         Chunk ch;
         ch.lo = lo;
         ch.cnt = std::min(chunk, n - lo);
-        while (!acquire_slot(ctx, prefer_dev, flying.empty(), &ch.dev, &ch.slot)) collect_oldest();
+        while (!acquire_slot(ctx, -1, flying.empty(), &ch.dev, &ch.slot)) collect_oldest();
         if ((rc = enqueue_chunk(c, ch, chunk))) {
             first_error = rc; first_text = g_last_error;
             cudaSetDevice(ctx->dev[ch.dev]->id);
@@ -1251,6 +1260,27 @@ int eval_host(lb2_ctx* ctx, const uint32_t* pol, const uint32_t* val, const uint
     while (!flying.empty()) collect_oldest();
     if (first_error) g_last_error = first_text;
     return first_error;
+}
+
+// One batch of at most max_batch positions on a (device, slot) the caller already holds; the slot is released when
+// the results are in `probs` / `win`.
+int eval_host_on_slot(lb2_ctx* ctx, int dev, int slot, const uint32_t* pol, const uint32_t* val, const uint8_t* rot, int n, float temp,
+                      float* probs, float* win) {
+    HostCall c;
+    int rc = prepare_host_call(ctx, pol, val, rot, n, temp, probs, win, false, &c);
+    if (rc || n == 0 || n > c.opt.max_batch) {
+        release_slot(ctx, dev, slot);
+        return rc ? rc : (n == 0 ? LB2_OK : fail(LB2_ERR_INVALID, "batch larger than max_batch"));
+    }
+    Chunk ch;
+    ch.dev = dev; ch.slot = slot; ch.lo = 0; ch.cnt = n;
+    if ((rc = enqueue_chunk(c, ch, (int)std::max<long>(n, std::min<long>(c.opt.max_batch, ctx->q_cap))))) {
+        cudaSetDevice(ctx->dev[dev]->id);
+        cudaStreamSynchronize(ctx->dev[dev]->slots[slot].stream);
+        release_slot(ctx, dev, slot);
+        return rc;
+    }
+    return finish_chunk(c, ch);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -1280,13 +1310,21 @@ QueueBatch* new_queue_batch(lb2_ctx* ctx) {
 
 void worker_loop(lb2_ctx* ctx, int dev_index) {
     cudaSetDevice(ctx->dev[dev_index]->id);
+    auto have_work = [&] { return !ctx->q_ready.empty() || (ctx->q_open[0] && ctx->q_open[0]->n) || (ctx->q_open[1] && ctx->q_open[1]->n); };
     for (;;) {
-        QueueBatch* b = nullptr;
         {
             std::unique_lock<std::mutex> lk(ctx->q_mu);
-            ctx->q_cv.wait(lk, [&] {
-                return !ctx->worker_run || !ctx->q_ready.empty() || (ctx->q_open[0] && ctx->q_open[0]->n) || (ctx->q_open[1] && ctx->q_open[1]->n);
-            });
+            ctx->q_cv.wait(lk, [&] { return !ctx->worker_run || have_work(); });
+            if (!have_work()) return;   // shutting down
+        }
+        // The slot FIRST, the batch second: while every I/O slot is busy, requests keep accumulating in the open batch
+        // instead of being carried off in small batches that then queue for the device. (A small batch costs the device as
+        // much time as a medium one: below ~90 positions a pass is bound by the latency of its 12 chained layers.)
+        int dev = -1, slot = -1;
+        acquire_slot(ctx, dev_index, true, &dev, &slot);
+        QueueBatch* b = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(ctx->q_mu);
             if (!ctx->q_ready.empty()) {
                 b = ctx->q_ready.front();
                 ctx->q_ready.pop_front();
@@ -1297,16 +1335,16 @@ void worker_loop(lb2_ctx* ctx, int dev_index) {
                     if (ctx->q_open[i] && ctx->q_open[i]->n && (k < 0 || ctx->q_open[i]->n > ctx->q_open[k]->n)) k = i;
                 if (k >= 0) { b = ctx->q_open[k]; ctx->q_open[k] = nullptr; }
             }
-            if (!b) {
-                if (!ctx->worker_run) return;
-                continue;
-            }
-            ctx->workers_busy++;
+            if (b) ctx->workers_busy++;
         }
+        if (!b) {   // another dispatcher took it meanwhile
+            release_slot(ctx, dev, slot);
+            continue;
+        }
+        cudaSetDevice(ctx->dev[dev]->id);
         ctx->stat_positions += b->n; ctx->stat_batches++; ctx->stat_requests += (long)b->req.size();
-        const int rc = b->kind == LB2_POLICY
-                           ? eval_host(ctx, b->planes, nullptr, b->rot, b->n, b->temp, b->out, nullptr, false, dev_index)
-                           : eval_host(ctx, nullptr, b->planes, b->rot, b->n, 1.0f, nullptr, b->out, false, dev_index);
+        const int rc = b->kind == LB2_POLICY ? eval_host_on_slot(ctx, dev, slot, b->planes, nullptr, b->rot, b->n, b->temp, b->out, nullptr)
+                                             : eval_host_on_slot(ctx, dev, slot, nullptr, b->planes, b->rot, b->n, 1.0f, nullptr, b->out);
         const size_t per = b->kind == LB2_POLICY ? lb2::kPoints : 1;
         size_t o = 0;
         for (auto& r : b->req) {
@@ -1325,8 +1363,7 @@ void worker_loop(lb2_ctx* ctx, int dev_index) {
             b->req.clear();
             ctx->q_free_list.push_back(b);
             ctx->workers_busy--;
-            if (ctx->q_ready.empty() && !(ctx->q_open[0] && ctx->q_open[0]->n) && !(ctx->q_open[1] && ctx->q_open[1]->n) && ctx->workers_busy == 0)
-                ctx->q_idle.notify_all();
+            if (!have_work() && ctx->workers_busy == 0) ctx->q_idle.notify_all();
         }
         ctx->q_free.notify_one();
     }
@@ -1343,8 +1380,10 @@ int submit(lb2_ctx* ctx, int kind, const uint32_t* planes, const uint8_t* rot, i
     if (!ctx->worker_run) {
         ctx->worker_run = true;
         { std::lock_guard<std::mutex> ol(ctx->opt_mu); ctx->q_cap = (int)std::max<long>(ctx->max_batch, 1); }
+        // more dispatchers than I/O slots: while kIoSlots of them have a batch on the device, the others hand out the
+        // results of finished batches (a copy and a callback per request) and pick up the next
         for (size_t di = 0; di < ctx->dev.size(); di++)
-            for (int i = 0; i < kIoSlots; i++) ctx->workers.emplace_back(worker_loop, ctx, (int)di);
+            for (int i = 0; i < kDispatchersPerDevice; i++) ctx->workers.emplace_back(worker_loop, ctx, (int)di);
     }
     if (n > ctx->q_cap) {
         // larger than a batch buffer: evaluate it on its own (blocking), then report through the callback as usual
@@ -1364,7 +1403,7 @@ int submit(lb2_ctx* ctx, int kind, const uint32_t* planes, const uint8_t* rot, i
             if (!ctx->q_free_list.empty()) {
                 open = ctx->q_free_list.back();
                 ctx->q_free_list.pop_back();
-            } else if (ctx->q_all.size() < 4 * kIoSlots * ctx->dev.size() + 4) {
+            } else if (ctx->q_all.size() < 2 * kDispatchersPerDevice * ctx->dev.size() + 4) {
                 if (!(open = new_queue_batch(ctx))) return fail(LB2_ERR_NOMEM, "pinned batch buffer");
             } else {
                 ctx->q_free.wait(lk);   // every buffer is filling or in flight: back-pressure on the submitters
