@@ -16,8 +16,9 @@
 //                              (no GPU needed; tests compare them with the reference's own)
 //   -DLB2_REFERENCE_BUILD  the same main for the reference's own CPU engine (oracle/ref/Makefile
 //                          `ref_engine`, the baseline of `bench.py --engine`): B200 options dropped
-//   the OpenCL self-test (GTP.cpp:105-125) is not run: it pins the reference's 192-wide weights,
-//   which are not in the snapshot.
+//   the OpenCL self-test (GTP.cpp:105-125) pins the reference's 192-wide weights, which are not in the
+//   snapshot; in its place leela_b200::self_test checks the known answers the weights file carries
+//   (the reference's CPU outputs for those weights on the empty board); --noselftest skips it.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -167,7 +168,7 @@ void print_evaluator_stats() {
 int main(int argc, char* argv[]) {
     bool gtp_mode = false, noponder = false, playouts_set = false;
     long batch = 0;
-    bool precise = false;
+    bool precise = false, no_selftest = false;
     const char* dump_out = nullptr;
     int dump_n = 0;
     uint32_t dump_seed = 0;
@@ -210,6 +211,7 @@ int main(int argc, char* argv[]) {
         else if (a == "--weights") leela_b200::set_weights_path(value("--weights"));
         else if (a == "--own-planes") leela_b200::set_planes_mode(1);
         else if (a == "--check-planes") leela_b200::set_planes_mode(2);
+        else if (a == "--noselftest") no_selftest = true;
         else if (a == "--max-outstanding") leela_b200::set_max_outstanding(atoi(value("--max-outstanding")));
         else if (a == "--batch") batch = atol(value("--batch"));
         else if (a == "--precise") precise = true;
@@ -260,6 +262,9 @@ int main(int argc, char* argv[]) {
 
     std::unique_ptr<GameState> maingame(new GameState);
     maingame->init_game(19, 7.5f);
+#ifndef LB2_REFERENCE_BUILD
+    if (cfg_enable_nets && !no_selftest && !leela_b200::self_test(*maingame)) return EXIT_FAILURE;
+#endif
 
     std::string input;
     for (;;) {

@@ -65,6 +65,10 @@ int g_planes_mode = 0;       // 0: planes through the reference's board queries;
 std::atomic<long> g_planes_checked{0};
 thread_local std::atomic<int> t_results_outstanding{0};
 
+struct KnownAnswer { int index, vertex; float prob; };
+std::vector<KnownAnswer> g_kat;   // known answers shipped with the weights file, see self_test()
+float g_kat_value = -1.0f;
+
 [[noreturn]] void die(const char* what) {
     // the OpenCL backend threw std::runtime_error / cl::Error here (OpenCL.cpp:665-669, 848-850)
     throw std::runtime_error(std::string("leela_b200: ") + what + ": " + lb2_last_error());
@@ -109,6 +113,17 @@ void load_weights(const std::string& path) {
             if (lb2_net_push_ip(net, n_in, n_out, w.data(), b.data())) die("lb2_net_push_ip");
         }
         if (lb2_net_finalize(net)) die("lb2_net_finalize");
+    }
+    // optional known-answer trailer (leela_b200/fileio.py:write_weights)
+    if (fread(magic, 1, 8, r.f) == 8 && !memcmp(magic, "LB2KAT01", 8)) {
+        const int n = r.i32();
+        for (int i = 0; i < n; i++) {
+            KnownAnswer k;
+            k.index = r.i32(); k.vertex = r.i32();
+            r.read(&k.prob, 4);
+            g_kat.push_back(k);
+        }
+        r.read(&g_kat_value, 4);
     }
 }
 
@@ -213,6 +228,29 @@ static void pack_features_reference_board(FastState* state, bool value_net, uint
     };
     if (mark(state->get_last_move(), L.last_move)) mark(state->get_prevlast_move(), L.prev_move);
     mark(state->get_komove(), L.ko);
+}
+
+// The reference checks its OpenCL backend at start-up against two known outputs of ITS weights on the empty board
+// (GTP::perform_self_test, GTP.cpp:105-125: entries 60 and 72 of get_scored_moves(DIRECT, 0)). The same check for whatever
+// weights were loaded: the file carries the answers of the reference's CPU path for them (probabilities of a few
+// Netresult entries with their vertices, and the winrate), compared at the tolerances the parity tests state.
+bool self_test(GameState& state) {
+    if (g_kat.empty()) {
+        myprintf("B200 self-test: skipped (the weights file carries no known answers).\n");
+        return true;
+    }
+    myprintf("B200 self-test: ");
+    bool ok = true;
+    const Network::Netresult vec = Network::get_Network()->get_scored_moves(&state, Network::Ensemble::DIRECT, 0);
+    for (const KnownAnswer& k : g_kat) {
+        ok = ok && k.index >= 0 && k.index < (int)vec.size();
+        if (!ok) break;
+        ok = ok && vec[k.index].second == k.vertex && std::fabs(vec[k.index].first - k.prob) < 6e-3f;
+    }
+    const float win = Network::get_Network()->get_value(&state, Network::Ensemble::DIRECT);   // DIRECT = symmetry 0
+    ok = ok && std::fabs(win - g_kat_value) < 1e-3f;
+    myprintf(ok ? "passed.\n" : "failed. The evaluator does not reproduce the reference's outputs for these weights.\n");
+    return ok;
 }
 
 void set_planes_mode(int mode) { g_planes_mode = mode; }

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <string>
 
+#include "GameState.h"
 #include "Network.h"
 #include "leela_b200.h"
 
@@ -21,5 +22,8 @@ long planes_checked();
 void set_weights_path(const std::string& path);   // "LB2WGT01" file, see leela_b200/fileio.py
 void set_max_outstanding(int n);                   // async policy requests a search thread may have in flight
 lb2_ctx* context();
+
+// start-up known-answer test against the answers shipped with the weights file (GTP.cpp:105-125 for this evaluator)
+bool self_test(GameState& state);
 
 }  // namespace leela_b200

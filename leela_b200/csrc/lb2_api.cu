@@ -277,6 +277,7 @@ struct lb2_ctx {
     int q_cap = 0;                         // positions per batch buffer
     bool worker_run = false;
     int workers_busy = 0;
+    int q_idle_workers = 0;                // dispatchers asleep on q_cv (a submitter only signals when there is one)
     std::vector<std::thread> workers;      // kDispatchersPerDevice per device
     std::string q_error;                   // text of the last asynchronous failure (reported by lb2_drain)
 };
@@ -1314,7 +1315,9 @@ void worker_loop(lb2_ctx* ctx, int dev_index) {
     for (;;) {
         {
             std::unique_lock<std::mutex> lk(ctx->q_mu);
+            ctx->q_idle_workers++;
             ctx->q_cv.wait(lk, [&] { return !ctx->worker_run || have_work(); });
+            ctx->q_idle_workers--;
             if (!have_work()) return;   // shutting down
         }
         // The slot FIRST, the batch second: while every I/O slot is busy, requests keep accumulating in the open batch
@@ -1419,8 +1422,9 @@ int submit(lb2_ctx* ctx, int kind, const uint32_t* planes, const uint8_t* rot, i
         open->req.push_back(QueueRequest{out, n, cb, user});
         break;
     }
+    const bool wake = ctx->q_idle_workers > 0;   // dispatchers that are busy (or waiting for a slot) look at the queue again by themselves
     lk.unlock();
-    ctx->q_cv.notify_one();
+    if (wake) ctx->q_cv.notify_one();
     return LB2_OK;
 }
 

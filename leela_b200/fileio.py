@@ -87,8 +87,13 @@ def read_outputs(path) -> RefOutputs:
     return RefOutputs(temp, pol, val, pavg, vavg)
 
 
-def write_weights(path, nets) -> None:
+def write_weights(path, nets, kat=None) -> None:
     """Weights file of the drop-in engine (engine/network_b200.cpp:load_weights), "LB2WGT01".
+
+    `kat` (optional): known answers the engine checks at start-up, as the reference's OpenCL self-test does for its own
+    weights (GTP.cpp:105-125): {"policy": [(netresult index, vertex, probability), ...], "value": winrate} for
+    Network::get_scored_moves(DIRECT, 0) / get_value(DIRECT, 0) on the empty 19x19 board — written as a trailer
+    "LB2KAT01", count, {int32 index, int32 vertex, float32 p} x count, float32 value.
 
     `nets`: {kind: NetWeights} with kind 0 = policy, 1 = value. Per net: the conv arrays in OIHW
     order with their biases, then the inner products [n_out][n_in] — the layout of the reference's
@@ -107,6 +112,13 @@ def write_weights(path, nets) -> None:
                 f.write(np.array([p.n_in, p.n_out], dtype=np.int32).tobytes())
                 f.write(np.ascontiguousarray(pw, dtype=np.float32).tobytes())
                 f.write(np.ascontiguousarray(pb, dtype=np.float32).tobytes())
+        if kat:
+            f.write(b"LB2KAT01")
+            f.write(np.array([len(kat["policy"])], dtype=np.int32).tobytes())
+            for index, vertex, prob in kat["policy"]:
+                f.write(np.array([index, vertex], dtype=np.int32).tobytes())
+                f.write(np.array([prob], dtype=np.float32).tobytes())
+            f.write(np.array([kat["value"]], dtype=np.float32).tobytes())
 
 
 @dataclasses.dataclass

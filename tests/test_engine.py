@@ -70,11 +70,18 @@ def test_weights_file_round_trip(tmp_path):
     assert raw.size == 8 + 4 * (n_floats + n_ints)
     first = raw[8 + 4 * (1 + 3 + 3):][:4 * pw.conv_w[0].size].view(np.float32)
     np.testing.assert_array_equal(first, pw.conv_w[0].ravel())
+    # with the known-answer trailer the engine's start-up self-test reads
+    from engine import build as eb
+    kat = eb.synth_kat()
+    assert len(kat["policy"]) == 3 and all(0 < p < 1 for _, _, p in kat["policy"]) and kat["policy"][0][1] == kat["policy"][0][0] % 19 + 1 + (kat["policy"][0][0] // 19 + 1) * 21
+    fileio.write_weights(path, {0: pw, 1: vw}, kat=kat)
+    raw2 = np.fromfile(path, dtype=np.uint8)
+    assert raw2.size == raw.size + 8 + 4 + 3 * 12 + 4 and raw2[raw.size:raw.size + 8].tobytes() == b"LB2KAT01"
 
 
-def gtp(commands, *args, timeout=600):
+def gtp(commands, *args, timeout=600, prefix=()):
     script = "\n".join(commands + ["quit"]) + "\n"
-    r = subprocess.run([ENGINE, "-g", "--noponder", "--nobook", "--weights", WEIGHTS, *args], input=script,
+    r = subprocess.run([*prefix, ENGINE, "-g", "--noponder", "--nobook", "--weights", WEIGHTS, *args], input=script,
                        capture_output=True, text=True, timeout=timeout)
     assert r.returncode == 0, r.stderr[-2000:]
     return r.stdout, r.stderr
@@ -100,16 +107,53 @@ def test_gtp_heatmap_and_winrate_match_reference_api_golden(ref_golden):
 @pytest.mark.gpu
 @needs_engine
 def test_gtp_search_uses_batched_leaf_queue():
-    out, err = gtp(["boardsize 19", "clear_board", "komi 7.5", "genmove b", "genmove w", "showboard"],
-                   "-t", "48", "-p", "3000", "--max-outstanding", "4", "--mature_threshold", "1", "--eval_thresh", "0")
+    """128 search threads (most of them asleep waiting for an evaluation at any time), the net-frequency knobs at their
+    most eager: requests of different threads share device batches. How full the batches get depends on the host: the
+    search spends its time in CPU playouts and asks for only a few thousand evaluations per second, and an idle device takes
+    a request at once (lowest latency) — on 16 cores the mean device batch is 21-24, on a 100-core box 1.4. The engine is
+    therefore held to 8 cores here (taskset), which makes the measured 8-16 reproducible; the floor asserted is 4."""
+    import shutil
+    cores = sorted(os.sched_getaffinity(0))[:8]
+    prefix = (shutil.which("taskset"), "-c", ",".join(map(str, cores))) if shutil.which("taskset") else ()
+    out, err = gtp(["boardsize 19", "clear_board", "komi 7.5", "time_settings 0 2 1", "genmove b", "genmove w", "showboard"],
+                   "-t", "128", "--lagbuffer", "0", "--max-outstanding", "8", "--mature_threshold", "1", "--eval_thresh", "0", prefix=prefix)
     moves = re.findall(r"^= ([A-T]\d+)\s*$", out, flags=re.M)
     assert len(moves) == 2 and moves[0] != moves[1], out
     stats = re.findall(r"(\d+) visits, (\d+) nodes, (\d+) playouts, (\d+) p/s", err)
-    assert len(stats) == 2 and all(int(s[2]) >= 3000 for s in stats), err[-1500:]
+    assert len(stats) == 2 and all(int(s[2]) >= 1000 for s in stats), err[-1500:]
     m = re.search(r"B200 evaluator: (\d+) positions in (\d+) device batches \(mean batch ([\d.]+)\)", err)
     assert m, err[-1500:]
-    assert int(m.group(1)) > 100            # the nets were consulted
-    assert int(m.group(1)) > int(m.group(2))   # requests of different search threads shared device batches
+    assert int(m.group(1)) > 1000           # the nets were consulted
+    assert float(m.group(3)) >= (4.0 if prefix else 1.2), m.group(0)   # requests of different search threads shared device batches
+
+
+@pytest.mark.gpu
+@needs_engine
+def test_engine_self_test_and_netbench():
+    """Start-up known-answer test (the reference's GTP.cpp:105-125 for this evaluator: the weights file carries what the
+    reference's CPU path answers on the empty board) and the GTP `netbench` command (Network::benchmark, Network.cpp:147-199)."""
+    out, err = gtp(["boardsize 19", "clear_board", "netbench"], "-t", "64")
+    assert "B200 self-test: passed." in err, err[-1500:]
+    legs = dict((what, (int(n), float(sec), int(ps))) for n, what, sec, ps in
+                re.findall(r"(\d+) (predictions|evaluations) in\s+([\d.]+) seconds -> (\d+) p/s", err))
+    assert set(legs) == {"predictions", "evaluations"}, err[-1500:]
+    assert legs["predictions"][0] >= 100000 and legs["evaluations"][0] >= 500000
+    # the reference's CPU path does ~1.2 k predictions/s and ~3.3 k evaluations/s on 16 cores (profiles/README.md)
+    assert legs["predictions"][2] > 20000 and legs["evaluations"][2] > 20000, legs
+    m = re.search(r"B200 evaluator: (\d+) positions in (\d+) device batches \(mean batch ([\d.]+)\)", err)
+    assert m and float(m.group(3)) >= 6.0, err[-800:]
+    assert re.search(r"feature planes: [\d.]+ us per position", err)
+    # a weights file whose known answers are wrong must stop the engine
+    import tempfile
+    from leela_b200 import synth
+    from engine import build as eb
+    kat = eb.synth_kat()
+    kat["policy"][0] = (kat["policy"][0][0], kat["policy"][0][1], kat["policy"][0][2] + 0.05)
+    with tempfile.TemporaryDirectory() as d:
+        bad = os.path.join(d, "bad.lb2w")
+        fileio.write_weights(bad, {0: synth.policy_weights(), 1: synth.value_weights()}, kat=kat)
+        r = subprocess.run([ENGINE, "-g", "--noponder", "--nobook", "--weights", bad], input="quit\n", capture_output=True, text=True, timeout=300)
+        assert r.returncode != 0 and "self-test: failed" in r.stderr
 
 
 @pytest.mark.gpu
