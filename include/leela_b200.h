@@ -185,6 +185,9 @@ int lb2_device_count(lb2_ctx* ctx);
  *                 Lite and full cannot be mixed between the two nets. May be switched between calls.
  *   "precise":    shorthand: 1 = both nets full (2, 2); 0 = the default (0, 1).
  *   "policy_clusters": resident mode: clusters that start on the policy net (-1 = split by estimated work)
+ *   "group_positions": net-major launches (resident_weights) run the batch in groups of this many positions — all layers of
+ *                 the first group, then of the next — so that the live activations fit in L2. A multiple of 128, 0 = off
+ *                 (default: at batch 256 groups of 128 cut the HBM write-back from 389 to 94 MB per launch but cost 5 % time)
  *   "use_graphs": 1 = from the second use of a batch shape on, its kernels (expand, trunk, heads) are launched as one
  *                 cached CUDA graph (default); 0 = always as separate launches
  *   "spin_wait":  1 = a blocking call polls for its results, yielding the core between polls (default); 0 = it sleeps

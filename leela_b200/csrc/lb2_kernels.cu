@@ -160,6 +160,12 @@ __device__ __forceinline__ void dependency_range(const LayerJob& J, int tile, in
         hi = ((p_hi + 1) * 441 - 1) / kTileRows;
     }
     if (hi > J.dep_n_items - 1) hi = J.dep_n_items - 1;
+    if (J.group_tiles) {
+        // Position groups: the rows behind a group's last position belong to the next group, which is scheduled later. Only
+        // outputs in this group's padding rows would read them, so the tile need not (and, in-order claiming, must not) wait.
+        const int cap = (tile / J.group_tiles + 1) * J.dep_group_tiles - 1;
+        if (hi > cap) hi = cap;
+    }
 }
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -198,6 +204,7 @@ __device__ __forceinline__ void locate_item(const TrunkParams& P, const LayerJob
     while (q >= P.round_base[r + 1]) r++;
     int local = q - P.round_base[r];
     const int first = P.round_first[r], m = P.round_jobs[r];
+    if (m == 1) { job = first; idx = P.round_idx0[r] + local; return; }   // net-major order: a slice of one job
     int done = 0;   // cycles dealt so far
     for (;;) {
         int active = 0, shortest = 0x7fffffff;

@@ -60,7 +60,8 @@ static_assert(kTrunkSmemBytesRes <= 227 * 1024, "resident-weights trunk shared m
 constexpr int kMaxLayers = 16;
 constexpr int kMaxTensorMaps = 6;
 constexpr int kMaxJobs = 40;
-constexpr int kMaxRounds = 40;  // a round = the jobs of equal depth (all nets, all column splits); their items are interleaved
+constexpr int kMaxRounds = 104;  // a round = the jobs of equal depth (all nets, all column splits), their items interleaved; or, in
+                                // net-major order, one position group of one layer ((12 + 11 layers) x up to 4 groups)
 constexpr int kMaxRoundJobs = 2 * kMaxSplit;
 constexpr int kTraceItems = 96;
 constexpr int kTraceEvents = 16;
@@ -102,6 +103,9 @@ struct LayerJob {
     int32_t lo_chunks;       // chunk planes of the OUTPUT buffer in front of the extra planes this job's epilogue stores
     int16_t term_base[3];    // virtual slab v = term * n_real_slabs + s reads input chunk planes term_base[term] + 2 s
     int16_t n_f16_slabs;     // virtual slabs [0, n_f16_slabs) are kind::f16 MMAs, the rest kind::f8f6f4
+    int32_t group_tiles;     // net-major order runs the batch in position groups (all layers of group 0, then of group 1, ...) so that
+    int32_t dep_group_tiles; // the live activations fit in L2: 256-row tiles per group of this job / of the producing job (0 = one group).
+                             // A group's last tile does not wait for the next group's first one (it would read only padding rows of it)
     int32_t out_mode;        // what the epilogue stores besides the fp16 activations (for the consuming layer):
                              //   kOutPlain nothing, kOutLo16 the fp16 residual planes (precise consumer),
                              //   kOutFp8 per 16 channels one e4m3 plane of the activations and one of the residual x 2^12
@@ -123,6 +127,7 @@ struct TrunkParams {
     int32_t n_rounds;
     int32_t round_base[kMaxRounds + 1];             // first item index of each round
     int16_t round_first[kMaxRounds], round_jobs[kMaxRounds];  // its jobs: round_jobs consecutive entries of the job table
+    int16_t round_idx0[kMaxRounds];                 // single-job rounds: the round covers items [idx0, idx0 + its length) of the job
     // Per-device scheduler words, reset by the expand kernel at the start of every evaluation (so that a launch does not
     // depend on its history and can be replayed from a CUDA graph): [0] in-order claim counter over all items, [1 + net] the
     // per-net claim counters of the resident-weights mode, [kSchedEpoch] the flag epoch of the evaluation.

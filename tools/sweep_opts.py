@@ -29,12 +29,9 @@ def timed(tag, steps=60):
     print("%-40s %.1f us/step  %.0f pos/s" % (tag, best, B / best * 1e6), flush=True)
     return best
 timed("default")
-for pc in (30, 34, 38, 40, 42, 44, 46, 50):
-    ev.set_option("policy_clusters", pc); timed(f"policy_clusters {pc}")
-ev.set_option("policy_clusters", -1)
-for mb in (64, 128, 192, 256):
-    ev.set_option("max_batch", mb); timed(f"max_batch {mb}")
-ev.set_option("max_batch", 256)
-ev.set_option("resident_weights", 0); timed("resident_weights 0"); ev.set_option("resident_weights", 2)
-ev.set_option("use_graphs", 0); timed("use_graphs 0"); ev.set_option("use_graphs", 1)
-ev.set_precision(0, 0); timed("precision (0, 0)")
+for gp in (0, 128, 0, 128):
+    ev.set_option("group_positions", gp); timed(f"group_positions {gp}", steps=200)
+ev.set_option("resident_weights", 0); timed("resident_weights 0", steps=200); ev.set_option("resident_weights", 2)
+ev.set_precision(0, 0)
+for gp in (0, 128):
+    ev.set_option("group_positions", gp); timed(f"fp16/fp16 group_positions {gp}", steps=200)
