@@ -603,6 +603,12 @@ JobPlan plan_jobs(DeviceState* d, const bool run[2], int n, const int limit_laye
                     J.dep_remap = pl.jobs[J.dep_job].remap;
                     J.dep_n_items = pl.tiles[J.dep_job];
                 }
+                // the input tiles of this layer are dead once read: which planes the publisher may drop from L2
+                if (l > 0 && t.n_split == 1 && nd.trunk[l - 1].n_split == 1) {
+                    J.in_base = nd.act[(l - 1) & 1];
+                    J.in_chunk_rows = nd.rows3;
+                    J.in_planes = t.c_in / 8 * (mode == kPrecFp16 ? 1 : 2);
+                }
                 J.n_pos = n;
                 J.net = k;
                 J.layer = (int)l;

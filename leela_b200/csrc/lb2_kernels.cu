@@ -57,6 +57,12 @@ constexpr int kEpiGroup = LB2_EPI_GROUP;
                                   // c_out <= 64 only) and the epilogue adds the two sums; 0 = straight onto the fp16 sum. kind::f8f6f4
                                   // adds an addend 2^-24 of the accumulator exactly (tools/mma_mixed_test.cu) and the results are
                                   // the same either way (value max 9.3e-5), so: 0
+#ifndef LB2_DISCARD_DEAD
+#define LB2_DISCARD_DEAD 0   // 1: the tile publisher drops activation tiles nobody will read again from L2 (discard.global.L2) instead of
+                             // letting them be written back. Correct (tests, soak) and useless: DRAM write-back 389 -> 361 MB per launch,
+                             // launch time unchanged — with ~105 MB of live activations the lines are evicted (and written back)
+                             // long before their last reader is done. Off.
+#endif
 #ifndef LB2_EPI_PIPE
 #define LB2_EPI_PIPE 1    // epilogue keeps the TMEM loads of the next two units in flight
 #endif
@@ -584,7 +590,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             const int upc = cols >> 3;            // 8-column units per 128-row half tile
             const int n_units = (kDebugFlags(P) & 64) ? 0 : 2 * upc;
             // this thread's row in each of the two half tiles
-            int out_row2[2]; bool valid2[2];
+            int out_row2[2]; bool valid2[2], skip2[2];   // skip: a row of the S = 21 space with no counterpart in the S = 20 space
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int row = tile * kTileRows + h * 128 + quad * 32 + lane;
@@ -593,6 +599,10 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                 else      { pos = row / 400; const int rem = row - pos * 400; y = rem / 20; x = rem - y * 20; }
                 valid2[h] = (x < kBoard) && (y < kBoard) && (!remap || pos < n_pos);
                 out_row2[h] = remap ? pos * 400 + y * 20 + x : row;
+                // Layer 1 re-addresses S = 21 rows into the S = 20 space: (x, y) <= 19 exist there, and the ones with x == 19 or
+                // y == 19 are its zero padding — written here as well (as every other layer does for its own padding rows), so
+                // that no launch relies on zeros an earlier launch left behind (dead activation tiles are discarded from L2).
+                skip2[h] = remap && (x > kBoard || y > kBoard || pos >= n_pos);
             }
             const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256 + col0;
             // unit -> (half, column block). The fused-head path walks half-major; the ordinary path pairs the halves
@@ -637,11 +647,11 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             auto store_unit = [&](const uint32_t (&r)[8], int u, const float4& b0, const float4& b1) {
                 const int h = unit_half(u);
                 const int cc = unit_col(u);
-                const bool valid = h ? valid2[1] : valid2[0];
+                const bool valid = h ? valid2[1] : valid2[0], skip = h ? skip2[1] : skip2[0];
                 const int out_row = h ? out_row2[1] : out_row2[0];
                 float v[8];
                 activate_b(r, unit_addr2(u), b0, b1, v);
-                if (valid || !remap) {
+                if (!skip) {
                     uint32_t pk[4], pl[4];
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
@@ -669,7 +679,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             // the consumer's correction MMAs need, per 16 channels, one 16-byte row of e4m3(a) and one of e4m3((a - fp16(a)) * 2^12):
             // chunk planes lo_chunks + 2 * (channel / 16) and the one behind it.
             auto store_pair_fp8 = [&](const uint32_t (&r)[2][8], int h, int cc) {
-                const bool valid = h ? valid2[1] : valid2[0];
+                const bool valid = h ? valid2[1] : valid2[0], skip = h ? skip2[1] : skip2[0];
                 const int out_row = h ? out_row2[1] : out_row2[0];
                 uint32_t qa[4], ql[4];
 #pragma unroll
@@ -693,13 +703,13 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
 #endif
                     qa[2 * g] = valid ? (q8[0] | (q8[1] << 16)) : 0u; qa[2 * g + 1] = valid ? (q8[2] | (q8[3] << 16)) : 0u;
                     ql[2 * g] = valid ? (q9[0] | (q9[1] << 16)) : 0u; ql[2 * g + 1] = valid ? (q9[2] | (q9[3] << 16)) : 0u;
-                    if (valid || !remap) {
+                    if (!skip) {
                         __half* ph = out + ((size_t)((col0 + cc) / 8 + g) * chunk_rows + out_row) * 8;
                         if (LB2_L2_HINTS) st_global_v4_hint(ph, make_uint4(pk[0], pk[1], pk[2], pk[3]), st_policy);
                         else *reinterpret_cast<uint4*>(ph) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
                 }
-                if (valid || !remap) {
+                if (!skip) {
                     __half* pa = out + ((size_t)(lo_chunks + 2 * ((col0 + cc) >> 4)) * chunk_rows + out_row) * 8;
                     __half* pl = pa + (size_t)chunk_rows * 8;
                     if (LB2_L2_HINTS) {
@@ -856,15 +866,45 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         // epilogue's critical path. One lane: wait until all 8 epilogue warps stored tile `it`,
         // then release its flag for the consumers' acquire (cumulative over the mbarrier sync).
         // Its progress counter also bounds how far ahead the scout hands out items.
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int jj, idx; item_get<true>(item_ring, it, jj, idx); it++) {
-                mbar_wait(pub_bar + (it % kPubDepth), (it / kPubDepth) & 1);
-                LB2_TRACE(it, 11);
-                if (P.use_flags) {
-                    fence_proxy_async();  // generic-proxy stores -> visible to other CTAs' TMA loads
-                    st_release_gpu(jobs[jj].flags + tile_of(idx), epoch);
+        // Before the release it drops dead activation tiles from L2 (discard.global.L2: no write-back): input tile c of this
+        // layer is dead once the three tiles that read it (c - 1, c, c + 1 of this layer) are complete, and nothing writes its
+        // rows before the next layer's tile c, which waits for exactly those three flags. Whoever completes the last of the
+        // three — judged before publishing its own flag — discards: so every discard happens-before the flag release that
+        // lets the rows be overwritten, and two neighbours finishing together at worst both leave the tile alone. Without
+        // this most of a layer's output was written back to HBM after its last read (389 MB per launch at batch 256).
+        uint32_t it = 0;
+        for (int jj, idx; item_get<true>(item_ring, it, jj, idx); it++) {
+            if (lane == 0) mbar_wait(pub_bar + (it % kPubDepth), (it / kPubDepth) & 1);
+            __syncwarp();
+            if (lane == 0) LB2_TRACE(it, 11);
+            if (P.use_flags) {
+                const LayerJob& J = jobs[jj];
+                const int T = tile_of(idx);
+                if (LB2_DISCARD_DEAD && J.in_planes) {
+                    const int n_tiles = kPair ? 2 * J.n_items : J.n_items;
+                    // lanes 0..4 look at tiles T - 2 .. T + 2. T itself counts as complete, and so does the peer CTA's tile of the
+                    // same item (T ^ 1): the item's MMAs — the last readers of its input — were complete before either epilogue ran.
+                    const int t = T - 2 + lane;
+                    const bool done = lane < 5 && (t == T || (kPair && t == (T ^ 1)) || t < 0 || t >= n_tiles || ld_acquire_gpu(J.flags + t) == epoch);
+                    const uint32_t mask = __ballot_sync(0xffffffffu, done);   // bit i: tile T - 2 + i complete (or outside)
+                    // this CTA looks after its own input tile and the neighbour on the far side of its peer
+                    const int c_lo = kPair ? (rank == 0 ? T - 1 : T) : T - 1, c_hi = kPair ? (rank == 0 ? T : T + 1) : T + 1;
+                    for (int c = c_lo; c <= c_hi; c++) {
+                        if (c < 0 || c >= n_tiles) continue;
+                        const int b = c - (T - 2);   // bit of tile c; its readers are bits b - 1, b, b + 1
+                        if (((mask >> (b - 1)) & 7u) != 7u) continue;
+                        // 256 rows x 16 bytes = 32 lines of 128 bytes per chunk plane
+                        const char* base = reinterpret_cast<const char*>(J.in_base) + (size_t)c * kTileRows * 16 + lane * 128;
+                        for (int p = 0; p < J.in_planes; p++) discard_l2_128(base + (size_t)p * J.in_chunk_rows * 16);
+                    }
+                    __syncwarp();
                 }
+                if (lane == 0) {
+                    fence_proxy_async();  // generic-proxy stores -> visible to other CTAs' TMA loads
+                    st_release_gpu(J.flags + T, epoch);
+                }
+            }
+            if (lane == 0) {
                 LB2_TRACE(it, 12);
                 *pub_done = it + 1;
             }

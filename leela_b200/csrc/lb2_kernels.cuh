@@ -45,7 +45,7 @@ constexpr int kRingBytesPair = kStagesPair * kStageBytesPair;         // 178,176
 constexpr int kTrunkRingBytes = kRingBytesSingle > kRingBytesPair ? kRingBytesSingle : kRingBytesPair;
 // ring | mbarriers etc. | bias [jobs][128] f32 | fused-head weights [kHeadSlots][9][128] f32 | job table
 constexpr int kCtrlBytes = 384;  // mbarriers, TMEM slot, progress counters, claim ring
-constexpr int kTrunkSmemBytes = kTrunkRingBytes + kCtrlBytes + kMaxLaunchJobs * 128 * 4 + kHeadSlots * 9 * 128 * 4 + kMaxLaunchJobs * 176;
+constexpr int kTrunkSmemBytes = kTrunkRingBytes + kCtrlBytes + kMaxLaunchJobs * 128 * 4 + kHeadSlots * 9 * 128 * 4 + kMaxLaunchJobs * 192;
 static_assert(kTrunkSmemBytes <= 227 * 1024, "trunk kernel shared memory");
 // Resident-weights mode (CTA pairs only): a CTA keeps ITS half of the whole layer's packed weights in
 // shared memory and re-uses it for every item of that layer it processes; the pipeline stages then
@@ -55,7 +55,7 @@ constexpr int kStagesRes = 5;
 constexpr int kResJobs = 24;        // jobs per launch in this mode (no column splits)
 constexpr int kResHeadSlots = 2;    // one fused-head weight set per net
 constexpr int kTrunkSmemBytesRes = kResWeightBytes + kStagesRes * kASlabBytes + kCtrlBytes + kResJobs * 128 * 4 +
-                                   kResHeadSlots * 9 * 128 * 4 + kResJobs * 176;
+                                   kResHeadSlots * 9 * 128 * 4 + kResJobs * 192;
 static_assert(kTrunkSmemBytesRes <= 227 * 1024, "resident-weights trunk shared memory");
 constexpr int kMaxLayers = 16;
 constexpr int kMaxTensorMaps = 6;
@@ -115,6 +115,9 @@ struct LayerJob {
     const float* bias;       // [n_out]
     __half* out;             // output activation buffer
     uint32_t* flags;         // [n_items] completion flags (value = launch epoch)
+    const __half* in_base;   // input buffer, for discarding dead tiles: in_planes chunk planes of in_chunk_rows rows each are dropped
+    int32_t in_chunk_rows;   // from L2 once every tile of this layer that reads them is complete (0 planes = never: the first
+    int32_t in_planes;       // layer's x0, column-split layers, per-layer launches)
     const float* head_w;     // fused head weights [9 taps][n_out] fp32
     float* zbuf;             // fused head output [splits * kColParts channel parts][9 taps][out_chunk_rows] fp32
 };
@@ -186,4 +189,4 @@ const void* kernel_address(int which);   // 0 expand, 1 heads, 2 ensemble mean
 
 }  // namespace lb2
 static_assert(sizeof(lb2::TrunkParams) < 32000, "kernel parameter space");
-static_assert(sizeof(lb2::LayerJob) <= 176 && sizeof(lb2::LayerJob) % 4 == 0, "job table slot size");
+static_assert(sizeof(lb2::LayerJob) <= 192 && sizeof(lb2::LayerJob) % 4 == 0, "job table slot size");

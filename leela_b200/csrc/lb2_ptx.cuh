@@ -164,6 +164,12 @@ __device__ __forceinline__ void st_global_v4_hint(void* ptr, uint4 v, uint64_t p
                  : "memory");
 }
 
+// drop a 128-byte line from L2 without writing it back: its contents are undefined until written again (a weak write in
+// the memory model, so a later release orders it)
+__device__ __forceinline__ void discard_l2_128(const void* p) {
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -295,9 +295,16 @@ def test_resident_weights_mode_bit_identical(ev, ref_golden, bench_positions):
         ev.set_option("policy_clusters", -1)
         assert np.array_equal(ev.eval_policy(cases[1][0], cases[1][2], TEMP), want_p)
         assert np.array_equal(ev.eval_value(cases[2][1], cases[2][2]), want_v)
+        # position groups (all layers of the first 128 positions, then of the next): another item order, the same bits
+        ev.set_option("resident_weights", 2)
+        ev.set_option("group_positions", 128)
+        for c, w in zip(cases, want):
+            p, v = ev.eval_both(*c, TEMP)
+            assert np.array_equal(p, w[0]) and np.array_equal(v, w[1])
     finally:
         ev.set_option("resident_weights", 2)
         ev.set_option("policy_clusters", -1)
+        ev.set_option("group_positions", 0)
 
 
 def test_cta_pair_and_single_cta_bit_identical(ev, ref_golden):

@@ -29,7 +29,7 @@ def timed(tag, steps=60):
     print("%-40s %.1f us/step  %.0f pos/s" % (tag, best, B / best * 1e6), flush=True)
     return best
 timed("default")
-for gp in (0, 128, 0, 128):
+for gp in (0,):
     ev.set_option("group_positions", gp); timed(f"group_positions {gp}", steps=200)
 ev.set_option("resident_weights", 0); timed("resident_weights 0", steps=200); ev.set_option("resident_weights", 2)
 ev.set_precision(0, 0)
