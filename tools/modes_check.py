@@ -1,4 +1,4 @@
-"""Bring-up of the lite precision mode: value net alone under every launch form, determinism, per-layer probe."""
+"""Every precision mode under every launch form (graphs, resident weights, per-layer launches, single CTA): value and policy error, run-to-run determinism, per-layer probe of the stored activations."""
 import sys, os, numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

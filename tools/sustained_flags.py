@@ -1,4 +1,5 @@
-"""Sustained (seconds-long, power-capped) trunk time at batch 256 under LB2_DEBUG_FLAGS variants: how much of
+"""(Needs a debug build: python -c "from leela_b200 import build; build.build(force=True, defines=['LB2_DEBUG_KNOBS'], out='tools/_variants/liblb2_dbg.so')" and LB2_LIB=tools/_variants/liblb2_dbg.so — the product library compiles the timing knobs out.)
+Sustained (seconds-long, power-capped) trunk time at batch 256 under LB2_DEBUG_FLAGS variants: how much of
 the launch each component costs once the 1000 W cap, not the schedule, sets the pace. Results are wrong under
 the flags; only the time matters. Usage (GPU box): python tools/sustained_flags.py [steps]"""
 import os, subprocess, sys
