@@ -63,6 +63,9 @@ constexpr int kEpiGroup = LB2_EPI_GROUP;
                              // launch time unchanged — with ~105 MB of live activations the lines are evicted (and written back)
                              // long before their last reader is done. Off.
 #endif
+#ifndef LB2_PACKED_F32
+#define LB2_PACKED_F32 1    // epilogue arithmetic in packed fp32 pairs (FFMA2 / FADD2 / FMUL2): the same bits at fewer issue slots
+#endif
 #ifndef LB2_EPI_PIPE
 #define LB2_EPI_PIPE 1    // epilogue keeps the TMEM loads of the next two units in flight
 #endif
@@ -198,6 +201,19 @@ __device__ __forceinline__ float elu_fast(float v) {
     float e;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 1.4426950408889634f));  // inf for large v is clamped by the min
     return fmaxf(v, fminf(e - 1.0f, 0.0f));  // v>0: e-1>0 -> max(v,0)=v; v<=0: e-1 in (-1,0] and e-1 >= v
+}
+
+// the same for two values with packed fp32 instructions (FMUL2, FADD2): identical bits, fewer issue slots
+__device__ __forceinline__ void elu_fast2(float& a, float& b) {
+    const f32x2 t = mul2(pack2(a, b), pack2(1.4426950408889634f, 1.4426950408889634f));
+    float ta, tb, ea, eb;
+    unpack2(t, ta, tb);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(ta));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(tb));
+    float ma, mb;
+    unpack2(add2(pack2(ea, eb), pack2(-1.0f, -1.0f)), ma, mb);
+    a = fmaxf(a, fminf(ma, 0.0f));
+    b = fmaxf(b, fminf(mb, 0.0f));
 }
 
 // Item index -> (job, item within the job). Rounds are consecutive in the launch-wide order; inside
@@ -628,17 +644,39 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                             printf("it %u job %d: main %g corr %g sc %g n_f16 %d n_slabs %d\n", it, jj, __uint_as_float(r[0]), __uint_as_float(c[0]), sc, (int)J.n_f16_slabs, J.n_slabs);
 #endif
                     }
+#if LB2_PACKED_F32
+                    const f32x2 sc2 = pack2(sc, sc);
+                    f32x2 p[4] = {fma2(pack2(a[0], a[1]), sc2, pack2(b0.x, b0.y)), fma2(pack2(a[2], a[3]), sc2, pack2(b0.z, b0.w)),
+                                  fma2(pack2(a[4], a[5]), sc2, pack2(b1.x, b1.y)), fma2(pack2(a[6], a[7]), sc2, pack2(b1.z, b1.w))};
+#pragma unroll
+                    for (int e = 0; e < 4; e++) unpack2(p[e], v[2 * e], v[2 * e + 1]);
+#else
                     v[0] = fmaf(a[0], sc, b0.x); v[1] = fmaf(a[1], sc, b0.y); v[2] = fmaf(a[2], sc, b0.z); v[3] = fmaf(a[3], sc, b0.w);
                     v[4] = fmaf(a[4], sc, b1.x); v[5] = fmaf(a[5], sc, b1.y); v[6] = fmaf(a[6], sc, b1.z); v[7] = fmaf(a[7], sc, b1.w);
+#endif
                 } else {
+#if LB2_PACKED_F32
+                    f32x2 p[4] = {add2(pack2(__uint_as_float(r[0]), __uint_as_float(r[1])), pack2(b0.x, b0.y)),
+                                  add2(pack2(__uint_as_float(r[2]), __uint_as_float(r[3])), pack2(b0.z, b0.w)),
+                                  add2(pack2(__uint_as_float(r[4]), __uint_as_float(r[5])), pack2(b1.x, b1.y)),
+                                  add2(pack2(__uint_as_float(r[6]), __uint_as_float(r[7])), pack2(b1.z, b1.w))};
+#pragma unroll
+                    for (int e = 0; e < 4; e++) unpack2(p[e], v[2 * e], v[2 * e + 1]);
+#else
                     v[0] = __uint_as_float(r[0]) + b0.x; v[1] = __uint_as_float(r[1]) + b0.y;
                     v[2] = __uint_as_float(r[2]) + b0.z; v[3] = __uint_as_float(r[3]) + b0.w;
                     v[4] = __uint_as_float(r[4]) + b1.x; v[5] = __uint_as_float(r[5]) + b1.y;
                     v[6] = __uint_as_float(r[6]) + b1.z; v[7] = __uint_as_float(r[7]) + b1.w;
+#endif
                 }
                 if (!(kDebugFlags(P) & 4)) {
+#if LB2_PACKED_F32
+#pragma unroll
+                    for (int e = 0; e < 4; e++) elu_fast2(v[2 * e], v[2 * e + 1]);
+#else
 #pragma unroll
                     for (int e = 0; e < 8; e++) v[e] = elu_fast(v[e]);
+#endif
                 }
             };
             // ordinary layer: pack to fp16 and store one 16-byte chunk row. Padding rows/columns of
@@ -695,7 +733,13 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                         pk[e] = valid ? *reinterpret_cast<uint32_t*>(&hh) : 0u;
                         const float2 hf = __half22float2(hh);
                         q8[e] = cvt_e4m3x2(v[2 * e], v[2 * e + 1]);
+#if LB2_PACKED_F32
+                        float d0, d1;   // (v - hi) * 2^12, exact
+                        unpack2(mul2(add2(pack2(v[2 * e], v[2 * e + 1]), pack2(-hf.x, -hf.y)), pack2(kLoScale, kLoScale)), d0, d1);
+                        q9[e] = cvt_e4m3x2(d0, d1);
+#else
                         q9[e] = cvt_e4m3x2((v[2 * e] - hf.x) * kLoScale, (v[2 * e + 1] - hf.y) * kLoScale);
+#endif
                     }
 #ifdef LB2_DEBUG_KNOBS
                     if ((kDebugFlags(P) & 128) && blockIdx.x == 0 && warp == 2 && lane == 5 && it < 40 && g == 0)

@@ -147,6 +147,32 @@ __device__ __forceinline__ void st_remote_shared(uint32_t* p, uint32_t cta, uint
         : "memory");
 }
 
+// ---------------------------------------------------------------- packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2)
+// One instruction for two IEEE-rn fp32 operations on a 64-bit register pair: the same bits as two scalar instructions at
+// half the issue slots — the epilogue of the trunk kernel is bound by instruction issue, not by the fp32 pipe.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 // ---------------------------------------------------------------- L2 eviction-priority hints
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     uint64_t p;

@@ -12,7 +12,8 @@ def do_build(specs):
     from leela_b200 import build
     os.makedirs(VDIR, exist_ok=True)
     for f in os.listdir(VDIR):
-        os.remove(os.path.join(VDIR, f))
+        if f.endswith(".so"):
+            os.remove(os.path.join(VDIR, f))
     for spec in specs:
         name, _, defs = spec.partition(":")
         defines = [d for d in defs.split(",") if d]
