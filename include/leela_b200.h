@@ -185,6 +185,10 @@ int lb2_device_count(lb2_ctx* ctx);
  *                 Lite and full cannot be mixed between the two nets. May be switched between calls.
  *   "precise":    shorthand: 1 = both nets full (2, 2); 0 = the default (0, 1).
  *   "policy_clusters": resident mode: clusters that start on the policy net (-1 = split by estimated work)
+ *   "small_batch": device passes of up to this many positions (default 48, 0 = never) run every layer of up to 128 channels as
+ *                 two column-split jobs, so that two clusters share an item's MMAs and epilogue: a small pass is bound by the
+ *                 latency of its chained layers, not by throughput (batch 1: 154 -> 131 us, batch 32: 170 -> 159 us; above ~56
+ *                 positions whole layers are faster). Bit-identical.
  *   "group_positions": net-major launches (resident_weights) run the batch in groups of this many positions — all layers of
  *                 the first group, then of the next — so that the live activations fit in L2. A multiple of 128, 0 = off
  *                 (default: at batch 256 groups of 128 cut the HBM write-back from 389 to 94 MB per launch but cost 5 % time)

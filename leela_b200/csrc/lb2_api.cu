@@ -85,19 +85,23 @@ struct HostIp {
     std::vector<float> w, b;
 };
 
-// One trunk layer on a device. A layer wider than 128 output channels is stored (and later run) as
-// n_split column splits of c_out / n_split channels each, every split packed like a layer of its own.
+// One way of cutting a trunk layer into column splits of c_out / n_split channels, every split packed like a layer of its own.
+struct SplitPacks {
+    int n_split = 1;
+    // packed weights [precision: fp16 / lite / full][0 = one CTA per item, 1 = CTA-pair packing][split] (see SlabPacker)
+    __half* w[3][2][lb2::kMaxSplit] = {};
+    float* bias[lb2::kMaxSplit] = {nullptr, nullptr};
+};
+
+// One trunk layer on a device. `nat`: a layer wider than 128 output channels is stored (and run) as two column splits.
+// `small`: layers of up to 128 channels packed as two splits as well, for small batches — a pass over a few positions is bound
+// by the latency of its chained layers (one 256-row item per layer and net, ~12 us each, while most clusters idle); with every
+// layer cut in two, two clusters share an item's MMAs and epilogue. CTA-pair packing only; never the last (fused-head) layer.
 struct TrunkLayerDev {
     int k, c_in, c_out;
-    int n_split = 1;
-    __half* wpk[lb2::kMaxSplit] = {nullptr, nullptr};
-    __half* wpk2[lb2::kMaxSplit] = {nullptr, nullptr};  // CTA-pair packing
-    __half* wpk_x[lb2::kMaxSplit] = {nullptr, nullptr};   // the same two packings for full split-operand precision (virtual
-    __half* wpk2_x[lb2::kMaxSplit] = {nullptr, nullptr};  // slabs, see SlabPacker)
-    __half* wpk_e[lb2::kMaxSplit] = {nullptr, nullptr};   // ... and for lite mode (fp16 slabs scaled by 2^q, then e4m3 correction slabs)
-    __half* wpk2_e[lb2::kMaxSplit] = {nullptr, nullptr};
-    int q = 0;                                            // lite mode: the packed weights carry the factor 2^q
-    float* bias[lb2::kMaxSplit] = {nullptr, nullptr};
+    SplitPacks nat, small;
+    bool has_small = false;
+    int q = 0;   // lite mode: the packed weights carry the factor 2^q
 };
 
 // One net replicated on one device, with its workspace.
@@ -259,6 +263,7 @@ struct lb2_ctx {
                                   // Measured at batch 256 with groups of 128: DRAM write-back per launch 389 -> 94 MB, L2 hit rate 56 -> 74 %,
                                   // and the launch 5 % SLOWER (634 k -> 705 k cycles: 100 items per layer and group leave the clusters waiting
                                   // at every layer transition; HBM traffic was never the limit) -> off
+    long small_batch = 48;        // device passes of up to this many positions run every layer as two column splits (0 = never)
     long spin_wait = 1;    // 1: a blocking call polls its completion event (yielding the core between polls); 0: it sleeps on it
     std::atomic<long> option_epoch{0};   // bumped by lb2_set_option: cached graphs of older epochs are rebuilt
     std::atomic<long> launches{0}, graph_launches{0};
@@ -390,27 +395,31 @@ int upload_net(const lb2_net* net, NetDev* nd) {
         const HostConv& c = net->convs[l];
         TrunkLayerDev t;
         t.k = c.k; t.c_in = c.c_in; t.c_out = c.c_out;
-        t.n_split = n_splits(c.c_out);
         t.q = lite_scale_exponent(c);   // one scale for the whole layer (all column splits)
-        const int w = c.c_out / t.n_split;
-        for (int sp = 0; sp < t.n_split; sp++) {
-            HostConv part;   // output channels [sp*w, (sp+1)*w): a contiguous block of the OIHW array
-            part.k = c.k; part.c_in = c.c_in; part.c_out = w;
-            const size_t per_out = (size_t)c.c_in * c.k * c.k;
-            part.w.assign(c.w.begin() + (size_t)sp * w * per_out, c.w.begin() + (size_t)(sp + 1) * w * per_out);
-            part.b.assign(c.b.begin() + sp * w, c.b.begin() + (sp + 1) * w);
-            const bool first = (l == 0);
-            struct { int mode; bool pair; __half** dst; } packs[] = {
-                {kPrecFp16, false, &t.wpk[sp]}, {kPrecFp16, true, &t.wpk2[sp]}, {kPrecFull, false, &t.wpk_x[sp]},
-                {kPrecFull, true, &t.wpk2_x[sp]}, {kPrecLite, false, &t.wpk_e[sp]}, {kPrecLite, true, &t.wpk2_e[sp]}};
-            int rc = LB2_OK;
-            for (auto& p : packs) {
-                std::vector<__half> pk = pack_trunk_weights(part, p.mode, first, t.q, p.pair);
-                if ((rc = upload(p.dst, pk.data(), pk.size() * sizeof(__half)))) return rc;
+        const bool first = (l == 0);
+        auto pack_splits = [&](SplitPacks& sp_set, int n_split, bool pair_only) -> int {
+            sp_set.n_split = n_split;
+            const int w = c.c_out / n_split;
+            for (int sp = 0; sp < n_split; sp++) {
+                HostConv part;   // output channels [sp*w, (sp+1)*w): a contiguous block of the OIHW array
+                part.k = c.k; part.c_in = c.c_in; part.c_out = w;
+                const size_t per_out = (size_t)c.c_in * c.k * c.k;
+                part.w.assign(c.w.begin() + (size_t)sp * w * per_out, c.w.begin() + (size_t)(sp + 1) * w * per_out);
+                part.b.assign(c.b.begin() + sp * w, c.b.begin() + (sp + 1) * w);
+                int rc = LB2_OK;
+                for (int mode = 0; mode < 3; mode++)
+                    for (int pair = pair_only ? 1 : 0; pair < 2; pair++) {
+                        std::vector<__half> pk = pack_trunk_weights(part, mode, first, t.q, pair != 0);
+                        if ((rc = upload(&sp_set.w[mode][pair][sp], pk.data(), pk.size() * sizeof(__half)))) return rc;
+                    }
+                if ((rc = upload(&sp_set.bias[sp], part.b.data(), part.b.size() * sizeof(float)))) return rc;
             }
-            rc = upload(&t.bias[sp], part.b.data(), part.b.size() * sizeof(float));
-            if (rc) return rc;
-        }
+            return LB2_OK;
+        };
+        int rc = pack_splits(t.nat, n_splits(c.c_out), false);
+        if (rc) return rc;
+        t.has_small = t.nat.n_split == 1 && l + 2 < nconv && (c.c_out / 2) % 32 == 0;
+        if (t.has_small && (rc = pack_splits(t.small, 2, true))) return rc;
         nd->trunk.push_back(t);
         nd->width = std::max(nd->width, c.c_out);
     }
@@ -525,7 +534,7 @@ int grow_workspaces(DeviceState* d, const bool need[2], int cap) {
 // the batch pipeline on one device; all pointers are device pointers
 // --------------------------------------------------------------------------------------------
 struct Options {   // snapshot of the context's options for one call
-    long trunk_mode, cta_pair, dynamic_items, use_graphs, resident_weights, policy_clusters, profile_trunk, max_batch, spin_wait, group_positions, epoch;
+    long trunk_mode, cta_pair, dynamic_items, use_graphs, resident_weights, policy_clusters, profile_trunk, max_batch, spin_wait, group_positions, small_batch, epoch;
     int prec[2];
 };
 Options snapshot(lb2_ctx* ctx) {
@@ -533,7 +542,7 @@ Options snapshot(lb2_ctx* ctx) {
     Options o;
     o.trunk_mode = ctx->trunk_mode; o.cta_pair = ctx->cta_pair; o.dynamic_items = ctx->dynamic_items; o.use_graphs = ctx->use_graphs;
     o.resident_weights = ctx->resident_weights; o.policy_clusters = ctx->policy_clusters; o.profile_trunk = ctx->profile_trunk;
-    o.max_batch = ctx->max_batch; o.spin_wait = ctx->spin_wait; o.group_positions = ctx->group_positions; o.epoch = ctx->option_epoch.load();
+    o.max_batch = ctx->max_batch; o.spin_wait = ctx->spin_wait; o.group_positions = ctx->group_positions; o.small_batch = ctx->small_batch; o.epoch = ctx->option_epoch.load();
     o.prec[0] = (int)ctx->precision[0]; o.prec[1] = (int)ctx->precision[1];
     return o;
 }
@@ -553,7 +562,7 @@ struct JobPlan {
 // independent jobs of equal depth (a layer wider than 128 channels contributes one job per column
 // split; they are consecutive in the table).
 // `net_major` (resident-weights mode): all policy jobs first, then all value jobs, every job a round of its own
-JobPlan plan_jobs(DeviceState* d, const bool run[2], int n, const int limit_layers[2], bool pair, bool net_major, const int prec[2]) {
+JobPlan plan_jobs(DeviceState* d, const bool run[2], int n, const int limit_layers[2], bool pair, bool net_major, const int prec[2], bool small) {
     JobPlan pl;
     size_t depth = 0;
     for (int k = 0; k < 2; k++)
@@ -568,8 +577,10 @@ JobPlan plan_jobs(DeviceState* d, const bool run[2], int n, const int limit_laye
             if (!run[k] || l >= nd.trunk.size() || (int)l >= limit_layers[k]) continue;
             const TrunkLayerDev& t = nd.trunk[l];
             const int first_job = (int)pl.jobs.size();
-            const int w = t.c_out / t.n_split;
-            for (int sp = 0; sp < t.n_split; sp++) {
+            // small batches: every layer that has the packing runs as two column splits (CTA pairs only)
+            const SplitPacks& S = (small && pair && t.has_small) ? t.small : t.nat;
+            const int w = t.c_out / S.n_split;
+            for (int sp = 0; sp < S.n_split; sp++) {
                 lb2::LayerJob J;
                 memset(&J, 0, sizeof J);
                 const bool first = (l == 0);
@@ -604,7 +615,7 @@ JobPlan plan_jobs(DeviceState* d, const bool run[2], int n, const int limit_laye
                     J.dep_n_items = pl.tiles[J.dep_job];
                 }
                 // the input tiles of this layer are dead once read: which planes the publisher may drop from L2
-                if (l > 0 && t.n_split == 1 && nd.trunk[l - 1].n_split == 1) {
+                if (l > 0 && S.n_split == 1 && prev_split[k] == 1) {
                     J.in_base = nd.act[(l - 1) & 1];
                     J.in_chunk_rows = nd.rows3;
                     J.in_planes = t.c_in / 8 * (mode == kPrecFp16 ? 1 : 2);
@@ -612,9 +623,9 @@ JobPlan plan_jobs(DeviceState* d, const bool run[2], int n, const int limit_laye
                 J.n_pos = n;
                 J.net = k;
                 J.layer = (int)l;
-                J.wpk = mode == kPrecFull ? t.wpk_x[sp] : (mode == kPrecLite ? t.wpk_e[sp] : t.wpk[sp]);
-                J.wpk2 = mode == kPrecFull ? t.wpk2_x[sp] : (mode == kPrecLite ? t.wpk2_e[sp] : t.wpk2[sp]);
-                J.bias = t.bias[sp];
+                J.wpk = S.w[mode][0][sp];
+                J.wpk2 = S.w[mode][1][sp];
+                J.bias = S.bias[sp];
                 J.flags = nd.flags + ((size_t)l * lb2::kMaxSplit + sp) * nd.flags_stride;
                 J.head_slot = net_major ? k : k * lb2::kMaxSplit + sp;
                 if (l + 1 == nd.trunk.size() && limit_layers[k] > (int)nd.trunk.size()) {
@@ -637,7 +648,7 @@ JobPlan plan_jobs(DeviceState* d, const bool run[2], int n, const int limit_laye
                 pl.last_act[k] = nd.act[l & 1];
             }
             prev_job[k] = first_job;
-            prev_split[k] = t.n_split;
+            prev_split[k] = S.n_split;
         }
     }
     return pl;
@@ -656,20 +667,22 @@ int plan_trunk(const Options& o, DeviceState* d, const bool run[2], int n, const
         if (lb2::kLiteSeparateAcc && run[k] && o.prec[k] == kPrecLite && d->net[k].width > lb2::kCorrCols)
             return fail(LB2_ERR_UNSUPPORTED, "lite precision needs layers of at most %d channels (the %s net has %d)", lb2::kCorrCols,
                         k == 0 ? "policy" : "value", d->net[k].width);
+    // small batches run every layer as two column splits (SplitPacks small): twice the items, each half as long
+    const bool small = pair && o.trunk_mode == 1 && n <= o.small_batch;
     const bool want_resident = o.resident_weights == 1 || (o.resident_weights == 2 && run[0] && run[1]);
-    bool resident = pair && want_resident && o.trunk_mode == 1 && o.dynamic_items != 0;
+    bool resident = pair && !small && want_resident && o.trunk_mode == 1 && o.dynamic_items != 0;
     int n_jobs_est = 0;
     for (int k = 0; k < 2 && resident; k++) {
         if (!run[k]) continue;
         for (size_t l = 0; l < d->net[k].trunk.size() && (int)l < limit_layers[k]; l++) {
             const TrunkLayerDev& t = d->net[k].trunk[l];
             const int terms = o.prec[k] == kPrecFp16 ? 1 : (o.prec[k] == kPrecFull && l > 0 ? 3 : 2);
-            if (t.n_split != 1 || (size_t)t.k * t.k * t.c_in * terms * (t.c_out / 2) * 2 > (size_t)lb2::kResWeightBytes) resident = false;
+            if (t.nat.n_split != 1 || (size_t)t.k * t.k * t.c_in * terms * (t.c_out / 2) * 2 > (size_t)lb2::kResWeightBytes) resident = false;
             n_jobs_est++;
         }
     }
     if (n_jobs_est > lb2::kResJobs) resident = false;
-    JobPlan pl = plan_jobs(d, run, n, limit_layers, pair, resident, o.prec);
+    JobPlan pl = plan_jobs(d, run, n, limit_layers, pair, resident, o.prec, small);
     if (pl.jobs.empty()) return fail(LB2_ERR_STATE, "no trunk layers to run");
     if ((int)pl.jobs.size() > lb2::kMaxLaunchJobs) return fail(LB2_ERR_UNSUPPORTED, "too many layers");
     TrunkLaunch L;
@@ -825,14 +838,14 @@ int build_plan(const Options& o, DeviceState* d, const EvalKey& key, EvalPlan* p
     if (run[0] && key.out[0] && key.limit[0] > (int)d->net[0].trunk.size()) {
         NetDev& nd = d->net[0];
         ha.p_zbuf = nd.zbuf; ha.p_chunk_rows = nd.rows3; ha.p_bias = nd.head_b; ha.probs = static_cast<float*>(key.out[0]); ha.n_policy = n;
-        ha.p_parts = nd.trunk.back().n_split * lb2::kColParts;
+        ha.p_parts = nd.trunk.back().nat.n_split * lb2::kColParts;
         pl->heads = true;
     }
     if (run[1] && key.out[1] && key.limit[1] > (int)d->net[1].trunk.size()) {
         NetDev& nd = d->net[1];
         ha.v_zbuf = nd.zbuf; ha.v_chunk_rows = nd.rows3; ha.v_bias = nd.head_b; ha.ip1_wt = nd.ip1_wt; ha.ip1_b = nd.ip1_b;
         ha.hidden = nd.hidden; ha.ip2_w = nd.ip2_w; ha.ip2_b = nd.ip2_b; ha.winrate = static_cast<float*>(key.out[1]); ha.n_value = n;
-        ha.v_parts = nd.trunk.back().n_split * lb2::kColParts;
+        ha.v_parts = nd.trunk.back().nat.n_split * lb2::kColParts;
         pl->heads = true;
     }
     ha.trace = d->trace;
@@ -1535,10 +1548,11 @@ void lb2_destroy(lb2_ctx* ctx) {
         for (int k = 0; k < 2; k++) {
             NetDev& nd = d.net[k];
             for (auto& t : nd.trunk)
-                for (int sp = 0; sp < lb2::kMaxSplit; sp++) {
-                    cudaFree(t.wpk[sp]); cudaFree(t.wpk2[sp]); cudaFree(t.wpk_x[sp]); cudaFree(t.wpk2_x[sp]);
-                    cudaFree(t.wpk_e[sp]); cudaFree(t.wpk2_e[sp]); cudaFree(t.bias[sp]);
-                }
+                for (SplitPacks* S : {&t.nat, &t.small})
+                    for (int sp = 0; sp < lb2::kMaxSplit; sp++) {
+                        for (int mode = 0; mode < 3; mode++) { cudaFree(S->w[mode][0][sp]); cudaFree(S->w[mode][1][sp]); }
+                        cudaFree(S->bias[sp]);
+                    }
             for (int sp = 0; sp < lb2::kMaxSplit; sp++) cudaFree(nd.head_wt[sp]);
             cudaFree(nd.head_b); cudaFree(nd.ip1_wt); cudaFree(nd.ip1_b);
             cudaFree(nd.ip2_w); cudaFree(nd.ip2_b);
@@ -1808,6 +1822,9 @@ int lb2_set_option(lb2_ctx* ctx, const char* name, long value) {
         ctx->use_graphs = value ? 1 : 0;
     } else if (!strcmp(name, "spin_wait")) {
         ctx->spin_wait = value ? 1 : 0;
+    } else if (!strcmp(name, "small_batch")) {
+        if (value < 0) return fail(LB2_ERR_INVALID, "small_batch must be >= 0");
+        ctx->small_batch = value;
     } else if (!strcmp(name, "group_positions")) {
         if (value < 0 || (value % 128)) return fail(LB2_ERR_INVALID, "group_positions must be 0 or a multiple of 128");
         ctx->group_positions = value;
@@ -1874,6 +1891,7 @@ long lb2_get_option(lb2_ctx* ctx, const char* name) {
     if (!strcmp(name, "use_graphs")) return ctx->use_graphs;
     if (!strcmp(name, "spin_wait")) return ctx->spin_wait;
     if (!strcmp(name, "group_positions")) return ctx->group_positions;
+    if (!strcmp(name, "small_batch")) return ctx->small_batch;
     if (!strcmp(name, "resident_weights")) return ctx->resident_weights;
     if (!strcmp(name, "precise")) return ctx->precision[0] == kPrecFull && ctx->precision[1] == kPrecFull;
     if (!strcmp(name, "policy_precision")) return ctx->precision[0];

@@ -35,7 +35,7 @@ constexpr int kEpilogueWarps = LB2_EPI_WARPS;  // 8 or 16: TMEM lane quadrant (w
 constexpr int kColParts = kEpilogueWarps / 4;     // parts the output channels of a tile are split into
 // warp0 TMA producer, warp1 MMA issuer, warps2-9 epilogue, warp10 tile publisher, warp11 dependency scout
 constexpr int kTrunkThreads = 64 + 32 * kEpilogueWarps + 64;
-constexpr int kMaxLaunchJobs = 40;  // jobs whose biases are kept resident in smem
+constexpr int kMaxLaunchJobs = 44;  // jobs whose biases are kept resident in smem (12 + 11 layers, all but the first policy layer and the last ones cut in two)
 constexpr int kMaxSplit = 2;        // a layer wider than 128 channels runs as this many column-split jobs
 constexpr int kHeadSlots = 2 * kMaxSplit;  // fused-head weight sets resident in smem: [net][split]
 constexpr int kPubDepth = 4;        // tiles that may be waiting for publication
@@ -59,7 +59,7 @@ constexpr int kTrunkSmemBytesRes = kResWeightBytes + kStagesRes * kASlabBytes + 
 static_assert(kTrunkSmemBytesRes <= 227 * 1024, "resident-weights trunk shared memory");
 constexpr int kMaxLayers = 16;
 constexpr int kMaxTensorMaps = 6;
-constexpr int kMaxJobs = 40;
+constexpr int kMaxJobs = 44;
 constexpr int kMaxRounds = 104;  // a round = the jobs of equal depth (all nets, all column splits), their items interleaved; or, in
                                 // net-major order, one position group of one layer ((12 + 11 layers) x up to 4 groups)
 constexpr int kMaxRoundJobs = 2 * kMaxSplit;

@@ -624,6 +624,32 @@ def test_api_level_dropin_against_live_reference_engine():
     assert r["top1_agree_or_near_tie"] == r["cases"]
 
 
+def test_small_batch_column_splits_bit_identical(ev, ref_golden):
+    """Device passes of up to `small_batch` positions (default 48) run every layer but the first policy layer and the fused-head
+    layers as TWO column-split jobs (two clusters share an item's MMAs and epilogue: a small pass is bound by the latency of its
+    chained layers — batch 1: 154 -> 131 us). Same K order per output channel, so the same bits as whole layers, in every
+    precision, for one net alone and for per-layer outputs."""
+    g = ref_golden
+    assert ev.get_option("small_batch") == 48
+    for mode in ((0, 1), (1, 1), (2, 2)):
+        ev.set_precision(*mode)
+        try:
+            for n in (1, 7, 37):
+                args = (g["policy_planes"][:n], g["value_planes"][:n], g["rotation"][:n], TEMP)
+                ev.set_option("small_batch", 0)
+                want = ev.eval_both(*args)
+                want_v = ev.eval_value(args[1], args[2])
+                want_l = ev.debug_trunk(1, args[1], args[2], 3, 64)
+                ev.set_option("small_batch", 48)
+                got = ev.eval_both(*args)
+                assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), (mode, n)
+                assert np.array_equal(ev.eval_value(args[1], args[2]), want_v)
+                assert np.array_equal(ev.debug_trunk(1, args[1], args[2], 3, 64), want_l)
+        finally:
+            ev.set_option("small_batch", 48)
+            ev.set_precision(0, 1)
+
+
 def test_cuda_graph_path_equals_separate_launches(ev, ref_golden, bench_positions):
     """From the second use of a batch shape on, expand -> trunk -> heads run as ONE cached CUDA graph (the kernels keep their
     scheduling state on the device, so the launch sequence is replayable). Same bits as separate launches, for host buffers
