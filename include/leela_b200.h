@@ -116,7 +116,8 @@ int lb2_eval_both_device(lb2_ctx* ctx, int dev_index, const uint32_t* d_policy_p
  * as soon as they are free — the batch size follows the load — and run it as one device batch;
  * cb(user, status) runs on such a thread once the caller's output buffer is filled. When status is
  * not LB2_OK, lb2_last_error() inside the callback (or lb2_queue_error later, from any thread) gives
- * the text. */
+ * the text. A request of more than max_batch positions is evaluated at once on the calling thread
+ * (its callback runs before lb2_submit_* returns). */
 typedef void (*lb2_callback)(void* user, int status);
 int lb2_submit_policy(lb2_ctx* ctx, const uint32_t* planes, const uint8_t* rotation, int n,
                       float softmax_temp, float* probs_out, lb2_callback cb, void* user);

@@ -1006,6 +1006,7 @@ int eval_on_device(lb2_ctx* ctx, const Options& o, DeviceState* d, EvalKey key, 
         EvalPlan pl;
         if ((rc = build_plan(o, d, key, &pl))) return rc;
         bool launched = false;
+        if (d->seen.size() > 4096) d->seen.clear();   // (a caller cycling through thousands of shapes: start counting afresh)
         if (graphs_ok && d->seen[shape_id(key, tag)]++ >= 1) {
             // second use of the shape: worth a graph. A full cache gives up its least recently used entry, unless even that
             // one was used a moment ago (many shapes in rotation: graphs would be built and thrown away all the time)

@@ -766,6 +766,46 @@ def test_submit_queue_single_position_load(ev, bench_positions):
     assert positions / batches >= 4, (positions, batches)
 
 
+def test_multi_device_dispatch_logic_on_one_gpu(ref_golden, bench_positions):
+    """The in-process multi-device path on a single-GPU box: lb2_init with the SAME device listed twice gives two device
+    states (own streams, workspaces, I/O slots, graph caches) that happen to share one GPU — chunks of a large call are dealt
+    over both, concurrent callers and the submit queue's dispatchers use both, and every result equals the one-device one."""
+    import threading
+    from leela_b200 import capi, synth
+    g, b = ref_golden, bench_positions
+    pw, vw = synth.policy_weights(), synth.value_weights()
+    one = capi.Evaluator(policy=pw, value=vw, devices=[0])
+    want = one.eval_both(b["policy_planes"], b["value_planes"], b["rotation"], TEMP)
+    one.close()
+    two = capi.Evaluator(policy=pw, value=vw, devices=[0, 0])
+    try:
+        assert two.get_option("sm_count") > 0 and capi.load().lb2_device_count(two.ctx) == 2
+        for rep in range(2):
+            got = two.eval_both(b["policy_planes"], b["value_planes"], b["rotation"], TEMP)     # 4 chunks of 256 over 2 x 2 slots
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+        two.set_option("max_batch", 64)                                                          # 16 chunks
+        got = two.eval_both(b["policy_planes"], b["value_planes"], b["rotation"], TEMP)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+        errors, outs = [], [None] * 6
+
+        def run(i):
+            try:
+                lo, n = [(0, 300), (100, 64), (500, 511), (7, 1), (640, 129), (40, 256)][i]
+                for _ in range(4):
+                    outs[i] = (lo, n, two.eval_both(b["policy_planes"][lo:lo + n], b["value_planes"][lo:lo + n], b["rotation"][lo:lo + n], TEMP))
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+
+        ts = [threading.Thread(target=run, args=(i,)) for i in range(6)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert not errors, errors
+        for lo, n, (p, v) in outs:
+            assert np.array_equal(p, want[0][lo:lo + n]) and np.array_equal(v, want[1][lo:lo + n])
+    finally:
+        two.close()
+
+
 def test_in_process_multi_device_sharding(ref_golden):
     """lb2_init with several devices: weights replicated; a call of up to max_batch positions runs as one batch on one
     device, larger calls are dealt to the devices in max_batch chunks; no collective; results identical to one device
