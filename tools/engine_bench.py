@@ -55,6 +55,9 @@ def summarize(name, rc, text, per_move, moves, wall, extra):
     if m:
         out["nn_positions"] = int(m.group(1)); out["device_batches"] = int(m.group(2))
         out["mean_device_batch"] = float(m.group(3)); out["nn_requests"] = int(m.group(4))
+    fp = re.search(r"feature planes: ([\d.]+) us per position", text)
+    if fp:
+        out["feature_planes_us_per_position"] = float(fp.group(1))
     out.update(extra)
     if rc != 0 or (not per_move and not nb):
         out["tail"] = text[-1500:]
