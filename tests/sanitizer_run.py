@@ -1,4 +1,5 @@
-"""Small run of every kernel mode (CTA pairs, single CTA, resident weights, precise, ensemble, 192-wide net) for
+"""Small run of every kernel mode (CTA pairs, single CTA, resident weights, lite / full precision, small-batch column splits,
+whole layers at 70 positions, CUDA graphs, ensemble, 192-wide net) for
 compute-sanitizer: `compute-sanitizer --tool memcheck|synccheck|initcheck python tests/sanitizer_run.py` (0 errors, round 1)."""
 import os, sys
 sys.path.insert(0, os.getcwd())
@@ -21,6 +22,14 @@ for pair in (0, 1):
     ev.set_option("cta_pair", pair); ev.set_option("precise", 1)
     p4, v4 = ev.eval_both(g["policy_planes"][:5], g["value_planes"][:5], g["rotation"][:5], 0.75)
     print("precise pair=%d" % pair, float(np.abs(p4 - g["policy"][:5]).max()), float(np.abs(v4 - g["value"][:5]).max()))
+ev.set_option("cta_pair", 1); ev.set_option("resident_weights", 2)
+for mode in ((0, 1), (1, 1)):   # lite precision: e4m3 correction MMAs, e4m3 planes from the epilogue
+    ev.set_precision(*mode)
+    for n, sb in ((5, 48), (5, 0), (70, 48)):   # column splits / whole layers at a small batch / resident-weights launch
+        ev.set_option("small_batch", sb)
+        for rep in range(3):   # the third call of a shape replays its CUDA graph
+            p5, v5 = ev.eval_both(g["policy_planes"][:n], g["value_planes"][:n], g["rotation"][:n], 0.75)
+        print("lite", mode, n, sb, float(np.abs(p5 - g["policy"][:n]).max()), float(np.abs(v5 - g["value"][:n]).max()))
 ev.close()
 e2 = capi.Evaluator(policy=synth.policy192_weights())
 q = e2.eval_policy(g["policy_planes"][:3], g["rotation"][:3], 0.75)

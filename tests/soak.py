@@ -47,10 +47,45 @@ def submits(t):
         counts[t] += len(idx)
 
 
+def queue(t):
+    """single-position requests through lb2_submit_* with one request outstanding, like a search thread"""
+    import ctypes as C
+    L = capi.load()
+    rng = np.random.default_rng(300 + t)
+    sem = threading.Semaphore(0)
+    status = []
+    cb = capi.CALLBACK(lambda user, st: (status.append(st), sem.release()))
+    out_p = np.zeros((1, 361), np.float32); out_v = np.zeros(1, np.float32)
+    while time.time() < stop and not errors:
+        i = int(rng.integers(0, 1024))
+        planes_p = np.ascontiguousarray(pp[i:i + 1]); planes_v = np.ascontiguousarray(vp[i:i + 1]); r = np.ascontiguousarray(rot[i:i + 1])
+        if rng.integers(0, 3) == 0:
+            capi.check(L.lb2_submit_policy(ev.ctx, planes_p.ctypes.data, r.ctypes.data, 1, 0.75, out_p.ctypes.data, cb, None)); sem.acquire()
+            ok = np.array_equal(out_p[0], want_p[i])
+        else:
+            capi.check(L.lb2_submit_value(ev.ctx, planes_v.ctypes.data, r.ctypes.data, 1, out_v.ctypes.data, cb, None)); sem.acquire()
+            ok = out_v[0] == want_v[i]
+        if not ok or status[-1] != 0:
+            errors.append(("queue", t, i)); return
+        counts[t] += 1
+
+
+def options(t):
+    """flips run-time options under the other threads' feet: cached graphs must be rebuilt, results must not change"""
+    k = 0
+    while time.time() < stop and not errors:
+        time.sleep(0.05)
+        ev.set_option("use_graphs", k & 1); ev.set_option("small_batch", 48 if k & 2 else 0); ev.set_option("resident_weights", 2 if k & 4 else 0)
+        k += 1
+    ev.set_option("use_graphs", 1); ev.set_option("small_batch", 48); ev.set_option("resident_weights", 2)
+
+
+counts += [0] * 10
 threads = [threading.Thread(target=blocking, args=(0,)), threading.Thread(target=blocking, args=(1,)),
-           threading.Thread(target=ensembles, args=(2,)), threading.Thread(target=submits, args=(3,))]
+           threading.Thread(target=ensembles, args=(2,)), threading.Thread(target=submits, args=(3,)),
+           threading.Thread(target=options, args=(15,))] + [threading.Thread(target=queue, args=(4 + i,)) for i in range(8)]
 for th in threads: th.start()
 for th in threads: th.join()
 ev.close()
-print(f"soak {SECONDS:.0f} s: positions per thread {counts[:4]}, errors {errors}")
+print(f"soak {SECONDS:.0f} s: positions per thread {counts[:12]}, errors {errors}")
 sys.exit(1 if errors else 0)
