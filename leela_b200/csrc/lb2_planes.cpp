@@ -11,10 +11,13 @@
 //   check_losing_ladder, check_winning_ladder         FastBoard.cpp:2647-2837, 2530-2564
 //   minimum_elib_count, critical_neighbours, can_kill_neighbours, in_atari, update_board_fast
 // The reference keeps strings incrementally (parent / next / libs arrays); its m_libs are TRUE
-// liberty counts, so a board that simply re-derives strings, sizes and liberties by flood fill after
-// every change gives the same answers — the ladder reader's decisions depend only on liberty counts
-// and on sets of points, never on the traversal order of a string. Positions are tiny (361 points),
-// a full re-analysis costs about a microsecond.
+// liberty counts, so a board that re-derives strings, sizes and liberties by flood fill gives the same
+// answers — the ladder reader's decisions depend only on liberty counts and on sets of points, never on
+// the traversal order of a string. Round 1 re-analysed the whole board after every stone (0.12 ms per
+// position, two thirds of it in the ladder readers and in the 2 x ~250 liberties-after-a-move fills);
+// now a move re-fills only the strings it touches (the one it joins, the ones it captures, their
+// neighbours), the liberties-after-a-move count for the planes stops at the 6 the planes distinguish,
+// and visited marks are generation stamps instead of cleared arrays.
 //
 // Checked against the reference's planes on thousands of seeded self-play positions
 // (tests/test_planes.py); exported through the C ABI as lb2_planes_from_position.
@@ -35,48 +38,79 @@ constexpr int kFar = 16384;                            // "liberties" of empty /
 inline int vertex_of(int idx) { return (idx / N + 1) * W + (idx % N + 1); }   // FastBoard::get_vertex
 inline int idx_of(int v) { return (v / W - 1) * N + (v % W - 1); }
 
+constexpr int kLibList = 6;        // liberties remembered per string (the planes distinguish 1..5 and ">= 6")
+constexpr int kMaxGroups = 1536;   // string ids are never recycled: <= 361 at the start + one per stone played in a ladder read
+
+// visited marks of the flood fills: a point is marked when mark[p] == stamp (no clearing between fills)
+struct Scratch {
+    uint16_t mark[SQ];
+    uint16_t stamp = 0;
+    int16_t stack[N * N + 4];
+    uint16_t next() {
+        if (++stamp == 0) { memset(mark, 0, sizeof mark); stamp = 1; }
+        return stamp;
+    }
+};
+thread_local Scratch g_scratch;
+
 struct Board {
     uint8_t sq[SQ];
-    int16_t group[SQ];      // string id per stone, -1 otherwise
-    int16_t libs[SQ / 2];   // per string: number of distinct empty points adjacent to it
-    int16_t stones[SQ / 2]; // per string: number of stones
+    int16_t group[SQ];             // string id per stone, -1 otherwise
+    int16_t libs[kMaxGroups];      // per string: number of distinct empty points adjacent to it
+    int16_t stones[kMaxGroups];    // per string: number of stones
+    int16_t lib_pts[kMaxGroups][kLibList];   // per string: its liberties, all of them when there are at most kLibList
+    int16_t n_groups;
     uint8_t tomove;
+
+    Board() = default;
+    Board(const Board& o) { *this = o; }
+    Board& operator=(const Board& o) {   // (the ladder readers copy the board per branch: only the string ids in use)
+        memcpy(sq, o.sq, sizeof sq);
+        memcpy(group, o.group, sizeof group);
+        memcpy(libs, o.libs, (size_t)o.n_groups * sizeof libs[0]);
+        memcpy(stones, o.stones, (size_t)o.n_groups * sizeof stones[0]);
+        memcpy(lib_pts, o.lib_pts, (size_t)o.n_groups * sizeof lib_pts[0]);
+        n_groups = o.n_groups;
+        tomove = o.tomove;
+        return *this;
+    }
 
     void clear() {
         for (int v = 0; v < SQ; v++) sq[v] = BORDER;
         for (int i = 0; i < N * N; i++) sq[vertex_of(i)] = EMPTY;
+        n_groups = 0;
     }
+    // the string containing the stone at v0 gets id g: its stones, size and true liberties by flood fill
+    void fill_group(int v0, int g) {
+        Scratch& S = g_scratch;
+        const uint16_t st = S.next();
+        const uint8_t c = sq[v0];
+        int sp = 0, n_st = 0, n_lib = 0;
+        S.stack[sp++] = (int16_t)v0;
+        S.mark[v0] = st;
+        group[v0] = (int16_t)g;
+        while (sp) {
+            const int v = S.stack[--sp];
+            n_st++;
+            for (int k = 0; k < 4; k++) {
+                const int a = v + kDirs[k];
+                if (S.mark[a] == st) continue;
+                if (sq[a] == EMPTY) { S.mark[a] = st; if (n_lib < kLibList) lib_pts[g][n_lib] = (int16_t)a; n_lib++; }
+                else if (sq[a] == c) { S.mark[a] = st; group[a] = (int16_t)g; S.stack[sp++] = (int16_t)a; }
+            }
+        }
+        libs[g] = (int16_t)n_lib;
+        stones[g] = (int16_t)n_st;
+    }
+    int new_group() { return n_groups < kMaxGroups - 1 ? n_groups++ : kMaxGroups - 1; }   // (the bound is never reached on a 19 x 19 board)
 
-    // strings, their sizes and true liberties
+    // strings, their sizes and true liberties of the whole board
     void analyze() {
-        int16_t stack[N * N];
-        int16_t seen_lib[SQ];   // last string that counted this empty point
-        memset(seen_lib, -1, sizeof seen_lib);
         for (int v = 0; v < SQ; v++) group[v] = -1;
-        int n_groups = 0;
+        n_groups = 0;
         for (int i = 0; i < N * N; i++) {
             const int v0 = vertex_of(i);
-            if (sq[v0] > WHITE || group[v0] >= 0) continue;
-            const int g = n_groups++;
-            const uint8_t c = sq[v0];
-            int sp = 0, n_st = 0, n_lib = 0;
-            stack[sp++] = (int16_t)v0;
-            group[v0] = (int16_t)g;
-            while (sp) {
-                const int v = stack[--sp];
-                n_st++;
-                for (int k = 0; k < 4; k++) {
-                    const int a = v + kDirs[k];
-                    if (sq[a] == EMPTY) {
-                        if (seen_lib[a] != g) { seen_lib[a] = (int16_t)g; n_lib++; }
-                    } else if (sq[a] == c && group[a] < 0) {
-                        group[a] = (int16_t)g;
-                        stack[sp++] = (int16_t)a;
-                    }
-                }
-            }
-            libs[g] = (int16_t)n_lib;
-            stones[g] = (int16_t)n_st;
+            if (sq[v0] <= WHITE && group[v0] < 0) fill_group(v0, new_group());
         }
     }
 
@@ -92,23 +126,62 @@ struct Board {
         return n;
     }
 
-    void remove_group(int g) {
-        for (int v = 0; v < SQ; v++)
-            if (group[v] == g) sq[v] = EMPTY;
+    // take the string containing v0 off the board; the strings of the other colour around it get their liberties back
+    void remove_group(int v0) {
+        Scratch& S = g_scratch;
+        const uint8_t c = sq[v0];
+        const int g = group[v0];
+        int16_t members[N * N];
+        int n = 0, sp = 0;
+        S.stack[sp++] = (int16_t)v0;
+        sq[v0] = EMPTY;                 // (emptied as it is visited: doubles as the visited mark)
+        while (sp) {
+            const int v = S.stack[--sp];
+            members[n++] = (int16_t)v;
+            group[v] = -1;
+            for (int k = 0; k < 4; k++) {
+                const int a = v + kDirs[k];
+                if (sq[a] == c && group[a] == g) { sq[a] = EMPTY; S.stack[sp++] = (int16_t)a; }
+            }
+        }
+        // every enemy string that touched a removed stone: re-fill it once (its liberties changed)
+        int16_t redone[N * N];
+        int n_redone = 0;
+        for (int i = 0; i < n; i++)
+            for (int k = 0; k < 4; k++) {
+                const int a = members[i] + kDirs[k];
+                if (sq[a] == (uint8_t)!c) {
+                    const int ga = group[a];
+                    bool dup = false;
+                    for (int j = 0; j < n_redone && !dup; j++) dup = redone[j] == ga;
+                    if (!dup) { redone[n_redone++] = (int16_t)ga; fill_group(a, ga); }
+                }
+            }
     }
 
     // update_board_fast (FastBoard.cpp:812-874): place a stone, capture, detect multi-stone
     // suicide; ko is not a concept here. A play into an opponent eye (all four neighbours opponent
-    // or border) takes the capture-only path of update_board_eye.
+    // or border) takes the capture-only path of update_board_eye. Only the strings the move touches
+    // are re-derived.
     void play(int c, int v) {
         const bool eyeplay = colour_neighbours(!c, v) == 4;
         sq[v] = (uint8_t)c;
-        analyze();
+        // the enemy strings around v each lose the liberty v (re-filled, so that their liberty lists stay exact)
+        int enemy[4], n_enemy = 0;
         for (int k = 0; k < 4; k++) {
             const int a = v + kDirs[k];
-            if (sq[a] == (uint8_t)!c && libs[group[a]] == 0) { remove_group(group[a]); analyze(); }
+            if (sq[a] == (uint8_t)!c) {
+                bool dup = false;
+                for (int j = 0; j < n_enemy; j++) dup |= enemy[j] == group[a];
+                if (!dup) { enemy[n_enemy++] = group[a]; fill_group(a, group[a]); }
+            }
         }
-        if (!eyeplay && libs[group[v]] == 0) { remove_group(group[v]); analyze(); }
+        fill_group(v, new_group());     // the stone and the friendly strings it joins
+        for (int k = 0; k < 4; k++) {
+            const int a = v + kDirs[k];
+            if (sq[a] == (uint8_t)!c && libs[group[a]] == 0) remove_group(a);   // (re-fills the string of v when it borders the capture)
+        }
+        if (!eyeplay && libs[group[v]] == 0) remove_group(v);
     }
 
     // is_suicide (FastBoard.cpp:191-240). The reference's early exits already decide everything:
@@ -132,11 +205,32 @@ struct Board {
     int in_atari(int v) const {
         const int g = group[v];
         if (libs[g] > 1) return 0;
-        for (int p = 0; p < SQ; p++)
-            if (group[p] == g)
-                for (int k = 0; k < 4; k++)
-                    if (sq[p + kDirs[k]] == EMPTY) return p + kDirs[k];
-        return 0;
+        int found = 0;
+        for_each_stone(v, [&](int p) {
+            for (int k = 0; k < 4 && !found; k++)
+                if (sq[p + kDirs[k]] == EMPTY) found = p + kDirs[k];
+            return found == 0;
+        });
+        return found;
+    }
+
+    // visits the stones of the string containing v0 until f returns false
+    template <class F>
+    void for_each_stone(int v0, F f) const {
+        Scratch& S = g_scratch;
+        const uint16_t st = S.next();
+        const uint8_t c = sq[v0];
+        int sp = 0;
+        S.stack[sp++] = (int16_t)v0;
+        S.mark[v0] = st;
+        while (sp) {
+            const int p = S.stack[--sp];
+            if (!f(p)) return;
+            for (int k = 0; k < 4; k++) {
+                const int a = p + kDirs[k];
+                if (sq[a] == c && S.mark[a] != st) { S.mark[a] = st; S.stack[sp++] = (int16_t)a; }
+            }
+        }
     }
 
     // kill_or_connect (FastBoard.cpp:1342-1355)
@@ -167,11 +261,11 @@ struct Board {
             if (sq[a] == EMPTY) {
                 add(a);
             } else if (sq[a] == c && libs_at(a) > 1) {
-                const int g = group[a];
-                for (int p = 0; p < SQ && n <= 2; p++)
-                    if (group[p] == g)
-                        for (int kk = 0; kk < 4; kk++)
-                            if (sq[p + kDirs[kk]] == EMPTY) add(p + kDirs[kk]);
+                for_each_stone(a, [&](int p) {
+                    for (int kk = 0; kk < 4; kk++)
+                        if (sq[p + kDirs[kk]] == EMPTY) add(p + kDirs[kk]);
+                    return n <= 2;
+                });
             }
             if (n > 2) return false;
         }
@@ -182,30 +276,63 @@ struct Board {
     // 0 for a suicide. The reference copies the board and plays the move; the same number comes out of
     // one local flood fill from v in which the enemy neighbour strings the move captures (those whose
     // only liberty is v) already count as empty points.
-    int after_liberties(int c, int v) const {
+    // `cap`: stop counting there (the planes only distinguish 1..5 and ">= 6"; the ladder reader needs the exact number)
+    int after_liberties(int c, int v, int cap = 1 << 20) const {
         if (is_suicide(v, c)) return 0;
-        int captured[4], n_cap = 0;
+        int captured[4], n_cap = 0, n_friends = 0, n_empty = 0;
         for (int k = 0; k < 4; k++) {
             const int a = v + kDirs[k];
-            if (sq[a] == (uint8_t)!c && libs[group[a]] == 1) captured[n_cap++] = group[a];
+            if (sq[a] == EMPTY) n_empty++;
+            else if (sq[a] == (uint8_t)!c) { if (libs[group[a]] == 1) captured[n_cap++] = group[a]; }
+            else if (sq[a] == c) {
+                if (libs[group[a]] > cap) return cap;   // joining a string with cap + 1 liberties (one of them is v) settles it at once
+                n_friends++;
+            }
+        }
+        if (!n_friends && !n_cap) return std::min(n_empty, cap);   // a lone stone that captures nothing: its empty neighbours
+        if (!n_cap && cap <= kLibList) {
+            // nothing captured and every string joined has at most `cap` liberties, all of them listed: the answer is the
+            // size of the union of the empty neighbours of v and those lists, without v
+            int pts[4 + 4 * kLibList], n = 0;
+            auto add = [&](int q) {
+                if (q == v) return;
+                for (int i = 0; i < n; i++) if (pts[i] == q) return;
+                pts[n++] = q;
+            };
+            int seen_g[4], n_seen = 0;
+            for (int k = 0; k < 4; k++) {
+                const int a = v + kDirs[k];
+                if (sq[a] == EMPTY) add(a);
+                else if (sq[a] == c) {
+                    const int g = group[a];
+                    bool dup = false;
+                    for (int i = 0; i < n_seen; i++) dup |= seen_g[i] == g;
+                    if (dup) continue;
+                    seen_g[n_seen++] = g;
+                    for (int i = 0; i < libs[g]; i++) add(lib_pts[g][i]);
+                }
+            }
+            return std::min(n, cap);
         }
         auto vacated = [&](int p) {
             for (int i = 0; i < n_cap; i++) if (group[p] == captured[i]) return true;
             return false;
         };
-        uint8_t seen[SQ];
-        memset(seen, 0, sizeof seen);
-        int16_t stack[N * N];
+        Scratch& S = g_scratch;
+        const uint16_t st = S.next();
         int sp = 0, n_lib = 0;
-        stack[sp++] = (int16_t)v;
-        seen[v] = 1;
+        S.stack[sp++] = (int16_t)v;
+        S.mark[v] = st;
         while (sp) {
-            const int p = stack[--sp];
+            const int p = S.stack[--sp];
             for (int k = 0; k < 4; k++) {
                 const int a = p + kDirs[k];
-                if (seen[a]) continue;
-                if (sq[a] == c) { seen[a] = 1; stack[sp++] = (int16_t)a; }
-                else if (sq[a] == EMPTY || (sq[a] == (uint8_t)!c && n_cap && vacated(a))) { seen[a] = 1; n_lib++; }
+                if (S.mark[a] == st) continue;
+                if (sq[a] == c) { S.mark[a] = st; S.stack[sp++] = (int16_t)a; }
+                else if (sq[a] == EMPTY || (sq[a] == (uint8_t)!c && n_cap && vacated(a))) {
+                    S.mark[a] = st;
+                    if (++n_lib >= cap) return cap;
+                }
             }
         }
         return n_lib;
@@ -234,20 +361,18 @@ struct Board {
         return false;
     }
 
-    // can_kill_neighbours (FastBoard.cpp:2587-2613): some enemy string touching string g is in atari
-    bool can_kill_neighbours(int g) const {
-        const uint8_t enemy = (uint8_t)!sq_of_group(g);
-        for (int p = 0; p < SQ; p++)
-            if (group[p] == g)
-                for (int k = 0; k < 4; k++) {
-                    const int a = p + kDirs[k];
-                    if (sq[a] == enemy && libs[group[a]] <= 1) return true;
-                }
-        return false;
-    }
-    uint8_t sq_of_group(int g) const {
-        for (int p = 0; p < SQ; p++) if (group[p] == g) return sq[p];
-        return EMPTY;
+    // can_kill_neighbours (FastBoard.cpp:2587-2613): some enemy string touching the string of v0 is in atari
+    bool can_kill_neighbours(int v0) const {
+        const uint8_t enemy = (uint8_t)!sq[v0];
+        bool found = false;
+        for_each_stone(v0, [&](int p) {
+            for (int k = 0; k < 4; k++) {
+                const int a = p + kDirs[k];
+                if (sq[a] == enemy && libs[group[a]] <= 1) found = true;
+            }
+            return !found;
+        });
+        return found;
     }
 
     // check_losing_ladder (FastBoard.cpp:2647-2837): `c` (== tomove) extends at v out of atari;
@@ -257,17 +382,17 @@ struct Board {
         const int elib = minimum_enemy_libs(c, v);
         if (elib == 0 || elib == 1) return false;                 // the move captures something
         // the friendly strings in atari next to v: more than one means we are connecting, not running
-        int crit[4], n_crit = 0;
+        int crit[4], crit_at = 0, n_crit = 0;
         for (int k = 0; k < 4; k++) {
             const int a = v + kDirs[k];
             if (sq[a] == c && libs_at(a) <= 1) {
                 bool dup = false;
                 for (int i = 0; i < n_crit; i++) dup |= crit[i] == group[a];
-                if (!dup) crit[n_crit++] = group[a];
+                if (!dup) { crit[n_crit++] = group[a]; crit_at = a; }
             }
         }
         if (n_crit != 1) return false;    // (the reference asserts n_crit > 0; callers guarantee it)
-        if (can_kill_neighbours(crit[0])) return false;           // an atari-giving stone can be captured instead
+        if (can_kill_neighbours(crit_at)) return false;           // an atari-giving stone can be captured instead
 
         Board t = *this;
         int atari = v;
@@ -283,13 +408,13 @@ struct Board {
             if (t.minimum_enemy_libs(c, atari) == 1) return false;  // counter-atari on a chaser
             // the two liberties of the running string
             int lib[2], nl = 0;
-            const int g = t.group[atari];
-            for (int p = 0; p < SQ && nl < 2; p++)
-                if (t.group[p] == g)
-                    for (int k = 0; k < 4 && nl < 2; k++) {
-                        const int a = p + kDirs[k];
-                        if (t.sq[a] == EMPTY && (nl == 0 || lib[0] != a)) lib[nl++] = a;
-                    }
+            t.for_each_stone(atari, [&](int p) {
+                for (int k = 0; k < 4 && nl < 2; k++) {
+                    const int a = p + kDirs[k];
+                    if (t.sq[a] == EMPTY && (nl == 0 || lib[0] != a)) lib[nl++] = a;
+                }
+                return nl < 2;
+            });
             if (t.empty_neighbours(lib[0]) == 3 && t.empty_neighbours(lib[1]) == 3) return false;   // two good ways out
             // where does the attacker atari next: the liberty whose escape would gain the defender more
             int gain0 = t.after_liberties(t.tomove, lib[0]);
@@ -319,13 +444,28 @@ struct Board {
     // check_winning_ladder (FastBoard.cpp:2530-2564): `c` (== tomove) gives atari at v on a
     // neighbouring two-liberty string whose only escape runs into a working ladder
     bool winning_ladder(int c, int v) const {
+        bool captures = false;   // does a stone at v capture anything?
+        for (int k = 0; k < 4; k++) {
+            const int a = v + kDirs[k];
+            captures |= sq[a] == (uint8_t)!c && libs[group[a]] == 1;
+        }
         for (int k = 0; k < 4; k++) {
             const int a = v + kDirs[k];
             if (sq[a] != (uint8_t)!c || libs[group[a]] != 2) continue;
             if (self_atari(c, v)) continue;
+            if (!captures) {
+                // the board after the move differs only by the stone at v: the string keeps its other liberty, and the ladder is
+                // only read when that escape point has exactly two empty neighbours — decided here, before any board is copied
+                const int g = group[a];
+                const int escape = lib_pts[g][0] == v ? lib_pts[g][1] : lib_pts[g][0];
+                int en = empty_neighbours(escape);
+                for (int kk = 0; kk < 4; kk++) en -= (escape + kDirs[kk] == v);
+                if (en != 2) continue;
+            }
             Board t = *this;
             t.play(t.tomove, v);
             const int escape = t.in_atari(a);
+            if (!escape) continue;   // (the capture gave the string room: the reference reads "0 empty neighbours" off its border vertex 0)
             if (t.empty_neighbours(escape) == 2) {
                 t.tomove = (uint8_t)!t.tomove;
                 if (t.losing_ladder(t.tomove, escape)) return true;
@@ -374,8 +514,8 @@ extern "C" int lb2_planes_from_position(const uint8_t* stones, int white_to_move
         if (p.sq != EMPTY) {
             p.libs = b.libs[b.group[v]];
         } else {
-            p.after_own = (int16_t)b.after_liberties(c, v);
-            p.after_opp = (int16_t)b.after_liberties(!c, v);
+            p.after_own = (int16_t)b.after_liberties(c, v, 6);
+            p.after_opp = (int16_t)b.after_liberties(!c, v, 6);
             p.ladder = b.empty_neighbours(v) == 2 && b.saves_something(c, v) && b.losing_ladder(c, v);
             p.ladder_win = b.winning_ladder(c, v);
         }
