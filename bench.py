@@ -58,6 +58,20 @@ def load_positions():
     return g["policy_planes"], g["value_planes"], g["rotation"]
 
 
+def executed_trunk_flops(prec, batch):
+    """bf16-equivalent tensor work one trunk launch EXECUTES (explains the distance between `roofline.frac`, which counts the
+    reference's algorithmic flops, and the tensor pipe's real load): every layer runs over the padded row space (S x S rows per
+    position, S = 21 in front of the 5x5 layer and 20 elsewhere, in whole 512-row items), and a split-operand net repeats the
+    K loop per term (lite: one e4m3 K = 32 instruction per fp16 K = 16 one — the same tensor time; full: three fp16 terms)."""
+    total = 0
+    for convs, mode in ((netdefs.POLICY_CONVS, prec[0]), (netdefs.VALUE_CONVS, prec[1])):
+        for i, c in enumerate(convs[:-1]):   # the last conv (C -> 1) is folded into the epilogue
+            terms = {0: 1, 1: 2, 2: 2 if i == 0 else 3}[mode]   # (binary inputs have no residual: the first layer splits the weights only)
+            rows = -(-batch * (441 if c.k == 5 else 400) // 512) * 512
+            total += 2 * rows * c.k * c.k * c.c_in * c.c_out * terms
+    return total
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -282,6 +296,8 @@ def run_ours(args):
                          args.value_precision if args.value_precision is not None else ev.get_option("value_precision"))
     if args.no_graphs:
         ev.set_option("use_graphs", 0)
+    for kv in args.opt:   # A/B of run-time library options, recorded in config.options
+        ev.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     prec = (ev.get_option("policy_precision"), ev.get_option("value_precision"))
     pp, vp, rot = load_positions()
     n_pos = pp.shape[0]
@@ -434,7 +450,7 @@ def run_ours(args):
                        "l2": "flushed between steps (256 MB write)" if args.flush_l2 else
                              f"inputs larger than L2: {n_sets} input batches = {n_sets * set_bytes / 2**20:.0f} MB, one per step; weights + workspace stay warm",
                        "precision": {"policy": prec[0], "value": prec[1], "legend": "0 fp16 operands, 1 lite (fp16 + e4m3 corrections), 2 full split operands"},
-                       "parity": parity,
+                       "parity": parity, **({"options": args.opt} if args.opt else {}),
                        "cuda_graphs": {"enabled": bool(ev.get_option("use_graphs")), "graph_launches_in_timed_region": graph_launches},
                        "flops_per_position": flops_pos,
                        "pct_of_bf16_burst_peak_whole_step": 100.0 * flops_pos * value / n_gpus / (peak_burst * 1e12),
@@ -449,7 +465,12 @@ def run_ours(args):
                          "peak_sustained": peak_sustained, "frac_of_sustained": achieved / peak_sustained,
                          "flops_per_launch": TRUNK_FLOPS * B, "launch_ms": trunk_s * 1e3,
                          "flops_note": "algorithmic (dense im2col-GEMM count of the reference); the correction terms of the "
-                                       "split-operand modes are extra tensor work and are not counted"},
+                                       "split-operand modes are extra tensor work and are not counted",
+                         "executed": {"tflops": executed_trunk_flops(prec, B) / trunk_s / 1e12 if trunk_s > 0 else 0.0,
+                                      "frac_of_burst": executed_trunk_flops(prec, B) / trunk_s / 1e12 / peak_burst if trunk_s > 0 else 0.0,
+                                      "per_algorithmic": executed_trunk_flops(prec, B) / (TRUNK_FLOPS * B),
+                                      "note": "bf16-equivalent tensor work the launch really issues: padded row space (400 or 441 rows per "
+                                              "361-point position) x the K-loop terms of the precision mode; explanatory, not the roofline figure"}},
             "e2e": {"value": e2e_values[n_main], "unit": UNIT, "h2d_bytes_per_step": B * (2 * 1444 + 1),
                     "d2h_bytes_per_step": B * (1444 + 4), "host_threads": n_main, "steps": e2e_steps,
                     "timing": f"host clock from the release of {n_main} persistent, warmed-up caller thread(s) to the last result; "
@@ -489,6 +510,7 @@ def main():
     ap.add_argument("--precise", action="store_true", help="both nets in full split-operand precision (2, 2): 3x the tensor work; the roofline "
                     "still counts the ALGORITHMIC flops")
     ap.add_argument("--no-graphs", action="store_true", help="A/B: separate kernel launches instead of one CUDA graph per evaluation")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE", help="A/B: set a run-time library option (lb2_set_option), repeatable")
     ap.add_argument("--e2e-threads", type=int, default=2, help="host threads calling the C ABI concurrently in the e2e leg")
     args = ap.parse_args()
     if args.engine:
@@ -503,7 +525,8 @@ def main():
                "--e2e-threads", str(args.e2e_threads)] + (["--flush-l2"] if args.flush_l2 else []) + (["--no-cpu"] if args.no_cpu else []) + \
               (["--precise"] if args.precise else []) + (["--no-graphs"] if args.no_graphs else []) + \
               (["--policy-precision", str(args.policy_precision)] if args.policy_precision is not None else []) + \
-              (["--value-precision", str(args.value_precision)] if args.value_precision is not None else [])
+              (["--value-precision", str(args.value_precision)] if args.value_precision is not None else []) + \
+              [x for kv in args.opt for x in ("--opt", kv)]
         return subprocess.call(cmd)
     return run_ours(args)
 

@@ -66,7 +66,8 @@ void usage() {
                  "      --extra_symmetry N  Visits per extra symmetry of the policy net (GPU default 350).\n"
                  "      --gpu ID            B200 device(s) to use (repeatable; weights replicated, batches sharded).\n"
                  "      --weights FILE      Network weights file (or LB2_WEIGHTS).\n"
-                 "      --own-planes        Build the feature planes with the library's own board (lb2_planes_from_position).\n"
+                 "      --own-planes        Build the feature planes with the library's own board (lb2_planes_from_position): the default.\n"
+                 "      --ref-planes        Build them through the reference's board queries instead (bit-identical, slower).\n"
                  "      --check-planes      Build them both ways and abort on the first difference.\n"
                  "      --max-outstanding N Async policy requests per search thread (default 2).\n"
                  "      --batch N           Positions per device pass (default 256).\n"
@@ -210,6 +211,7 @@ int main(int argc, char* argv[]) {
         else if (a == "--gpu") cfg_gpus.push_back(atoi(value("--gpu")));
         else if (a == "--weights") leela_b200::set_weights_path(value("--weights"));
         else if (a == "--own-planes") leela_b200::set_planes_mode(1);
+        else if (a == "--ref-planes") leela_b200::set_planes_mode(0);
         else if (a == "--check-planes") leela_b200::set_planes_mode(2);
         else if (a == "--noselftest") no_selftest = true;
         else if (a == "--max-outstanding") leela_b200::set_max_outstanding(atoi(value("--max-outstanding")));

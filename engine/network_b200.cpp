@@ -60,7 +60,7 @@ namespace {
 lb2_ctx* g_ctx = nullptr;
 std::string g_weights_path;
 int g_max_outstanding = 2;   // per search thread, as OpenCL::thread_can_issue (OpenCL.cpp:446-454)
-int g_planes_mode = 0;       // 0: planes through the reference's board queries; 1: lb2_planes_from_position (own board);
+int g_planes_mode = 1;       // 1 (default): lb2_planes_from_position (own board, 2-12x faster); 0: planes through the reference's board queries;
                              // 2: both, and abort on the first difference (cross-check on the positions a real search visits)
 std::atomic<long> g_planes_checked{0};
 thread_local std::atomic<int> t_results_outstanding{0};

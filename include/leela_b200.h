@@ -197,6 +197,10 @@ int lb2_device_count(lb2_ctx* ctx);
  *                 cached CUDA graph (default); 0 = always as separate launches
  *   "spin_wait":  1 = a blocking call polls for its results, yielding the core between polls (default); 0 = it sleeps
  *                 on a blocking-sync event (frees the core, adds wake-up latency)
+ *   "queue_linger": 1 = a dispatcher of the submit queue that holds a free I/O slot lets requests accumulate while the device
+ *                 is still computing the previous batch (kernels of one device run one after the other, and a small pass
+ *                 costs the same ~130 us whatever its size), until that pass is done or a full batch is waiting (default);
+ *                 0 = it carries off whatever has arrived at once
  *   "max_batch":  positions per device pass (larger calls are chunked), default 256
  *   "profile_trunk": 1 = bracket every trunk launch with CUDA events (nodes of the graph when graphs are on);
  *                 lb2_get_option("trunk_ns") then returns the device nanoseconds accumulated since the last query.

@@ -26,6 +26,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -120,6 +121,8 @@ struct NetDev {
     __half* x0 = nullptr;           // first-conv input (S=21 row space)
     __half* act[2] = {nullptr, nullptr};
     float* zbuf = nullptr;          // fused-head partial sums [splits * parts][9][rows3]
+    float* head_partial = nullptr;  // value head: partial inner products per (position group, matrix slice), see heads_kernel
+    uint32_t* head_count = nullptr; // ... and the groups' arrival counters (zero at rest)
     uint32_t* flags = nullptr;
     int flags_stride = 0;
     CUtensorMap tm_x0, tm_act[2];
@@ -135,6 +138,9 @@ struct IoSlot {
     cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
     int cap = 0;
     bool busy = false;
+    // 0: free; 1: taken, work being enqueued; 2: kernels enqueued and ev_done recorded behind them; 3: taken by a dispatcher of
+    // the submit queue that is letting requests accumulate (linger_for_device)
+    std::atomic<int> phase{0};
     uint32_t* d_planes[2] = {nullptr, nullptr};
     uint8_t* d_rot = nullptr;
     float *d_probs = nullptr, *d_win = nullptr;
@@ -264,6 +270,8 @@ struct lb2_ctx {
                                   // and the launch 5 % SLOWER (634 k -> 705 k cycles: 100 items per layer and group leave the clusters waiting
                                   // at every layer transition; HBM traffic was never the limit) -> off
     long small_batch = 48;        // device passes of up to this many positions run every layer as two column splits (0 = never)
+    long queue_linger = 1; // 1: a dispatcher of the submit queue with a free I/O slot lets requests accumulate while the device is still
+                           // computing the other slot's batch (see linger_for_device); 0: it takes what is there at once
     long spin_wait = 1;    // 1: a blocking call polls its completion event (yielding the core between polls); 0: it sleeps on it
     std::atomic<long> option_epoch{0};   // bumped by lb2_set_option: cached graphs of older epochs are rebuilt
     std::atomic<long> launches{0}, graph_launches{0};
@@ -286,6 +294,7 @@ struct lb2_ctx {
     int q_cap = 0;                         // positions per batch buffer
     bool worker_run = false;
     int workers_busy = 0;
+    std::atomic<long> q_waiting{0};        // positions in the open and sealed batches (read without q_mu by lingering dispatchers)
     int q_idle_workers = 0;                // dispatchers asleep on q_cv (a submitter only signals when there is one)
     std::vector<std::thread> workers;      // kDispatchersPerDevice per device
     std::string q_error;                   // text of the last asynchronous failure (reported by lb2_drain)
@@ -473,7 +482,8 @@ int make_act_tmap(CUtensorMap* tm, __half* base, int rows, int chunks, int halo)
 
 void free_workspace(NetDev* nd) {
     cudaFree(nd->planes); cudaFree(nd->act[0]); cudaFree(nd->act[1]);
-    cudaFree(nd->flags); cudaFree(nd->x0); cudaFree(nd->zbuf);
+    cudaFree(nd->flags); cudaFree(nd->x0); cudaFree(nd->zbuf); cudaFree(nd->head_partial); cudaFree(nd->head_count);
+    nd->head_partial = nullptr; nd->head_count = nullptr;
     nd->planes = nullptr; nd->act[0] = nd->act[1] = nullptr; nd->flags = nullptr; nd->x0 = nullptr; nd->zbuf = nullptr;
     nd->cap = 0;
 }
@@ -490,6 +500,11 @@ int ensure_workspace(NetDev* nd, int cap) {
     CU_TRY(cudaMalloc(&nd->x0, x0_bytes));
     CU_TRY(cudaMemset(nd->x0, 0, x0_bytes));
     CU_TRY(cudaMalloc(&nd->zbuf, (size_t)9 * lb2::kColParts * lb2::kMaxSplit * nd->rows3 * sizeof(float)));
+    if (nd->hidden) {
+        CU_TRY(cudaMalloc(&nd->head_partial, lb2::heads_partial_floats(cap) * sizeof(float)));
+        CU_TRY(cudaMalloc(&nd->head_count, lb2::heads_count_words(cap) * sizeof(uint32_t)));
+        CU_TRY(cudaMemset(nd->head_count, 0, lb2::heads_count_words(cap) * sizeof(uint32_t)));
+    }
     CU_TRY(cudaMalloc(&nd->act[0], act_bytes));
     CU_TRY(cudaMalloc(&nd->act[1], act_bytes));
     CU_TRY(cudaMemset(nd->act[0], 0, act_bytes));  // padding rows/columns must start (and stay) zero
@@ -846,6 +861,7 @@ int build_plan(const Options& o, DeviceState* d, const EvalKey& key, EvalPlan* p
         ha.v_zbuf = nd.zbuf; ha.v_chunk_rows = nd.rows3; ha.v_bias = nd.head_b; ha.ip1_wt = nd.ip1_wt; ha.ip1_b = nd.ip1_b;
         ha.hidden = nd.hidden; ha.ip2_w = nd.ip2_w; ha.ip2_b = nd.ip2_b; ha.winrate = static_cast<float*>(key.out[1]); ha.n_value = n;
         ha.v_parts = nd.trunk.back().nat.n_split * lb2::kColParts;
+        ha.v_partial = nd.head_partial; ha.v_count = nd.head_count;
         pl->heads = true;
     }
     ha.trace = d->trace;
@@ -1091,7 +1107,8 @@ void free_slot(IoSlot* sl) {
     if (sl->ev_done) cudaEventDestroy(sl->ev_done);
     if (sl->ev_out) cudaEventDestroy(sl->ev_out);
     if (sl->stream) cudaStreamDestroy(sl->stream);
-    *sl = IoSlot();
+    sl->~IoSlot();
+    new (sl) IoSlot();
 }
 
 // Buffers of a slot for `cap` device positions. The owner of the slot calls this; growing drops the device's cached
@@ -1145,6 +1162,7 @@ bool acquire_slot(lb2_ctx* ctx, int prefer, bool wait, int* dev_out, int* slot_o
                     if (!d.slots[s].busy) { free_slots++; if (pick < 0) pick = s; }
                 if (free_slots >= want_free && pick >= 0) {
                     d.slots[pick].busy = true;
+                    d.slots[pick].phase.store(1, std::memory_order_release);
                     *dev_out = (start + i) % ndev;
                     *slot_out = pick;
                     return true;
@@ -1158,6 +1176,7 @@ void release_slot(lb2_ctx* ctx, int dev, int slot) {
     {
         std::lock_guard<std::mutex> lk(ctx->slot_mu);
         ctx->dev[dev]->slots[slot].busy = false;
+        ctx->dev[dev]->slots[slot].phase.store(0, std::memory_order_release);
     }
     ctx->slot_cv.notify_all();
 }
@@ -1226,6 +1245,7 @@ int enqueue_chunk(const HostCall& c, const Chunk& ch, int cap) {
     }
     if ((rc = eval_on_device(c.ctx, c.opt, d, key, ch.slot, d->stream))) return rc;
     CU_TRY(cudaEventRecord(sl->ev_done, d->stream));
+    sl->phase.store(2, std::memory_order_release);
     CU_TRY(cudaStreamWaitEvent(sl->stream, sl->ev_done, 0));
     if (c.need[0])
         CU_TRY(cudaMemcpyAsync(c.pin_probs ? c.probs + (size_t)ch.lo * lb2::kPoints : sl->h_probs, res_probs,
@@ -1366,6 +1386,29 @@ QueueBatch* new_queue_batch(lb2_ctx* ctx) {
     return ctx->q_all.back().get();
 }
 
+// A dispatcher holds a free I/O slot of `dev` while the device's compute stream still runs the batch of the other slot:
+// kernels of one device execute one after the other, and below ~90 positions a pass costs the same ~130 us whatever its size
+// (12 chained layers), so carrying off the two or three requests that have arrived so far would only put a second
+// latency-bound pass behind the first. Let them accumulate until the running pass is done (ev_done: its kernels, not its
+// copy down) or a full batch is waiting; the copy up and the launch of the new batch then overlap the old one's copy down
+// and callbacks. (16 submitting threads: 46 k -> requests/s, see profiles/r2_queue_linger.json.)
+void linger_for_device(lb2_ctx* ctx, int dev, int slot) {
+    static_assert(kIoSlots == 2, "the other slot");
+    IoSlot& mine = ctx->dev[dev]->slots[slot];
+    IoSlot& other = ctx->dev[dev]->slots[slot ^ 1];
+    // phase 3 = "waiting here": two dispatchers that took the two slots of an idle device at the same moment must not
+    // wait for each other — whoever sees the other one lingering (3) or free (0) goes ahead
+    mine.phase.store(3, std::memory_order_seq_cst);
+    for (;;) {
+        const int ph = other.phase.load(std::memory_order_seq_cst);
+        if (ph == 0 || ph == 3) break;
+        if (ph == 2 && cudaEventQuery(other.ev_done) != cudaErrorNotReady) break;
+        if (ctx->q_waiting.load(std::memory_order_relaxed) >= ctx->q_cap) break;
+        std::this_thread::yield();
+    }
+    mine.phase.store(1, std::memory_order_seq_cst);
+}
+
 void worker_loop(lb2_ctx* ctx, int dev_index) {
     cudaSetDevice(ctx->dev[dev_index]->id);
     auto have_work = [&] { return !ctx->q_ready.empty() || (ctx->q_open[0] && ctx->q_open[0]->n) || (ctx->q_open[1] && ctx->q_open[1]->n); };
@@ -1382,6 +1425,9 @@ void worker_loop(lb2_ctx* ctx, int dev_index) {
         // much time as a medium one: below ~90 positions a pass is bound by the latency of its 12 chained layers.)
         int dev = -1, slot = -1;
         acquire_slot(ctx, dev_index, true, &dev, &slot);
+        bool linger;
+        { std::lock_guard<std::mutex> ol(ctx->opt_mu); linger = ctx->queue_linger != 0; }
+        if (linger) linger_for_device(ctx, dev, slot);
         QueueBatch* b = nullptr;
         {
             std::lock_guard<std::mutex> lk(ctx->q_mu);
@@ -1395,7 +1441,7 @@ void worker_loop(lb2_ctx* ctx, int dev_index) {
                     if (ctx->q_open[i] && ctx->q_open[i]->n && (k < 0 || ctx->q_open[i]->n > ctx->q_open[k]->n)) k = i;
                 if (k >= 0) { b = ctx->q_open[k]; ctx->q_open[k] = nullptr; }
             }
-            if (b) ctx->workers_busy++;
+            if (b) { ctx->workers_busy++; ctx->q_waiting.fetch_sub(b->n, std::memory_order_relaxed); }
         }
         if (!b) {   // another dispatcher took it meanwhile
             release_slot(ctx, dev, slot);
@@ -1476,6 +1522,7 @@ int submit(lb2_ctx* ctx, int kind, const uint32_t* planes, const uint8_t* rot, i
         memcpy(open->planes + (size_t)open->n * lb2::kPoints, planes, (size_t)n * lb2::kPoints * sizeof(uint32_t));
         memcpy(open->rot + open->n, rot, n);
         open->n += n;
+        ctx->q_waiting.fetch_add(n, std::memory_order_relaxed);
         open->req.push_back(QueueRequest{out, n, cb, user});
         break;
     }
@@ -1823,6 +1870,8 @@ int lb2_set_option(lb2_ctx* ctx, const char* name, long value) {
         ctx->use_graphs = value ? 1 : 0;
     } else if (!strcmp(name, "spin_wait")) {
         ctx->spin_wait = value ? 1 : 0;
+    } else if (!strcmp(name, "queue_linger")) {
+        ctx->queue_linger = value ? 1 : 0;
     } else if (!strcmp(name, "small_batch")) {
         if (value < 0) return fail(LB2_ERR_INVALID, "small_batch must be >= 0");
         ctx->small_batch = value;
@@ -1891,6 +1940,7 @@ long lb2_get_option(lb2_ctx* ctx, const char* name) {
     if (!strcmp(name, "dynamic_items")) return ctx->dynamic_items;
     if (!strcmp(name, "use_graphs")) return ctx->use_graphs;
     if (!strcmp(name, "spin_wait")) return ctx->spin_wait;
+    if (!strcmp(name, "queue_linger")) return ctx->queue_linger;
     if (!strcmp(name, "group_positions")) return ctx->group_positions;
     if (!strcmp(name, "small_batch")) return ctx->small_batch;
     if (!strcmp(name, "resident_weights")) return ctx->resident_weights;

@@ -12,6 +12,7 @@
 //   value_head_kernel     last conv (C -> 1) + ELU + ip 361->H + ELU + ip H->1 + (1+tanh)/2
 //                         (Network.cpp:731-737, 395-423; OpenCL innerproduct OpenCL.cpp:407-438)
 #include <cuda_fp8.h>
+#include <algorithm>
 #include <cstdio>
 
 #include "lb2_kernels.cuh"
@@ -1059,148 +1060,158 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// policy head: one CTA per position. logit = ELU(b + conv), softmax with temperature over the
-// 361 points (Network.cpp:450-469), un-rotate (Network.cpp:820-823).
+// Both heads in ONE launch of kHeadThreads-thread blocks, all of them resident at once at batch 256 (round 1 ran the value
+// head as 64 blocks of 1024 threads that each streamed the whole 370 KB ip matrix through 218 KB of shared memory, and the
+// policy head as one such block per position: 320 blocks, one per SM, 2.2 waves, 19 us):
+//   blocks [0, value_blocks): value head, block = (group of kVGroup positions, slice of kVSliceRows rows of the 361 x H matrix)
+//   the rest:                 policy head, kPolicyPerBlock positions per block, 128 threads each
+constexpr int kHeadThreads = 512;
+constexpr int kVGroup = 16;        // positions per value block
+constexpr int kVSliceRows = 41;    // rows (board points) of the 361 x H inner-product matrix per value block
+constexpr int kVSlices = (kPoints + kVSliceRows - 1) / kVSliceRows;   // 9
+constexpr int kVHiddenMax = 256;
+constexpr int kPolicyPerBlock = kHeadThreads / 128;
+
+// policy head: logit = ELU(b + conv), softmax with temperature over the 361 points (Network.cpp:450-469), un-rotate
+// (Network.cpp:820-823). 128 threads per position, three points each.
 __device__ __forceinline__ void policy_head_body(const float* __restrict__ zbuf, int chunk_rows, int n_parts,
                                                  const float* __restrict__ bias, const uint8_t* __restrict__ rotation, int ensemble,
-                                                 float temp, float* __restrict__ probs, int pos, float* smem_f) {
-    float* sm = smem_f;            // [361]
-    float* red = smem_f + 368;     // [12]
-    const int tid = threadIdx.x;
+                                                 float temp, float* __restrict__ probs, int n, int block, float* smem_f) {
+    const int sub = threadIdx.x >> 7, t = threadIdx.x & 127, w = t >> 5;
+    const int pos = block * kPolicyPerBlock + sub;
+    float* sm = smem_f + sub * 384;                       // [361] this position's probabilities
+    float* red = smem_f + kPolicyPerBlock * 384 + sub * 8;  // [4] per-warp partial results
     if (LB2_PDL) grid_dep_wait();
-    if (tid >= 384) return;        // 12 warps do the work (no block-wide barrier below this point involves the rest)
-    float logit = -INFINITY;
-    if (tid < kPoints) {
-        const int y = tid / kBoard, x = tid - y * kBoard;
-        logit = elu1(bias[0] + head_gather(zbuf, chunk_rows, n_parts, pos * 400, y, x));
+    if (pos >= n) return;   // (all 128 threads of the position: its named barrier is not used)
+    float logit[3], e[3];
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int p = t + 128 * k;
+        logit[k] = -INFINITY;
+        if (p < kPoints) {
+            const int y = p / kBoard, x = p - y * kBoard;
+            logit[k] = elu1(bias[0] + head_gather(zbuf, chunk_rows, n_parts, pos * 400, y, x));
+        }
+        m = fmaxf(m, logit[k]);
     }
-    float m = warp_max(logit);
-    if ((tid & 31) == 0) red[tid >> 5] = m;
-    named_bar_sync(3, 384);
-    m = red[0];
-    for (int i = 1; i < 12; i++) m = fmaxf(m, red[i]);
-    named_bar_sync(3, 384);
-    const float e = (tid < kPoints) ? expf(logit / temp - m / temp) : 0.0f;
-    float s = warp_sum(e);
-    if ((tid & 31) == 0) red[tid >> 5] = s;
-    named_bar_sync(3, 384);
-    s = 0.0f;
-    for (int i = 0; i < 12; i++) s += red[i];
-    if (tid < kPoints) sm[tid] = e / s;
-    named_bar_sync(3, 384);
-    if (tid < kPoints) probs[(size_t)pos * kPoints + tid] = sm[rev_rotate_idx(tid, ensemble ? (pos & 7) : (rotation[pos] & 7))];
+    m = warp_max(m);
+    if ((t & 31) == 0) red[w] = m;
+    named_bar_sync(1 + sub, 128);
+    m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    named_bar_sync(1 + sub, 128);
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        e[k] = (t + 128 * k < kPoints) ? expf(logit[k] / temp - m / temp) : 0.0f;
+        s += e[k];
+    }
+    s = warp_sum(s);
+    if ((t & 31) == 0) red[w] = s;
+    named_bar_sync(1 + sub, 128);
+    s = (red[0] + red[1]) + (red[2] + red[3]);
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        if (t + 128 * k < kPoints) sm[t + 128 * k] = e[k] / s;
+    named_bar_sync(1 + sub, 128);
+    const int rot = ensemble ? (pos & 7) : (rotation[pos] & 7);
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        if (t + 128 * k < kPoints) probs[(size_t)pos * kPoints + t + 128 * k] = sm[rev_rotate_idx(t + 128 * k, rot)];
 }
 
-// value head: kValueGroup positions per CTA. v = ELU(b + conv) [361]; h = ELU(W1 v + b1);
-// out = (1 + tanh(w2.h + b2)) / 2. The 361 x H matrix W1 (fp32, 370 KB) is streamed through a
-// 4-slot shared-memory ring with bulk copies (19 tiles of 19 input rows) so the kernel runs at
-// copy bandwidth instead of one L2/HBM round trip per unrolled load batch.
-constexpr int kValueGroup = 4;
-constexpr int kValueThreads = 1024;  // thread (o, part): output o, input rows part, part+4, ... of each tile
-#ifndef LB2_VTILE_ROWS
-#define LB2_VTILE_ROWS 64
-#endif
-constexpr int kVTileRows = LB2_VTILE_ROWS;                      // rows of the 361 x H matrix per ring slot
-constexpr int kVTiles = (kPoints + kVTileRows - 1) / kVTileRows;
-constexpr int kVSlots = kVTileRows >= 48 ? 3 : 4;
-
-__device__ __forceinline__ void value_head_body(const float* __restrict__ zbuf, int chunk_rows, int n_zparts,
-                                                const float* __restrict__ bias,
-                                                const float* __restrict__ ip1_wt /*[361][hidden]*/,
-                                                const float* __restrict__ ip1_b, int hidden,
-                                                const float* __restrict__ ip2_w, const float* __restrict__ ip2_b, int n,
-                                                float* __restrict__ winrate, int block, uint8_t* vsm) {
-    float* w_s = reinterpret_cast<float*>(vsm);                       // [kVSlots][19][hidden]
-    float* v_s = w_s + kVSlots * kVTileRows * hidden;                 // [361][G]
-    float* h_s = v_s + kValueGroup * kPoints;                         // [G][hidden]
-    float* part_s = h_s + kValueGroup * hidden;                       // [3][G][hidden]
-    uint64_t* full = reinterpret_cast<uint64_t*>(part_s + 3 * kValueGroup * hidden);  // [kVSlots]
+// value head: v = ELU(b + conv) [361]; h = ELU(W1 v + b1); out = (1 + tanh(w2.h + b2)) / 2 (Network.cpp:731-737, 395-423).
+// Block (g, s) multiplies rows [s * 41, s * 41 + 41) of W1 (one bulk copy into shared memory, <= 42 KB) with the matching
+// points of positions [16 g, 16 g + 16) and leaves its partial sums in `partial`; the block that arrives last at the
+// group's counter adds the nine slices IN SLICE ORDER (so a position's result does not depend on which block that was, nor
+// on the batch around it), applies b1 + ELU, the second inner product and the tanh, and zeroes the counter for the next launch.
+__device__ __forceinline__ void value_head_body(const HeadArgs& A, int block, uint8_t* vsm) {
+    const int hidden = A.hidden, n = A.n_value;
+    float* w_s = reinterpret_cast<float*>(vsm);                                  // [41][hidden]; later h [16][hidden]
+    const int w_floats = (kVSliceRows * hidden > kVGroup * kVHiddenMax) ? kVSliceRows * hidden : kVGroup * kVHiddenMax;
+    float* v_s = w_s + w_floats;                                                 // [41][16]
+    uint64_t* full = reinterpret_cast<uint64_t*>(v_s + kVSliceRows * kVGroup);
+    uint32_t* last_s = reinterpret_cast<uint32_t*>(full + 1);
     const int tid = threadIdx.x;
-    const int pos0 = block * kValueGroup;
-    auto tile_rows = [](int t) { return min(kVTileRows, kPoints - t * kVTileRows); };
-    auto tile_bytes = [&](int t) { return (uint32_t)(tile_rows(t) * hidden * sizeof(float)); };
+    const int g = block / kVSlices, s = block - g * kVSlices;
+    const int row0 = s * kVSliceRows, rows = min(kVSliceRows, kPoints - row0);
+    const int pos0 = g * kVGroup;
     if (tid == 0) {
-        for (int i = 0; i < kVSlots; i++) mbar_init(full + i, 1);
+        mbar_init(full, 1);
         fence_mbar_init();
         fence_proxy_async_smem();
-        for (int t = 0; t < kVSlots - 1 && t < kVTiles; t++) {  // prefetch distance kVSlots - 1
-            mbar_arrive_expect_tx(full + t, tile_bytes(t));
-            bulk_load_1d(w_s + t * kVTileRows * hidden, ip1_wt + (size_t)t * kVTileRows * hidden, tile_bytes(t), full + t);
-        }
+        const uint32_t bytes = (uint32_t)(rows * hidden * sizeof(float));
+        mbar_arrive_expect_tx(full, bytes);
+        bulk_load_1d(w_s, A.ip1_wt + (size_t)row0 * hidden, bytes, full);
     }
-    if (LB2_PDL) grid_dep_wait();   // the weight tiles above do not depend on the trunk; zbuf does
-    for (int i = tid; i < kValueGroup * kPoints; i += blockDim.x) {
-        const int g = i / kPoints, p = i - g * kPoints;
+    if (LB2_PDL) grid_dep_wait();   // the weights above do not depend on the trunk; zbuf does
+    for (int i = tid; i < kVGroup * rows; i += kHeadThreads) {   // consecutive threads: consecutive points of one position
+        const int gp = i / rows, r = i - gp * rows;
         float v = 0.0f;
-        if (pos0 + g < n) {
-            const int y = p / kBoard, x = p - y * kBoard;
-            v = elu1(bias[0] + head_gather(zbuf, chunk_rows, n_zparts, (pos0 + g) * 400, y, x));
+        if (pos0 + gp < n) {
+            const int p = row0 + r, y = p / kBoard, x = p - y * kBoard;
+            v = elu1(A.v_bias[0] + head_gather(A.v_zbuf, A.v_chunk_rows, A.v_parts, (pos0 + gp) * 400, y, x));
         }
-        v_s[p * kValueGroup + g] = v;
+        v_s[r * kVGroup + gp] = v;
     }
     __syncthreads();
-    const int o = tid % hidden, part = tid / hidden, n_parts = min((int)blockDim.x / hidden, 4);
-    float a[kValueGroup];
+    mbar_wait(full, 0);
+    const int o = tid & (kVHiddenMax - 1), half = tid >> 8;   // output o, positions [8 half, 8 half + 8) of the group
+    float a[8];
 #pragma unroll
-    for (int g = 0; g < kValueGroup; g++) a[g] = 0.0f;
-    for (int t = 0; t < kVTiles; t++) {
-        const int slot = t % kVSlots;
-        mbar_wait(full + slot, (t / kVSlots) & 1);
-        if (part < n_parts) {
-            const float* wt = w_s + slot * kVTileRows * hidden + o;
-            const int rows = tile_rows(t);
+    for (int j = 0; j < 8; j++) a[j] = 0.0f;
+    if (o < hidden) {
 #pragma unroll 4
-            for (int row = part; row < rows; row += n_parts) {   // n_parts == 4 for hidden == 256
-                const float wv = wt[row * hidden];
-                const float4 v0 = *reinterpret_cast<const float4*>(v_s + (t * kVTileRows + row) * kValueGroup);
-                a[0] = fmaf(wv, v0.x, a[0]); a[1] = fmaf(wv, v0.y, a[1]); a[2] = fmaf(wv, v0.z, a[2]); a[3] = fmaf(wv, v0.w, a[3]);
-            }
+        for (int r = 0; r < rows; r++) {
+            const float wv = w_s[r * hidden + o];
+            const float4 v0 = *reinterpret_cast<const float4*>(v_s + r * kVGroup + half * 8);
+            const float4 v1 = *reinterpret_cast<const float4*>(v_s + r * kVGroup + half * 8 + 4);
+            a[0] = fmaf(wv, v0.x, a[0]); a[1] = fmaf(wv, v0.y, a[1]); a[2] = fmaf(wv, v0.z, a[2]); a[3] = fmaf(wv, v0.w, a[3]);
+            a[4] = fmaf(wv, v1.x, a[4]); a[5] = fmaf(wv, v1.y, a[5]); a[6] = fmaf(wv, v1.z, a[6]); a[7] = fmaf(wv, v1.w, a[7]);
         }
-        __syncthreads();  // everyone is done with this slot's predecessor: refill it
-        if (tid == 0 && t + kVSlots - 1 < kVTiles) {
-            const int tn = t + kVSlots - 1, sn = tn % kVSlots;
-            mbar_arrive_expect_tx(full + sn, tile_bytes(tn));
-            bulk_load_1d(w_s + sn * kVTileRows * hidden, ip1_wt + (size_t)tn * kVTileRows * hidden, tile_bytes(tn), full + sn);
-        }
-    }
-    if (part > 0 && part < n_parts) {
+        float* part = A.v_partial + ((size_t)(g * kVSlices + s) * kVGroup + half * 8) * kVHiddenMax + o;
 #pragma unroll
-        for (int g = 0; g < kValueGroup; g++) part_s[((part - 1) * kValueGroup + g) * hidden + o] = a[g];
+        for (int j = 0; j < 8; j++) part[(size_t)j * kVHiddenMax] = a[j];
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) *last_s = (atomicAdd(A.v_count + g, 1u) == (uint32_t)(kVSlices - 1)) ? 1u : 0u;
+    __syncthreads();
+    if (!*last_s) return;
+    __threadfence();
+    float* h_s = w_s;   // (every thread of this block is past its reads of the weight slice)
+    if (o < hidden) {
+        const float* part = A.v_partial + ((size_t)g * kVSlices * kVGroup + half * 8) * kVHiddenMax + o;
+        const float b1 = A.ip1_b[o];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            float sum = __ldcg(part + (size_t)j * kVHiddenMax);
+            for (int s2 = 1; s2 < kVSlices; s2++) sum += __ldcg(part + ((size_t)s2 * kVGroup + j) * kVHiddenMax);
+            h_s[(half * 8 + j) * hidden + o] = elu1(sum + b1);
+        }
     }
     __syncthreads();
-    if (part == 0) {
-#pragma unroll
-        for (int g = 0; g < kValueGroup; g++) {
-            float sum = a[g];
-            for (int p = 1; p < n_parts; p++) sum += part_s[((p - 1) * kValueGroup + g) * hidden + o];
-            h_s[g * hidden + o] = elu1(sum + ip1_b[o]);
-        }
+    const int warp = tid >> 5, lane = tid & 31;   // 16 warps: one position each
+    if (pos0 + warp < n) {
+        float d = 0.0f;
+        for (int k = lane; k < hidden; k += 32) d = fmaf(A.ip2_w[k], h_s[warp * hidden + k], d);
+        d = warp_sum(d);
+        if (lane == 0) A.winrate[pos0 + warp] = (1.0f + tanhf(d + A.ip2_b[0])) * 0.5f;
     }
-    __syncthreads();
-    const int warp = tid >> 5, lane = tid & 31;
-    if (warp < kValueGroup && pos0 + warp < n) {
-        float s = 0.0f;
-        for (int k = lane; k < hidden; k += 32) s = fmaf(ip2_w[k], h_s[warp * hidden + k], s);
-        s = warp_sum(s);
-        if (lane == 0) winrate[pos0 + warp] = (1.0f + tanhf(s + ip2_b[0])) * 0.5f;
-    }
+    if (tid == 0) A.v_count[g] = 0;
 }
 
-// Both heads in one launch: blocks [0, value_blocks) run the value head, the rest the policy head
-// (one position per block, first 384 threads). (Keeping the launch to one wave — the policy blocks
-// looping over positions on the SMs the value head leaves free — measured the same 20 us: dropped.)
-__global__ void __launch_bounds__(kValueThreads) heads_kernel(const HeadArgs A) {
+__global__ void __launch_bounds__(kHeadThreads) heads_kernel(const HeadArgs A) {
     extern __shared__ __align__(128) uint8_t hsm[];
-    const int value_blocks = (A.n_value + kValueGroup - 1) / kValueGroup;
+    const int value_blocks = ((A.n_value + kVGroup - 1) / kVGroup) * kVSlices;
     unsigned long long* tr = (A.trace && threadIdx.x == 0 && (int)blockIdx.x < A.trace_ctas)
                                  ? A.trace + ((size_t)blockIdx.x * kTraceItems + (kTraceItems - 2)) * kTraceEvents : nullptr;
     if (tr) tr[0] = global_ns();
     if ((int)blockIdx.x < value_blocks)
-        value_head_body(A.v_zbuf, A.v_chunk_rows, A.v_parts, A.v_bias, A.ip1_wt, A.ip1_b, A.hidden, A.ip2_w, A.ip2_b, A.n_value,
-                        A.winrate, blockIdx.x, hsm);
+        value_head_body(A, blockIdx.x, hsm);
     else
-        policy_head_body(A.p_zbuf, A.p_chunk_rows, A.p_parts, A.p_bias, A.rotation, A.ensemble, A.temp, A.probs, blockIdx.x - value_blocks,
-                         reinterpret_cast<float*>(hsm));
+        policy_head_body(A.p_zbuf, A.p_chunk_rows, A.p_parts, A.p_bias, A.rotation, A.ensemble, A.temp, A.probs, A.n_policy,
+                         blockIdx.x - value_blocks, reinterpret_cast<float*>(hsm));
     if (tr) tr[8] = global_ns();
 }
 
@@ -1292,16 +1303,21 @@ cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool 
     return cudaErrorInvalidValue;
 }
 
+size_t heads_partial_floats(int n_value) { return (size_t)((n_value + kVGroup - 1) / kVGroup) * kVSlices * kVGroup * kVHiddenMax; }
+size_t heads_count_words(int n_value) { return (size_t)((n_value + kVGroup - 1) / kVGroup); }
+
 cudaError_t launch_heads(const HeadArgs& a, cudaStream_t st) {
-    const int value_blocks = (a.n_value + kValueGroup - 1) / kValueGroup;
-    const int blocks = value_blocks + a.n_policy;
+    const int value_blocks = ((a.n_value + kVGroup - 1) / kVGroup) * kVSlices;
+    const int blocks = value_blocks + (a.n_policy + kPolicyPerBlock - 1) / kPolicyPerBlock;
     if (blocks == 0) return cudaSuccess;
-    size_t smem = 2048;  // policy head scratch
-    if (a.n_value)
-        smem = ((size_t)kVSlots * kVTileRows * a.hidden + kValueGroup * kPoints + 4 * kValueGroup * a.hidden) * sizeof(float) + 64;
+    size_t smem = (size_t)kPolicyPerBlock * (384 + 8) * sizeof(float);  // policy head scratch
+    if (a.n_value) {
+        const size_t w_floats = std::max(kVSliceRows * a.hidden, kVGroup * kVHiddenMax);
+        smem = std::max(smem, (w_floats + kVSliceRows * kVGroup) * sizeof(float) + 64);
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(blocks);
-    cfg.blockDim = dim3(kValueThreads);
+    cfg.blockDim = dim3(kHeadThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];

@@ -168,6 +168,8 @@ struct HeadArgs {
     const float* v_zbuf; int32_t v_chunk_rows; const float* v_bias; const float* ip1_wt; const float* ip1_b; int32_t hidden;
     const float* ip2_w; const float* ip2_b; float* winrate; int32_t n_value; int32_t v_parts;
     int32_t ensemble;            // 1: position p was evaluated under symmetry p % 8 (rotation is unused)
+    float* v_partial;            // value head workspace: per (group of 16 positions, slice of the 361 x H matrix) partial sums [16][256]
+    uint32_t* v_count;           // ... and per group the number of slices done (zero between launches)
     unsigned long long* trace;   // debug timeline (option "trace"): block b < trace_ctas stamps %globaltimer at its start and end
     int32_t trace_ctas;          // into slot [b][kTraceItems - 2][0 / 8] (tools/trace_heads.py)
 };
@@ -183,6 +185,8 @@ struct MeanArgs {
 cudaError_t launch_expand(const ExpandArgs& a, cudaStream_t st);
 cudaError_t launch_trunk(const TrunkParams& p, int grid, bool cooperative, bool pair, bool resident, int out_modes, cudaStream_t st);
 cudaError_t launch_heads(const HeadArgs& a, cudaStream_t st);
+size_t heads_partial_floats(int n_value);   // sizes of HeadArgs::v_partial / v_count for up to n_value positions
+size_t heads_count_words(int n_value);
 cudaError_t launch_ensemble_mean(const MeanArgs& a, cudaStream_t st);
 cudaError_t trunk_kernel_setup();
 const void* kernel_address(int which);   // 0 expand, 1 heads, 2 ensemble mean

@@ -26,11 +26,13 @@ needs_engine = pytest.mark.skipif(not os.path.exists(ENGINE), reason="engine not
 
 @needs_engine
 @pytest.mark.skipif(not os.path.exists(HARNESS), reason="reference harness not built")
-@pytest.mark.parametrize("n,seed", [(300, 7), (1500, 99)])
-def test_feature_planes_bit_identical_to_reference(tmp_path, n, seed):
+@pytest.mark.parametrize("n,seed,builder", [(300, 7, "--ref-planes"), (1500, 99, "--ref-planes"), (1500, 99, "--own-planes")])
+def test_feature_planes_bit_identical_to_reference(tmp_path, n, seed, builder):
+    """both of the engine's plane builders — the pass over the reference's own board queries, and (the default) the
+    library's own board through lb2_planes_from_position — against the reference's gather_features on the same games"""
     from oracle import reference
     ours, ref = str(tmp_path / "ours.pos"), str(tmp_path / "ref")
-    subprocess.run([ENGINE, "-q", "--dump-planes", ours, str(n), str(seed)], check=True, timeout=300)
+    subprocess.run([ENGINE, "-q", builder, "--dump-planes", ours, str(n), str(seed)], check=True, timeout=300)
     subprocess.run([HARNESS, "planes", ref, str(n), str(seed)], check=True, timeout=300, env=reference._env())
     a, b = fileio.read_positions(ours), fileio.read_positions(ref + ".pos")
     assert a.n == b.n == n

@@ -3,7 +3,7 @@
 //   T threads, each with ONE request outstanding: lb2_submit_value (or _policy) of 1 position, wait for the callback, repeat.
 // Reports requests/s and the mean device batch. Weights: the synthetic nets of the engine's weight file.
 //   build: g++ -O2 -std=c++17 -Iinclude -o tools/_variants/queue_bench tools/queue_bench.cpp -Lleela_b200 -lleela_b200 -lpthread -Wl,-rpath,$PWD/leela_b200
-//   run:   tools/_variants/queue_bench <weights.lb2w> [threads=64] [seconds=3] [gpus=1] [policy_every=6]
+//   run:   tools/_variants/queue_bench <weights.lb2w> [threads=64] [seconds=3] [gpus=1] [policy_every=6] [queue_linger=1]
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -81,11 +81,13 @@ int main(int argc, char** argv) {
     const double seconds = argc > 3 ? atof(argv[3]) : 3.0;
     const int gpus = argc > 4 ? atoi(argv[4]) : 1;
     const int policy_every = argc > 5 ? atoi(argv[5]) : 6;   // one policy request per this many requests (netbench: 2000 : 10000)
+    const int linger = argc > 6 ? atoi(argv[6]) : 1;
     std::vector<int> ids;
     for (int i = 0; i < gpus; i++) ids.push_back(i);
     lb2_ctx* ctx = nullptr;
     if (lb2_init(ids.data(), gpus, &ctx)) { fprintf(stderr, "lb2_init: %s\n", lb2_last_error()); return 1; }
     if (!load_weights(ctx, argv[1])) return 1;
+    lb2_set_option(ctx, "queue_linger", linger);
     // any bit patterns are valid planes; a few distinct ones so that results differ
     std::vector<uint32_t> planes(16 * 361);
     uint64_t z = 88172645463325252ull;
@@ -123,8 +125,8 @@ int main(int argc, char** argv) {
     lb2_drain(ctx);
     const long pos = lb2_get_option(ctx, "stat_positions") - pos0, bat = lb2_get_option(ctx, "stat_batches") - bat0;
     printf("{\"threads\": %d, \"gpus\": %d, \"seconds\": %.2f, \"requests\": %ld, \"requests_per_s\": %.0f, \"device_batches\": %ld, "
-           "\"mean_device_batch\": %.1f, \"failed\": %ld, \"policy_every\": %d}\n",
-           threads, gpus, dt, total.load(), total.load() / dt, bat, bat ? (double)pos / bat : 0.0, failed.load(), policy_every);
+           "\"mean_device_batch\": %.1f, \"failed\": %ld, \"policy_every\": %d, \"queue_linger\": %d}\n",
+           threads, gpus, dt, total.load(), total.load() / dt, bat, bat ? (double)pos / bat : 0.0, failed.load(), policy_every, linger);
     lb2_destroy(ctx);
     return failed ? 1 : 0;
 }

@@ -17,6 +17,8 @@ rot = torch.from_numpy(g["rotation"][:B].copy()).to(dev)
 probs = torch.empty((B, 361), device=dev); win = torch.empty((B,), device=dev)
 ev = capi.Evaluator(policy=synth.policy_weights(), value=synth.value_weights())
 ev.set_option("max_batch", max(B, 512))
+if "LB2_PRECISION" in os.environ:   # e.g. LB2_PRECISION=0,0 (policy, value)
+    ev.set_precision(*[int(x) for x in os.environ["LB2_PRECISION"].split(",")])
 a = (pp.data_ptr(), vp.data_ptr(), rot.data_ptr(), B, 0.75, probs.data_ptr() if which != "value" else None,
      win.data_ptr() if which != "policy" else None)
 for _ in range(5):
