@@ -493,6 +493,9 @@ int ensure_workspace(NetDev* nd, int cap) {
     free_workspace(nd);
     nd->rows5 = round_up(cap * 441, 2 * lb2::kTileRows);  // whole CTA-pair items
     nd->rows3 = round_up(cap * 400, 2 * lb2::kTileRows);
+    // the kernels index [planes][rows] buffers with 32-bit row offsets (activations: 2 * width / 8 planes; fused-head sums: 36)
+    if ((uint64_t)std::max(2 * nd->width / 8, 9 * lb2::kColParts * lb2::kMaxSplit) * (uint64_t)nd->rows3 >= (1ull << 32))
+        return fail(LB2_ERR_UNSUPPORTED, "batch of %d positions is too large for the activation workspace", cap);
     const size_t x0_bytes = (size_t)4 * nd->rows5 * 16;
     // fp16 planes + the extra planes of the split-operand modes (fp16 residuals, or e4m3 activations and residuals)
     const size_t act_bytes = (size_t)(2 * nd->width / 8) * nd->rows3 * 16;

@@ -46,6 +46,12 @@ constexpr int kEpiGroup = LB2_EPI_GROUP;
                                  // no writes of its own to publish, and the MMA reads the peer's shared memory itself (no cache
                                  // in between). `.release.cluster` cost a MEMBAR.ALL.GPU round trip per stage: trunk 331 -> 319 us.
 #endif
+#ifndef LB2_PEER_DIRECT
+#define LB2_PEER_DIRECT 1        // resident-weights mode, stages that carry activations only: the peer CTA's TMA loads complete on the
+                                 // LEADER's stage barrier (cp.async.bulk.tensor.cta_group::2 with a remote mbarrier) and the peer's
+                                 // producer adds its own arrival there — no local barrier, no forwarding thread in between
+                                 // (the forward hop was ~0.4 us of the ~1.7 us from issuing a load to the MMA warp seeing it)
+#endif
 #ifndef LB2_EPI_PAIR_HALVES
 #define LB2_EPI_PAIR_HALVES 1    // ordinary epilogue: unit u = (half u & 1, column block u >> 1): the two units of a group share
                                  // their eight bias values — one shared-memory read (the port the tensor core's operands come
@@ -386,6 +392,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         int stage = 0; uint32_t phase = 0; uint32_t pit = 0;
         int resident_job = -1;   // kRes: the job whose weights (this CTA's half) are in shared memory
         const uint64_t ld_policy = LB2_L2_HINTS == 2 ? l2_policy_evict_last() : (LB2_L2_HINTS == 3 ? l2_policy_evict_first() : 0);
+        const uint32_t leader_full0 = kPair ? mapa_u32(full_bar, 0) : 0u;   // the leader's full_bar[0] as a shared::cluster address
         for (int jj, idx; item_get(item_ring, pit, jj, idx); pit++) {
             const LayerJob& J = jobs[jj];
             const int tile = tile_of(idx);
@@ -424,16 +431,27 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                 }
                 uint32_t unit_off = 0;   // kRes: byte offset of the stage's weights inside the resident area
                 int term = 0, ts = 0;    // virtual slab s = term * n_real + ts
+                // peer CTA, activations only: straight onto the leader's barrier (see LB2_PEER_DIRECT)
+                const bool direct = LB2_PEER_DIRECT && kRes && !leader && !reload;
                 for (int s = 0; s < n_slabs; s++) {
                     for (int g = 0; g < ng; g++) {
                         const uint32_t b_bytes = (tap_group_end(ksize, g) - tap_group_begin(g)) * n_mine * 32;
                         mbar_wait(empty_bar + st, ph ^ 1);
                         uint8_t* sa = ring + st * kStageBytes;
                         const bool skip_b = (kDebugFlags(P) & 8) != 0 || (kRes && !reload), skip_a = (kDebugFlags(P) & 16) != 0;
+                        // split-operand modes: every term of the K loop has its own set of input chunk planes
+                        const int ac = (term == 0 ? tb0 : (term == 1 ? tb1 : tb2)) + 2 * ts;
+                        if (direct) {
+                            const uint32_t lbar = leader_full0 + 8u * (uint32_t)st;
+                            mbar_arrive_expect_tx_cluster_relaxed(lbar, a_bytes);
+                            if (LB2_L2_HINTS >= 2) tma_load_3d_pair_hint(sa, &P.tmaps[tmap], lbar, 0, row0_8, ac, ld_policy);
+                            else tma_load_3d_pair(sa, &P.tmaps[tmap], lbar, 0, row0_8, ac);
+                            if (++st == kStages) { st = 0; ph ^= 1; }
+                            if (s == 0 && g == 0) LB2_TRACE(pit, 2);
+                            continue;
+                        }
                         mbar_arrive_expect_tx(full_bar + st, (skip_a ? 0u : a_bytes) + (skip_b ? 0u : b_bytes));
                         if (!skip_a) {
-                            // split-operand modes: every term of the K loop has its own set of input chunk planes
-                            const int ac = (term == 0 ? tb0 : (term == 1 ? tb1 : tb2)) + 2 * ts;
                             if (LB2_L2_HINTS >= 2) tma_load_3d_hint(sa, &P.tmaps[tmap], full_bar + st, 0, row0_8, ac, ld_policy);
                             else tma_load_3d(sa, &P.tmaps[tmap], full_bar + st, 0, row0_8, ac);
                         }
@@ -460,13 +478,20 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         // No MMAs are issued here (the leader's tcgen05.mma.cta_group::2 drives both SMs); this
         // warp only tells the leader when each of OUR stages has landed.
         if (lane == 0) {
-            int stage = 0; uint32_t phase = 0; uint32_t fit = 0;
+            // (with LB2_PEER_DIRECT only the stages of an item that brings a new job's weights use our own barriers: the parity
+            // of each is kept per slot)
+            int stage = 0; uint32_t parity = 0; uint32_t fit = 0;
+            int resident_job = -1;
             for (int jj, idx; item_get<true>(item_ring, fit, jj, idx); fit++) {
                 const int n_st = jobs[jj].n_slabs * n_tap_groups(jobs[jj].ksize);
+                const bool direct = LB2_PEER_DIRECT && kRes && jj == resident_job;
+                resident_job = jj;
+                if (direct) { stage = (stage + n_st) % kStages; continue; }
                 for (int s = 0; s < n_st; s++) {
-                    mbar_wait(full_bar + stage, phase);
+                    mbar_wait(full_bar + stage, (parity >> stage) & 1u);
+                    parity ^= 1u << stage;
                     if (LB2_RELAXED_FORWARD) mbar_arrive_remote_relaxed(full_bar + stage, 0); else mbar_arrive_remote(full_bar + stage, 0);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == kStages) stage = 0;
                 }
             }
         }
@@ -621,6 +646,9 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                 // that no launch relies on zeros an earlier launch left behind (dead activation tiles are discarded from L2).
                 skip2[h] = remap && (x > kBoard || y > kBoard || pos >= n_pos);
             }
+            // plane p, row r of a [planes][chunk_rows] buffer, in rows — 32-bit: planes x rows stays below 2^32 for every batch the
+            // host accepts (ensure_workspace), and the 64-bit sign-extending index arithmetic cost the epilogue registers it spilled
+            auto row_off = [&](int plane, int r) { return (uint32_t)plane * (uint32_t)chunk_rows + (uint32_t)r; };
             const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256 + col0;
             // unit -> (half, column block). The fused-head path walks half-major; the ordinary path pairs the halves
             auto unit_addr = [&](int u) { const int h = u >= upc ? 1 : 0; return tbase + h * 128 + (u - h * upc) * 8; };
@@ -704,14 +732,14 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                     }
                     const int c8 = (col0 + cc) >> 3;
                     if (kLo16 && out_mode == kOutLo16) {
-                        __half* lo = out + ((size_t)(lo_chunks + c8) * chunk_rows + out_row) * 8;
+                        __half* lo = out + (size_t)row_off(lo_chunks + c8, out_row) * 8;
                         if (LB2_L2_HINTS) st_global_v4_hint(lo, make_uint4(pl[0], pl[1], pl[2], pl[3]), st_policy);
                         else *reinterpret_cast<uint4*>(lo) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                     }
                     if (LB2_L2_HINTS)
-                        st_global_v4_hint(out + ((size_t)c8 * chunk_rows + out_row) * 8, make_uint4(pk[0], pk[1], pk[2], pk[3]), st_policy);
+                        st_global_v4_hint(out + (size_t)row_off(c8, out_row) * 8, make_uint4(pk[0], pk[1], pk[2], pk[3]), st_policy);
                     else
-                        *reinterpret_cast<uint4*>(out + ((size_t)c8 * chunk_rows + out_row) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4*>(out + (size_t)row_off(c8, out_row) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
             };
             // Lite mode (kOutFp8): 16 channels (column blocks cc, cc + 8) of one row half. Besides the two fp16 chunk rows
@@ -749,14 +777,14 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                     qa[2 * g] = valid ? (q8[0] | (q8[1] << 16)) : 0u; qa[2 * g + 1] = valid ? (q8[2] | (q8[3] << 16)) : 0u;
                     ql[2 * g] = valid ? (q9[0] | (q9[1] << 16)) : 0u; ql[2 * g + 1] = valid ? (q9[2] | (q9[3] << 16)) : 0u;
                     if (!skip) {
-                        __half* ph = out + ((size_t)((col0 + cc) / 8 + g) * chunk_rows + out_row) * 8;
+                        __half* ph = out + (size_t)row_off(((col0 + cc) >> 3) + g, out_row) * 8;
                         if (LB2_L2_HINTS) st_global_v4_hint(ph, make_uint4(pk[0], pk[1], pk[2], pk[3]), st_policy);
                         else *reinterpret_cast<uint4*>(ph) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
                 }
                 if (!skip) {
-                    __half* pa = out + ((size_t)(lo_chunks + 2 * ((col0 + cc) >> 4)) * chunk_rows + out_row) * 8;
-                    __half* pl = pa + (size_t)chunk_rows * 8;
+                    __half* pa = out + (size_t)row_off(lo_chunks + 2 * ((col0 + cc) >> 4), out_row) * 8;
+                    __half* pl = pa + (size_t)(uint32_t)chunk_rows * 8;
                     if (LB2_L2_HINTS) {
                         st_global_v4_hint(pa, make_uint4(qa[0], qa[1], qa[2], qa[3]), st_policy);
                         st_global_v4_hint(pl, make_uint4(ql[0], ql[1], ql[2], ql[3]), st_policy);
@@ -819,11 +847,16 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                         taps(rb, k + 1);
                         tmem_ld_wait();
                     }
-                    float* zb = zbuf + (size_t)(J.zparts + part) * 9 * chunk_rows;
+                    const int zp = (J.zparts + part) * 9;
 #pragma unroll
-                    for (int t = 0; t < 9; t++) {
-                        zb[(size_t)t * chunk_rows + out_row2[0]] = valid2[0] ? z0[t] : 0.0f;
-                        zb[(size_t)t * chunk_rows + out_row2[1]] = valid2[1] ? z1[t] : 0.0f;
+                    for (int t = 0; t < 9; t++) {   // (kept in L2 for the heads kernel like the activations: next to evict_last lines, plain ones go first)
+                        if (LB2_L2_HINTS) {
+                            st_global_f32_hint(zbuf + row_off(zp + t, out_row2[0]), valid2[0] ? z0[t] : 0.0f, st_policy);
+                            st_global_f32_hint(zbuf + row_off(zp + t, out_row2[1]), valid2[1] ? z1[t] : 0.0f, st_policy);
+                        } else {
+                            zbuf[row_off(zp + t, out_row2[0])] = valid2[0] ? z0[t] : 0.0f;
+                            zbuf[row_off(zp + t, out_row2[1])] = valid2[1] ? z1[t] : 0.0f;
+                        }
                     }
                 }
             } else if (kFp8 && out_mode == kOutFp8) {

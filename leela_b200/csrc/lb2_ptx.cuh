@@ -96,6 +96,18 @@ __device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32
         : "memory");
 }
 
+// the peer CTA's own "my bytes are on their way" arrive on the leader's stage barrier: arrival + transaction count in one
+// (relaxed: the signalling thread publishes no memory of its own — the bytes are written by the TMA unit, whose complete_tx on
+// the same barrier makes them visible to whoever waits on it)
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t cta) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(p)), "r"(cta));
+    return ra;
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster_relaxed(uint32_t cluster_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch
 // A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (and run its
 // prologue) while its predecessor in the stream is still finishing; grid_dep_wait() blocks until the
@@ -189,6 +201,9 @@ __device__ __forceinline__ void st_global_v4_hint(void* ptr, uint4 v, uint64_t p
                  "r"(v.w), "l"(policy)
                  : "memory");
 }
+__device__ __forceinline__ void st_global_f32_hint(float* ptr, float v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(ptr), "f"(v), "l"(policy) : "memory");
+}
 
 // drop a 128-byte line from L2 without writing it back: its contents are undefined until written again (a weak write in
 // the memory model, so a later release orders it)
@@ -215,6 +230,21 @@ __device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const CUtensorM
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
         "r"(c2), "l"(policy)
+        : "memory");
+}
+// CTA-pair form: the destination is this CTA's shared memory, the mbarrier may live in either CTA of the pair (a
+// shared::cluster address) — the peer's loads complete on the LEADER's stage barrier without a forwarding hop
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair_hint(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1, int c2,
+                                                      uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
         : "memory");
 }
 // 1-D bulk copy global -> shared

@@ -725,15 +725,19 @@ def test_registered_host_buffers_and_queue_error_api(ev, ref_golden):
     assert buf.value == b""
 
 
-def test_submit_queue_single_position_load(ev, bench_positions):
-    """64 threads each submitting single positions back to back (what the search's threads do through
+@pytest.mark.parametrize("linger,n_threads", [(1, 64), (0, 64), (1, 6)])
+def test_submit_queue_single_position_load(ev, bench_positions, linger, n_threads):
+    """Threads each submitting single positions back to back (what the search's threads do through
     Network::get_value / async_scored_moves): every result equals the blocking call's, and the dispatcher coalesces —
-    the mean device batch is far above 1."""
+    the mean device batch is far above 1. With `queue_linger` a dispatcher lets requests accumulate while the device is
+    still computing the previous batch (also with a handful of threads, where two dispatchers can take the two slots of
+    an idle device at the same moment and must not wait for each other)."""
     import ctypes as C
     import threading
     from leela_b200 import capi
     b = bench_positions
-    n_threads, per = 64, 24
+    ev.set_option("queue_linger", linger)
+    per = 24
     n = n_threads * per
     idx = np.arange(n) % 1024
     want_v = ev.eval_value(b["value_planes"], b["rotation"])
@@ -762,8 +766,9 @@ def test_submit_queue_single_position_load(ev, bench_positions):
     assert np.array_equal(outs_v, want_v[idx])
     assert np.array_equal(outs_p, want_p)
     positions, batches = ev.get_option("stat_positions") - pos0, ev.get_option("stat_batches") - bat0
+    ev.set_option("queue_linger", 1)
     assert positions == n + n_threads
-    assert positions / batches >= 4, (positions, batches)
+    assert positions / batches >= (4 if n_threads >= 64 else 1.5), (positions, batches)
 
 
 def test_multi_device_dispatch_logic_on_one_gpu(ref_golden, bench_positions):

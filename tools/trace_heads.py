@@ -33,7 +33,7 @@ for generic in (1,):
         tr = ev.read_trace().astype(np.int64)
         trunk_start = tr[:, 95, 0].min(); trunk_end = tr[:, 95, 2].max()
         h = tr[:, 94, :9] - trunk_end
-        nv = 64
+        nv = 144   # value blocks: 16 groups of 16 positions x 9 slices of the inner-product matrix (the first 148 blocks are traced)
         val, pol = h[:nv], h[nv:]
         print(f"generic={generic} rep {rep}: trunk {1e-3 * (trunk_end - trunk_start):.1f} us; value blocks ({nv}) stamps rel. to trunk end, us:")
         for e in range(9):
