@@ -58,7 +58,10 @@ constexpr int kEpiGroup = LB2_EPI_GROUP;
                                  // through) instead of two
 #endif
 #ifndef LB2_CONSUMER_PROXY_FENCE
-#define LB2_CONSUMER_PROXY_FENCE 1   // producer: fence.proxy.async (MEMBAR.ALL.GPU) between seeing an item's dependencies and its TMA loads
+#define LB2_CONSUMER_PROXY_FENCE 1   // consumer-side fence.proxy.async (MEMBAR.ALL.GPU, ~0.8 us) between seeing an item's dependency flags and its
+                                     // TMA loads: 1 = in the producer, right before the loads; 2 = in the scout warp, right after the flag
+                                     // acquires and before it releases the item to the producer (off the load path: the scout runs items
+                                     // ahead); 0 = none (the writer's fence before its flag release already orders the proxies)
 #endif
 // LB2_LITE_SEPARATE_ACC (default 0, lb2_kernels.cuh): lite mode: 1 = the e4m3 correction terms accumulate in TMEM columns of their own (kCorrCols to the right,
                                   // c_out <= 64 only) and the epilogue adds the two sums; 0 = straight onto the fp16 sum. kind::f8f6f4
@@ -300,14 +303,22 @@ __device__ __forceinline__ uint32_t geom_pack(uint32_t k, const LayerJob* J) {
 //   resident:   [this CTA's half of the layer's weights][stages: A slab only][ctrl][bias][head weights][job table]
 // kOutModes: which LayerJob::out_mode values besides kOutPlain may occur in the launch (bit kOutLo16 - 1: precise, bit
 // kOutFp8 - 1: lite) — the epilogue's extra stores are compiled in only where a launch can need them.
+// Slots of the shared-memory stage ring a job uses. Streaming modes: all of them, at a fixed slot size. Resident-weights
+// mode: the slots hold activation slabs only and are packed at the job's own slab size — 6 slots of 304 rows for the 3x3
+// layers (halo 24), 5 of 352 rows for the 5x5 first layer (halo 48) in the same 58 KB. The sixth slot matters: a slot is
+// free only when its MMAs have COMPLETED, about two stages behind the issuer, so of five slots only three were ahead of it
+// and the first slab of every item arrived ~0.4 us late (1.7 us from issuing a load to the issuer seeing it).
+template <bool kRes, int kStages>
+__device__ __forceinline__ int ring_slots(int halo) { return kRes ? (halo <= kResHalo3 ? kStagesRes3 : kStagesRes) : kStages; }
+
 template <bool kPair, bool kRes, int kOutModes>
 __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_constant__ TrunkParams P) {
     static_assert(!kRes || kPair, "resident weights need CTA pairs");
     constexpr bool kLo16 = (kOutModes & 1) != 0, kFp8 = (kOutModes & 2) != 0;
-    constexpr int kStages = kRes ? kStagesRes : (kPair ? kStagesPair : kStagesSingle);
+    constexpr int kStages = kRes ? kStagesRes : (kPair ? kStagesPair : kStagesSingle);   // (kRes: see ring_slots)
     constexpr int kStageBytes = kRes ? kASlabBytes : (kPair ? kStageBytesPair : kStageBytesSingle);
     constexpr int kRingOff = kRes ? kResWeightBytes : 0;
-    constexpr int kCtrlOff = kRes ? kResWeightBytes + kStagesRes * kASlabBytes : kTrunkRingBytes;
+    constexpr int kCtrlOff = kRes ? kResWeightBytes + kResRingBytes : kTrunkRingBytes;
     constexpr int kJobSlots = kRes ? kResJobs : kMaxLaunchJobs;
     constexpr int kHeadW = kRes ? kResHeadSlots : kHeadSlots;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -339,7 +350,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 127u) __trap();  // TMA destinations need 128-byte alignment
         // pair mode: the leader's "stage full" barrier also counts the peer's "my half landed" arrive
-        for (int i = 0; i < kStages; i++) { mbar_init(full_bar + i, (kPair && leader) ? 2 : 1); mbar_init(empty_bar + i, 1); }
+        for (int i = 0; i < kMaxStages; i++) { mbar_init(full_bar + i, (kPair && leader) ? 2 : 1); mbar_init(empty_bar + i, 1); }
         for (int i = 0; i < 2; i++) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, kPair ? 2 * kEpilogueWarps : kEpilogueWarps); }
         for (int i = 0; i < kPubDepth; i++) mbar_init(pub_bar + i, kEpilogueWarps);
         *pub_done = 0;
@@ -387,9 +398,12 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        // The whole warp walks the item ring; one elected lane issues the copies. In pair mode each
-        // CTA loads the A slab of its own tile and its half of the output channels of the B block.
-        int stage = 0; uint32_t phase = 0; uint32_t pit = 0;
+        // One lane walks the item ring and issues the copies. In pair mode each CTA loads the A slab of its own tile and its
+        // half of the output channels of the B block. Ring slots carry their own phase parity (bit k of `pbits` = parity of
+        // slot k's next fill), so the number of slots in use may change from job to job (ring_slots).
+        if (lane == 0) {
+        int st = 0; uint32_t pbits = 0; uint32_t pit = 0;
+        int ring_n = 0;          // slots of the ring geometry in use (0: none yet)
         int resident_job = -1;   // kRes: the job whose weights (this CTA's half) are in shared memory
         const uint64_t ld_policy = LB2_L2_HINTS == 2 ? l2_policy_evict_last() : (LB2_L2_HINTS == 3 ? l2_policy_evict_first() : 0);
         const uint32_t leader_full0 = kPair ? mapa_u32(full_bar, 0) : 0u;   // the leader's full_bar[0] as a shared::cluster address
@@ -398,58 +412,53 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             const int tile = tile_of(idx);
             const int halo = J.halo, ksize = J.ksize, n_out = J.n_out, n_slabs = J.n_slabs, tmap = J.tmap, n_real = J.n_real_slabs;
             const int tb0 = J.term_base[0], tb1 = J.term_base[1], tb2 = J.term_base[2];
-            if (lane == 0) { LB2_TRACE(pit, 0); if (P.trace && pit < (uint32_t)kTraceItems) P.trace[((size_t)blockIdx.x * kTraceItems + pit) * kTraceEvents + 15] = (unsigned long long)((jj << 21) | idx); }
+            LB2_TRACE(pit, 0);
+            if (P.trace && pit < (uint32_t)kTraceItems) P.trace[((size_t)blockIdx.x * kTraceItems + pit) * kTraceEvents + 15] = (unsigned long long)((jj << 21) | idx);
             // the scout warp polls the dependency flags ahead of us; wait for its go-ahead
             while (ld_acquire_cta_shared(deps_ready) <= pit) {}
-            __syncwarp();
             const int rows_halo = kTileRows + 2 * halo;
             const uint32_t a_bytes = rows_halo * 32;
             const int row0_8 = (tile * kTileRows - halo) / 8;  // exact: both multiples of 8
             const int ng = n_tap_groups(ksize);
             const int n_mine = kPair ? (n_out >> 1) : n_out;   // output channels whose weights this CTA stages
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(kPair ? J.wpk2 : J.wpk);
+            const int rn = ring_slots<kRes, kStages>(halo);
+            const uint32_t sbytes = kRes ? a_bytes : (uint32_t)kStageBytes;   // kRes: slots are packed at the job's own slab size
             // kRes: a new job's weights replace the resident ones unit by unit (unit = the taps of one
             // stage), each riding on its stage's barrier. Overwriting unit u is safe once the MMAs that
-            // read the bytes under it are done: for a job of the same geometry with at least kStages
-            // stages that is implied by owning the stage's ring slot (the old unit u was last read
-            // n_stages >= kStages stages ago); otherwise drain the pipeline first.
+            // read the bytes under it are done: for a job of the same geometry with at least as many stages as the ring has
+            // slots that is implied by owning the stage's ring slot (the old unit u was last read a whole ring ago); otherwise
+            // — and whenever the ring's slot size changes — drain the pipeline first.
             const bool reload = kRes && jj != resident_job;
-            bool drain = false;
+            bool drain = ring_n != 0 && rn != ring_n;
             if (reload && resident_job >= 0) {
                 const LayerJob& O = jobs[resident_job];
-                drain = !(O.ksize == ksize && O.n_out == n_out && O.n_slabs == n_slabs && n_slabs * ng >= kStages);
+                drain |= !(O.ksize == ksize && O.n_out == n_out && O.n_slabs == n_slabs && n_slabs * ng >= rn);
             }
-            if (elect_one()) {
-                int st = stage; uint32_t ph = phase;  // private walk; all lanes advance the shared view below
-                LB2_TRACE(pit, 1);
-                if (LB2_CONSUMER_PROXY_FENCE) fence_proxy_async();  // order the TMA (async proxy) reads after the acquires above
-                if (drain) {
-                    for (int k = 0; k < kStages; k++) {   // the waits the next kStages stage fills would do, done now
-                        const int s2 = st + k;
-                        mbar_wait(empty_bar + s2 % kStages, (ph ^ (s2 >= kStages ? 1u : 0u)) ^ 1u);
-                    }
-                }
-                uint32_t unit_off = 0;   // kRes: byte offset of the stage's weights inside the resident area
-                int term = 0, ts = 0;    // virtual slab s = term * n_real + ts
-                // peer CTA, activations only: straight onto the leader's barrier (see LB2_PEER_DIRECT)
-                const bool direct = LB2_PEER_DIRECT && kRes && !leader && !reload;
-                for (int s = 0; s < n_slabs; s++) {
-                    for (int g = 0; g < ng; g++) {
-                        const uint32_t b_bytes = (tap_group_end(ksize, g) - tap_group_begin(g)) * n_mine * 32;
-                        mbar_wait(empty_bar + st, ph ^ 1);
-                        uint8_t* sa = ring + st * kStageBytes;
-                        const bool skip_b = (kDebugFlags(P) & 8) != 0 || (kRes && !reload), skip_a = (kDebugFlags(P) & 16) != 0;
-                        // split-operand modes: every term of the K loop has its own set of input chunk planes
-                        const int ac = (term == 0 ? tb0 : (term == 1 ? tb1 : tb2)) + 2 * ts;
-                        if (direct) {
-                            const uint32_t lbar = leader_full0 + 8u * (uint32_t)st;
-                            mbar_arrive_expect_tx_cluster_relaxed(lbar, a_bytes);
-                            if (LB2_L2_HINTS >= 2) tma_load_3d_pair_hint(sa, &P.tmaps[tmap], lbar, 0, row0_8, ac, ld_policy);
-                            else tma_load_3d_pair(sa, &P.tmaps[tmap], lbar, 0, row0_8, ac);
-                            if (++st == kStages) { st = 0; ph ^= 1; }
-                            if (s == 0 && g == 0) LB2_TRACE(pit, 2);
-                            continue;
-                        }
+            LB2_TRACE(pit, 1);
+            if (LB2_CONSUMER_PROXY_FENCE == 1) fence_proxy_async();  // order the TMA (async proxy) reads after the acquires above
+            if (drain)
+                for (int k = 0; k < ring_n; k++) mbar_wait(empty_bar + k, ((pbits >> k) & 1u) ^ 1u);   // the wait the slot's next fill would do, done now
+            if (rn != ring_n) { st = 0; ring_n = rn; }
+            uint32_t unit_off = 0;   // kRes: byte offset of the stage's weights inside the resident area
+            int term = 0, ts = 0;    // virtual slab s = term * n_real + ts
+            // peer CTA, activations only: straight onto the leader's barrier (see LB2_PEER_DIRECT)
+            const bool direct = LB2_PEER_DIRECT && kRes && !leader && !reload;
+            for (int s = 0; s < n_slabs; s++) {
+                for (int g = 0; g < ng; g++) {
+                    const uint32_t b_bytes = (tap_group_end(ksize, g) - tap_group_begin(g)) * n_mine * 32;
+                    mbar_wait(empty_bar + st, ((pbits >> st) & 1u) ^ 1u);
+                    pbits ^= 1u << st;
+                    uint8_t* sa = ring + st * sbytes;
+                    const bool skip_b = (kDebugFlags(P) & 8) != 0 || (kRes && !reload), skip_a = (kDebugFlags(P) & 16) != 0;
+                    // split-operand modes: every term of the K loop has its own set of input chunk planes
+                    const int ac = (term == 0 ? tb0 : (term == 1 ? tb1 : tb2)) + 2 * ts;
+                    if (direct) {
+                        const uint32_t lbar = leader_full0 + 8u * (uint32_t)st;
+                        mbar_arrive_expect_tx_cluster_relaxed(lbar, a_bytes);
+                        if (LB2_L2_HINTS >= 2) tma_load_3d_pair_hint(sa, &P.tmaps[tmap], lbar, 0, row0_8, ac, ld_policy);
+                        else tma_load_3d_pair(sa, &P.tmaps[tmap], lbar, 0, row0_8, ac);
+                    } else {
                         mbar_arrive_expect_tx(full_bar + st, (skip_a ? 0u : a_bytes) + (skip_b ? 0u : b_bytes));
                         if (!skip_a) {
                             if (LB2_L2_HINTS >= 2) tma_load_3d_hint(sa, &P.tmaps[tmap], full_bar + st, 0, row0_8, ac, ld_policy);
@@ -458,20 +467,15 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                         if (!skip_b) bulk_load_1d(kRes ? smem + unit_off : sa + kASlabBytes, wsrc + (kPair ? rank * b_bytes : 0u), b_bytes, full_bar + st);
                         wsrc += kPair ? 2 * b_bytes : b_bytes;
                         unit_off += b_bytes;
-                        if (++st == kStages) { st = 0; ph ^= 1; }
-                        if (s == 0 && g == 0) LB2_TRACE(pit, 2);
                     }
-                    if (++ts == n_real) { ts = 0; term++; }
+                    if (++st == rn) st = 0;
+                    if (s == 0 && g == 0) LB2_TRACE(pit, 2);
                 }
-                LB2_TRACE(pit, 3);
+                if (++ts == n_real) { ts = 0; term++; }
             }
+            LB2_TRACE(pit, 3);
             resident_job = jj;
-            // every lane tracks the ring position the elected lane advanced to
-            const int adv = n_slabs * ng;
-            stage += adv;
-            phase ^= (stage / kStages) & 1;
-            stage %= kStages;
-            __syncwarp();
+        }
         }
     } else if (warp == 1 && !leader) {
         // ================================ pair mode, peer CTA ==========================
@@ -481,17 +485,19 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
             // (with LB2_PEER_DIRECT only the stages of an item that brings a new job's weights use our own barriers: the parity
             // of each is kept per slot)
             int stage = 0; uint32_t parity = 0; uint32_t fit = 0;
-            int resident_job = -1;
+            int resident_job = -1, ring_n = 0;
             for (int jj, idx; item_get<true>(item_ring, fit, jj, idx); fit++) {
                 const int n_st = jobs[jj].n_slabs * n_tap_groups(jobs[jj].ksize);
+                const int rn = ring_slots<kRes, kStages>(jobs[jj].halo);
+                if (rn != ring_n) { stage = 0; ring_n = rn; }
                 const bool direct = LB2_PEER_DIRECT && kRes && jj == resident_job;
                 resident_job = jj;
-                if (direct) { stage = (stage + n_st) % kStages; continue; }
+                if (direct) { stage = (stage + n_st) % rn; continue; }
                 for (int s = 0; s < n_st; s++) {
                     mbar_wait(full_bar + stage, (parity >> stage) & 1u);
                     parity ^= 1u << stage;
                     if (LB2_RELAXED_FORWARD) mbar_arrive_remote_relaxed(full_bar + stage, 0); else mbar_arrive_remote(full_bar + stage, 0);
-                    if (++stage == kStages) stage = 0;
+                    if (++stage == rn) stage = 0;
                 }
             }
         }
@@ -503,8 +509,9 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
         // and the readiness of the NEXT stage is probed (non-blocking) in the middle of this
         // stage's MMAs, so both latencies hide behind queued tensor work.
         if (elect_one()) {
-            int stage = 0; uint32_t phase = 0; uint32_t it = 0;
-            bool next_ready = false;  // full_bar[stage] already observed complete for `phase`
+            int stage = 0; uint32_t cbits = 0; uint32_t it = 0;   // bit k of cbits: parity of ring slot k's next use
+            int ring_n = 0;
+            bool next_ready = false;  // full_bar[stage] already observed complete for its next use
             for (;; it++) {
                 uint32_t gw;
                 while (!item_peek(geom_ring, it, gw)) {}
@@ -530,17 +537,21 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                 const int ng = n_tap_groups(ksize);
                 const int pad = ksize >> 1;
                 const int n_st = n_slabs * ng;
+                const int rn = ring_slots<kRes, kStages>(halo);
+                const uint32_t sbytes = kRes ? (uint32_t)rows_halo * 32u : (uint32_t)kStageBytes;
+                if (rn != ring_n) { stage = 0; ring_n = rn; next_ready = false; }   // (the producer drained the ring before it changed the slot size)
                 uint32_t accumulate = 0;
                 int g = 0;
                 uint32_t res16 = 0;   // kRes: offset of the stage's weights in the resident area, in 16-byte units
                 for (int s = 0; s < n_st; s++) {
-                    if (!next_ready) mbar_wait(full_bar + stage, phase);
+                    if (!next_ready) mbar_wait(full_bar + stage, (cbits >> stage) & 1u);
+                    cbits ^= 1u << stage;
                     tc_fence_after_sync();
                     if (s == 0) LB2_TRACE(it, 6);
-                    int nstage = stage + 1; uint32_t nphase = phase;
-                    if (nstage == kStages) { nstage = 0; nphase ^= 1; }
+                    const int nstage = stage + 1 == rn ? 0 : stage + 1;
+                    const uint32_t nphase = (cbits >> nstage) & 1u;
                     if (LB2_PROBE_TAP < 0) next_ready = mbar_try_wait(full_bar + nstage, nphase);
-                    const uint32_t a_addr = smem_u32(ring + stage * kStageBytes);
+                    const uint32_t a_addr = smem_u32(ring + stage * sbytes);
                     // (address of row `halo` of the A slab) >> 4; a tap shifts it by dy*S+dx rows
                     const uint32_t a16 = (a_addr >> 4) + halo;
                     // B: behind the A slab of the stage, or (kRes) this stage's unit of the resident weights
@@ -593,7 +604,7 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                         if (++g == ng) g = 0;
                     }
                     umma_commit<kPair>(empty_bar + stage);  // frees the smem stage (in both CTAs) when these MMAs finish
-                    stage = nstage; phase = nphase;
+                    stage = nstage;
                 }
                 umma_commit<kPair>(tfull_bar + acc);  // accumulator complete -> epilogue (both CTAs)
                 LB2_TRACE(it, 7);
@@ -1046,7 +1057,10 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                 }
             }
             __syncwarp();
-            if (lane == 0) st_release_cta_shared(deps_ready, it + 1);
+            if (lane == 0) {
+                if (LB2_CONSUMER_PROXY_FENCE == 2) fence_proxy_async();   // flags acquired (all lanes, above) -> fence -> release to the producer
+                st_release_cta_shared(deps_ready, it + 1);
+            }
         }
     }
 

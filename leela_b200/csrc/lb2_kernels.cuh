@@ -51,10 +51,18 @@ static_assert(kTrunkSmemBytes <= 227 * 1024, "trunk kernel shared memory");
 // shared memory and re-uses it for every item of that layer it processes; the pipeline stages then
 // carry activation slabs only. Needs c_in <= 128 and c_out <= 128 (9 x 128 x 64 x 2 B = 147,456 B).
 constexpr int kResWeightBytes = 9 * 128 * 64 * 2;
-constexpr int kStagesRes = 5;
+constexpr int kStagesRes = 5;       // ring slots for jobs with the full halo (the 5x5 first layer): kASlabBytes each
+constexpr int kResHalo3 = 24;       // halo of the 3x3 layers in S = 20 space (20 + 1 -> 24)
+#ifndef LB2_RES_STAGES3
+#define LB2_RES_STAGES3 6
+#endif
+constexpr int kStagesRes3 = LB2_RES_STAGES3;   // ... and for the 3x3 layers: (256 + 2 * 24) rows x 32 B = 9,728 B each
+constexpr int kResRingBytes = (kStagesRes3 * (kTileRows + 2 * kResHalo3) * 32 > kStagesRes * kASlabBytes) ? kStagesRes3 * (kTileRows + 2 * kResHalo3) * 32
+                                                                                                          : kStagesRes * kASlabBytes;
+static_assert(kStagesRes3 <= kMaxStages && ((kTileRows + 2 * kResHalo3) * 32) % 128 == 0, "resident ring geometry");
 constexpr int kResJobs = 24;        // jobs per launch in this mode (no column splits)
 constexpr int kResHeadSlots = 2;    // one fused-head weight set per net
-constexpr int kTrunkSmemBytesRes = kResWeightBytes + kStagesRes * kASlabBytes + kCtrlBytes + kResJobs * 128 * 4 +
+constexpr int kTrunkSmemBytesRes = kResWeightBytes + kResRingBytes + kCtrlBytes + kResJobs * 128 * 4 +
                                    kResHeadSlots * 9 * 128 * 4 + kResJobs * 192;
 static_assert(kTrunkSmemBytesRes <= 227 * 1024, "resident-weights trunk shared memory");
 constexpr int kMaxLayers = 16;
