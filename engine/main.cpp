@@ -71,6 +71,7 @@ void usage() {
                  "      --check-planes      Build them both ways and abort on the first difference.\n"
                  "      --max-outstanding N Async policy requests per search thread (default 2).\n"
                  "      --batch N           Positions per device pass (default 256).\n"
+                 "      --queue-linger 0|1  lb2 option queue_linger (default 1: requests accumulate while the device computes).\n"
                  "      --precise           Split-operand evaluation (fp16 hi + lo): within 1e-4 of the fp32 nets, ~0.4x throughput.\n"
                  "      --dump-planes OUT N SEED  Dump feature planes of seeded self-play positions and exit.\n";
 }
@@ -168,7 +169,7 @@ void print_evaluator_stats() {
 
 int main(int argc, char* argv[]) {
     bool gtp_mode = false, noponder = false, playouts_set = false;
-    long batch = 0;
+    long batch = 0, linger = -1;
     bool precise = false, no_selftest = false;
     const char* dump_out = nullptr;
     int dump_n = 0;
@@ -217,6 +218,7 @@ int main(int argc, char* argv[]) {
         else if (a == "--max-outstanding") leela_b200::set_max_outstanding(atoi(value("--max-outstanding")));
         else if (a == "--batch") batch = atol(value("--batch"));
         else if (a == "--precise") precise = true;
+        else if (a == "--queue-linger") linger = atol(value("--queue-linger"));
         else if (a == "--dump-planes") {
             dump_out = value("--dump-planes");
             dump_n = atoi(value("--dump-planes N"));
@@ -251,6 +253,7 @@ int main(int argc, char* argv[]) {
         Network::get_Network();
 #ifndef LB2_REFERENCE_BUILD
         if ((batch > 0 && lb2_set_option(leela_b200::context(), "max_batch", batch)) ||
+            (linger >= 0 && lb2_set_option(leela_b200::context(), "queue_linger", linger)) ||
             (precise && lb2_set_option(leela_b200::context(), "precise", 1))) {
             myprintf("%s\n", lb2_last_error());
             return EXIT_FAILURE;

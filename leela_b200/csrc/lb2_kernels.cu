@@ -58,7 +58,7 @@ constexpr int kEpiGroup = LB2_EPI_GROUP;
                                  // through) instead of two
 #endif
 #ifndef LB2_CONSUMER_PROXY_FENCE
-#define LB2_CONSUMER_PROXY_FENCE 1   // consumer-side fence.proxy.async (MEMBAR.ALL.GPU, ~0.8 us) between seeing an item's dependency flags and its
+#define LB2_CONSUMER_PROXY_FENCE 2   // consumer-side fence.proxy.async (MEMBAR.ALL.GPU, ~0.8 us) between seeing an item's dependency flags and its
                                      // TMA loads: 1 = in the producer, right before the loads; 2 = in the scout warp, right after the flag
                                      // acquires and before it releases the item to the producer (off the load path: the scout runs items
                                      // ahead); 0 = none (the writer's fence before its flag release already orders the proxies)

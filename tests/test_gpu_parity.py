@@ -256,6 +256,37 @@ def test_wide_policy_net_192_vs_oracle(ref_golden, bench_positions):
         e.close()
 
 
+def test_value_net_other_shape_vs_oracle(ref_golden, bench_positions):
+    """A value net that is not NNValue — four 3x3 layers of 32 channels, hidden size 100 (a multiple of 4, not of 32) —
+    against the C oracle in full precision, at batch sizes that leave a ragged last group of 16 in the heads kernel
+    (1, 16, 17, 40 positions), and independent of the batch a position is in."""
+    from leela_b200 import capi, synth
+    from leela_b200.netdefs import Conv, InnerProduct
+    from oracle import oracle
+    convs = (Conv(5, 32, 32),) + (Conv(3, 32, 32),) * 3 + (Conv(3, 32, 1),)
+    ips = (InnerProduct(361, 100), InnerProduct(100, 1))
+    seed = 77
+    w = [synth.synth_weights(c.n_weights, seed, 2 * j, c.fan_in).reshape(c.c_out, c.c_in, c.k, c.k) for j, c in enumerate(convs)]
+    b = [synth.synth_biases(c.c_out, seed, 2 * j + 1) for j, c in enumerate(convs)]
+    ipw = [synth.synth_weights(361 * 100, seed, 40, 361).reshape(100, 361), synth.synth_weights(100, seed, 42, 100).reshape(1, 100)]
+    ipb = [synth.synth_biases(100, seed, 41), synth.synth_biases(1, seed, 43)]
+    net = synth.NetWeights(convs, w, b, ips, ipw, ipb)
+    onet = oracle.OracleNet(net)
+    planes, rot = bench_positions["value_planes"][:40], bench_positions["rotation"][:40]
+    want = oracle.value_forward(onet, planes, rot)
+    e = capi.Evaluator(value=net)
+    try:
+        e.set_option("value_precision", 2)
+        full = e.eval_value(planes, rot)
+        assert np.abs(full - want).max() < 2e-4
+        for n in (1, 16, 17):
+            np.testing.assert_array_equal(e.eval_value(planes[:n], rot[:n]), full[:n])
+        e.set_option("value_precision", 1)
+        assert np.abs(e.eval_value(planes, rot) - want).max() < 1e-3
+    finally:
+        e.close()
+
+
 def test_launch_modes_bit_identical(ev, ref_golden):
     """One launch per layer vs the single persistent dataflow launch: same arithmetic, same bits."""
     g = ref_golden

@@ -1,6 +1,9 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 500 python tools/ab_variants.py run 3 > gpurun_out/r2f_ab_variants.txt 2>&1; tail -5 gpurun_out/r2f_ab_variants.txt
-LB2_LIB=$PWD/tools/_variants/scoutfence.so timeout 120 python tools/trace_timeline.py 256 both > gpurun_out/r2f_timeline_scoutfence.txt 2>&1; mv gpurun_out/trace_both_256.npy gpurun_out/r2f_trace_scoutfence.npy; head -9 gpurun_out/r2f_timeline_scoutfence.txt
-LB2_LIB=$PWD/tools/_variants/scoutfence.so timeout 400 python -m pytest tests -m gpu -x -q -k "not engine" 2>&1 | tail -3
+for rep in 1 2 3; do for l in 0 1; do
+  timeout 120 python tools/engine_bench.py --seconds 3 --moves 2 --threads 16 --extra="--queue-linger $l" | python -c "
+import sys, json
+d = json.loads(sys.stdin.read()); print('linger', '$l', {k: d.get(k) for k in ('playouts_per_s_mean', 'mean_device_batch', 'nn_positions', 'rc')})"
+done; done 2>&1 | tee gpurun_out/r2h_engine_linger.txt
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "other_shape" 2>&1 | tail -3
