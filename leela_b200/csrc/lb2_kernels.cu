@@ -52,6 +52,11 @@ constexpr int kEpiGroup = LB2_EPI_GROUP;
                                  // producer adds its own arrival there — no local barrier, no forwarding thread in between
                                  // (the forward hop was ~0.4 us of the ~1.7 us from issuing a load to the MMA warp seeing it)
 #endif
+#ifndef LB2_RELOAD_FORWARD_RELEASE
+#define LB2_RELOAD_FORWARD_RELEASE 0   // 1: with LB2_PEER_DIRECT, the few stages that are still forwarded (a new job's weights: bulk copies cannot
+                                       // signal a remote mbarrier) use the formally ordered .release.cluster arrive. Measured: its fence sits on the
+                                       // critical path of every layer switch, trunk 377.5 -> 385.5 us (4 interleaved rounds). Off.
+#endif
 #ifndef LB2_EPI_PAIR_HALVES
 #define LB2_EPI_PAIR_HALVES 1    // ordinary epilogue: unit u = (half u & 1, column block u >> 1): the two units of a group share
                                  // their eight bias values — one shared-memory read (the port the tensor core's operands come
@@ -496,7 +501,10 @@ __global__ void __launch_bounds__(kTrunkThreads, 1) trunk_kernel(const __grid_co
                 for (int s = 0; s < n_st; s++) {
                     mbar_wait(full_bar + stage, (parity >> stage) & 1u);
                     parity ^= 1u << stage;
-                    if (LB2_RELAXED_FORWARD) mbar_arrive_remote_relaxed(full_bar + stage, 0); else mbar_arrive_remote(full_bar + stage, 0);
+                    // (resident mode with direct signalling: only the few stages that bring a new job's weights come through here —
+                    // they take the formally ordered .release.cluster arrive; the streaming modes forward every stage and keep the
+                    // relaxed one, see LB2_RELAXED_FORWARD)
+                    if (LB2_RELAXED_FORWARD && !(LB2_RELOAD_FORWARD_RELEASE && LB2_PEER_DIRECT && kRes)) mbar_arrive_remote_relaxed(full_bar + stage, 0); else mbar_arrive_remote(full_bar + stage, 0);
                     if (++stage == rn) stage = 0;
                 }
             }
