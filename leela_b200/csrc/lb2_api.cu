@@ -1430,6 +1430,7 @@ void worker_loop(lb2_ctx* ctx, int dev_index) {
         acquire_slot(ctx, dev_index, true, &dev, &slot);
         bool linger;
         { std::lock_guard<std::mutex> ol(ctx->opt_mu); linger = ctx->queue_linger != 0; }
+        cudaSetDevice(ctx->dev[dev]->id);   // (the slot may be another device's than this dispatcher's usual one)
         if (linger) linger_for_device(ctx, dev, slot);
         QueueBatch* b = nullptr;
         {
