@@ -26,7 +26,7 @@
 #define USE_SEARCH
 #define PROGRAM_NAME "Leela"
 #define PROGRAM_VERSION "0.11.0"
-#define MAX_CPUS 128
+#define MAX_CPUS 1024   // (only a clamp on --threads in the reference, GTP.cpp:67: search and netbench threads mostly sleep on their evaluation)
 
 #include <sys/time.h>
 #include <time.h>
