@@ -71,13 +71,15 @@ def queue(t):
 
 
 def options(t):
-    """flips run-time options under the other threads' feet: cached graphs must be rebuilt, results must not change"""
+    """flips run-time options under the other threads' feet: cached graphs must be rebuilt, the queue's dispatchers change
+    their batching policy, results must not change"""
     k = 0
     while time.time() < stop and not errors:
         time.sleep(0.05)
         ev.set_option("use_graphs", k & 1); ev.set_option("small_batch", 48 if k & 2 else 0); ev.set_option("resident_weights", 2 if k & 4 else 0)
+        ev.set_option("queue_linger", 0 if k & 8 else 1)
         k += 1
-    ev.set_option("use_graphs", 1); ev.set_option("small_batch", 48); ev.set_option("resident_weights", 2)
+    ev.set_option("use_graphs", 1); ev.set_option("small_batch", 48); ev.set_option("resident_weights", 2); ev.set_option("queue_linger", 1)
 
 
 counts += [0] * 10
