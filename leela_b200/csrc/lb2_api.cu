@@ -1368,7 +1368,7 @@ int eval_host_on_slot(lb2_ctx* ctx, int dev, int slot, const uint32_t* pol, cons
 // asynchronous submission: requests of many threads packed into device batches
 // --------------------------------------------------------------------------------------------
 // A submitter appends its planes straight into the pinned buffer of the open batch of its kind (one short critical
-// section: reserve + 1.4 KB copy per position); kIoSlots dispatcher threads per device take whatever has accumulated
+// section: reserve + 1.4 KB copy per position); kDispatchersPerDevice dispatcher threads per device take whatever has accumulated
 // as soon as they are free (so the batch size follows the load), evaluate it as ONE device batch on their device
 // (eval_host with the pinned buffers: no second staging copy) and hand the results out.
 QueueBatch* new_queue_batch(lb2_ctx* ctx) {
@@ -1394,7 +1394,8 @@ QueueBatch* new_queue_batch(lb2_ctx* ctx) {
 // (12 chained layers), so carrying off the two or three requests that have arrived so far would only put a second
 // latency-bound pass behind the first. Let them accumulate until the running pass is done (ev_done: its kernels, not its
 // copy down) or a full batch is waiting; the copy up and the launch of the new batch then overlap the old one's copy down
-// and callbacks. (16 submitting threads: 46 k -> requests/s, see profiles/r2_queue_linger.json.)
+// and callbacks. (One request outstanding per thread, one B200: 16 threads 46 k -> 58 k requests/s, 64 threads 163 k -> 201 k,
+// 128 threads 278 k -> 371 k: profiles/r2_queue_n1.json against r2_queue_n1_nolinger.json.)
 void linger_for_device(lb2_ctx* ctx, int dev, int slot) {
     static_assert(kIoSlots == 2, "the other slot");
     IoSlot& mine = ctx->dev[dev]->slots[slot];
