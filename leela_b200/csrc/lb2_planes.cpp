@@ -338,6 +338,50 @@ struct Board {
         return n_lib;
     }
 
+    // The planes ask for the liberties-after-a-move of BOTH colours at every empty point: one scan of the four neighbours serves
+    // both. Same answers as after_liberties(c, v, cap) for c = BLACK, WHITE (cap <= kLibList).
+    void after_liberties_both(int v, int cap, int out[2]) const {
+        int nb_sq[4], nb_g[4], nb_l[4], n_empty = 0;
+        for (int k = 0; k < 4; k++) {
+            const int a = v + kDirs[k];
+            nb_sq[k] = sq[a];
+            nb_g[k] = sq[a] <= WHITE ? group[a] : -1;
+            nb_l[k] = nb_g[k] >= 0 ? libs[nb_g[k]] : kFar;
+            n_empty += sq[a] == EMPTY;
+        }
+        for (int c = 0; c < 2; c++) {
+            int n_friends = 0, n_cap = 0;
+            bool big = false, live_friend = false;
+            for (int k = 0; k < 4; k++) {
+                if (nb_sq[k] == c) { n_friends++; big |= nb_l[k] > cap; live_friend |= nb_l[k] > 1; }
+                else if (nb_sq[k] == (c ^ 1)) n_cap += nb_l[k] == 1;
+            }
+            if (!n_empty && !live_friend && !n_cap) { out[c] = 0; continue; }      // is_suicide
+            if (big) { out[c] = cap; continue; }
+            if (!n_friends && !n_cap) { out[c] = std::min(n_empty, cap); continue; }
+            if (n_cap) { out[c] = after_liberties(c, v, cap); continue; }           // captures: the flood fill
+            int pts[4 + 4 * kLibList], n = 0;
+            auto add = [&](int q) {
+                if (q == v) return;
+                for (int i = 0; i < n; i++) if (pts[i] == q) return;
+                pts[n++] = q;
+            };
+            int seen_g[4], n_seen = 0;
+            for (int k = 0; k < 4; k++) {
+                if (nb_sq[k] == EMPTY) add(v + kDirs[k]);
+                else if (nb_sq[k] == c) {
+                    const int g = nb_g[k];
+                    bool dup = false;
+                    for (int i = 0; i < n_seen; i++) dup |= seen_g[i] == g;
+                    if (dup) continue;
+                    seen_g[n_seen++] = g;
+                    for (int i = 0; i < nb_l[k]; i++) add(lib_pts[g][i]);
+                }
+            }
+            out[c] = std::min(n, cap);
+        }
+    }
+
     // minimum_elib_count (FastBoard.cpp:2429-2443)
     int minimum_enemy_libs(int c, int v) const {
         int m = 100;
@@ -514,8 +558,10 @@ extern "C" int lb2_planes_from_position(const uint8_t* stones, int white_to_move
         if (p.sq != EMPTY) {
             p.libs = b.libs[b.group[v]];
         } else {
-            p.after_own = (int16_t)b.after_liberties(c, v, 6);
-            p.after_opp = (int16_t)b.after_liberties(!c, v, 6);
+            int after[2];
+            b.after_liberties_both(v, 6, after);
+            p.after_own = (int16_t)after[c];
+            p.after_opp = (int16_t)after[!c];
             p.ladder = b.empty_neighbours(v) == 2 && b.saves_something(c, v) && b.losing_ladder(c, v);
             p.ladder_win = b.winning_ladder(c, v);
         }
