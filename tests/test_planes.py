@@ -71,3 +71,47 @@ def test_bad_arguments_are_rejected():
     assert e.value.code == -1
     with pytest.raises(capi.Lb2Error):
         capi.planes_from_position(np.zeros(361, np.uint8), 0, ko_point=361)
+
+
+def _sym_index(s):
+    """where board point idx lands under symmetry s of the square (bit 2: transpose, bit 0: flip y, bit 1: flip x)"""
+    out = np.empty(361, np.int64)
+    for idx in range(361):
+        x, y = idx % 19, idx // 19
+        if s & 4: x, y = y, x
+        if s & 1: y = 18 - y
+        if s & 2: x = 18 - x
+        out[idx] = y * 19 + x
+    return out
+
+
+@needs_engine
+def test_planes_commute_with_board_symmetries_and_colour_swap(tmp_path):
+    """Size-independent properties of the path: liberties, liberties after a move and both ladder readers do not know
+    directions or colours. (1) Mapping a position through any of the 8 symmetries of the board permutes its planes the same
+    way (the third-line plane is symmetric itself). (2) Swapping the colours of all stones AND the side to move leaves every
+    plane where it is, except the white-has-komi plane, which follows the white stones."""
+    out = str(tmp_path / "p.pos")
+    subprocess.run([ENGINE, "-q", "--dump-planes", out, "400", "4242"], check=True, timeout=600)
+    raw = fileio.read_raw_positions(out + ".raw")
+    komi_plane_p, komi_plane_v = 1 << 30, 1 << 29
+    checked_ladders = 0
+    for i in range(0, 400, 2):
+        st, tm, ko, last, prev, komi = raw.stones[i], int(raw.to_move[i]), int(raw.ko[i]), int(raw.last[i]), int(raw.prev[i]), float(raw.komi[i])
+        pol, val = capi.planes_from_position(st, tm, ko, last, prev, komi)
+        checked_ladders += int(((pol >> 25) & 3).any())
+        for s in (1, 2, 4, 7, 5):
+            to = _sym_index(s)
+            st2 = np.zeros_like(st); st2[to] = st
+            mv = lambda v: int(to[v]) if v >= 0 else v
+            pol2, val2 = capi.planes_from_position(st2, tm, mv(ko), mv(last), mv(prev), komi)
+            want_p = np.zeros_like(pol); want_p[to] = pol
+            want_v = np.zeros_like(val); want_v[to] = val
+            assert np.array_equal(pol2, want_p) and np.array_equal(val2, want_v), (i, s)
+        swapped = np.where(st == 1, 2, np.where(st == 2, 1, 0)).astype(st.dtype)
+        pol3, val3 = capi.planes_from_position(swapped, 1 - tm, ko, last, prev, komi)
+        assert np.array_equal(pol3 & ~np.uint32(komi_plane_p), pol & ~np.uint32(komi_plane_p)), i
+        assert np.array_equal(val3 & ~np.uint32(komi_plane_v), val & ~np.uint32(komi_plane_v)), i
+        if abs(komi) > 0.75:
+            assert np.array_equal((pol3 & komi_plane_p) != 0, swapped == 2) and np.array_equal((val3 & komi_plane_v) != 0, swapped == 2)
+    assert checked_ladders > 20   # the sample has positions where the ladder readers fire
