@@ -2,5 +2,4 @@
 # scratch: whatever the current GPU call needs (every step under its own timeout)
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 300 python tools/modes_time.py 2>&1 | tail -6
