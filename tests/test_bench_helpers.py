@@ -50,3 +50,13 @@ def test_relaunch_forwards_every_measurement_flag():
     for flag in ("--steps", "--warmup", "--batch", "--e2e-threads", "--flush-l2", "--no-cpu", "--precise", "--no-graphs",
                  "--policy-precision", "--value-precision", "--opt"):
         assert flag in relaunch, flag
+
+
+def test_trunk_model_agrees_with_the_executed_work_accounting():
+    """tools/trunk_model.py derives the issued MMA work from the layer shapes; bench.py's `roofline.executed` must be the same figure"""
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "trunk_model.py"), "--measured-us", "369"], capture_output=True, text=True, check=True).stdout
+    m = re.search(r"executed \(issued\) ([\d.]+) G bf16-equivalent = x([\d.]+)", out)
+    assert m, out
+    assert abs(float(m.group(1)) * 1e9 - bench.executed_trunk_flops((0, 1), 256)) / bench.executed_trunk_flops((0, 1), 256) < 1e-3
+    assert re.search(r"0\.8\d of the formulation bound", out), out
