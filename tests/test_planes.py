@@ -115,3 +115,37 @@ def test_planes_commute_with_board_symmetries_and_colour_swap(tmp_path):
         if abs(komi) > 0.75:
             assert np.array_equal((pol3 & komi_plane_p) != 0, swapped == 2) and np.array_equal((val3 & komi_plane_v) != 0, swapped == 2)
     assert checked_ladders > 20   # the sample has positions where the ladder readers fire
+
+
+def test_random_boards_satisfy_the_plane_invariants():
+    """Arbitrary stone patterns through the C ABI — including ones no game reaches (strings without liberties, full boards):
+    the builder must return (bounded ladder reads, no out-of-range string ids) and its planes must be well-formed: every point
+    is exactly one of empty / own / opponent, a stone carries at most one liberty-count plane of its own side, and the
+    after-a-move and ladder planes only ever sit on empty points."""
+    rng = np.random.default_rng(2026)
+    t0 = __import__("time").time()
+    for trial in range(300):
+        density = rng.uniform(0.05, 0.98)
+        r = rng.random(361)
+        st = np.where(r < density / 2, 1, np.where(r < density, 2, 0)).astype(np.uint8)
+        tm = int(rng.integers(0, 2))
+        empties = np.flatnonzero(st == 0)
+        ko = int(rng.choice(empties)) if len(empties) and rng.random() < 0.3 else -1
+        stones = np.flatnonzero(st != 0)
+        last = int(rng.choice(stones)) if len(stones) and rng.random() < 0.8 else -1
+        prev = int(rng.choice(stones)) if len(stones) and rng.random() < 0.8 else -1
+        pol, val = capi.planes_from_position(st, tm, ko, last, prev, float(rng.choice([0.5, 7.5, -7.5])))
+        own, opp = (1, 2) if tm == 0 else (2, 1)
+        for planes, libs_own, libs_opp, n_lib, after_lo, after_hi, ladders in ((pol, 3, 8, 5, 13, 24, (25, 26)), (val, 3, 9, 6, 15, 26, (27, 28))):
+            p = planes.astype(np.uint64)
+            assert np.array_equal((p >> 0) & 1, st == 0) and np.array_equal((p >> 1) & 1, st == own) and np.array_equal((p >> 2) & 1, st == opp)
+            own_bits = (p >> libs_own) & ((1 << n_lib) - 1)
+            opp_bits = (p >> libs_opp) & ((1 << n_lib) - 1)
+            popcount = lambda x: np.array([bin(int(v)).count("1") for v in x])
+            assert (popcount(own_bits)[st == own] <= 1).all() and (own_bits[st != own] == 0).all()
+            assert (popcount(opp_bits)[st == opp] <= 1).all() and (opp_bits[st != opp] == 0).all()
+            after = (p >> after_lo) & ((1 << (after_hi - after_lo + 1)) - 1)
+            assert (after[st != 0] == 0).all()
+            for b in ladders:
+                assert (((p >> b) & 1)[st != 0] == 0).all()
+    assert __import__("time").time() - t0 < 60
